@@ -1,0 +1,174 @@
+"""CPU: the oracle restatement reproduces the committed outputs of the real reference
+(tests/golden/*, produced by tools/make_golden.py from /root/reference)."""
+import importlib
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import PKG_NAME, load_golden, load_spec, t
+from oracle import airnet, detfill, freq, uformer
+
+synth = importlib.import_module(PKG_NAME + '.synth')
+
+
+def test_freq_cases():
+    g = load_golden('freq.npz')
+    meta = json.loads(str(g['meta']))
+    for n, (kind, size, xn, inv) in enumerate(meta):
+        y = freq.decompose(t(g[xn]), kind, size, inv)
+        ref = t(g[f'out{n}'])
+        assert y.shape == ref.shape, (kind, size)
+        tol = 1e-5 if inv is True else 2e-4          # spectra / abs are O(N^2) in magnitude
+        assert (y - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item()), (kind, size, inv)
+
+
+def test_partition_of_unity():
+    # the reference's only (commented) invariant: encoder_ViT.py:88, decoder_Uformer.py:268
+    x = torch.rand(2, 3, 64, 64)
+    for kind, size in (('frequency_decompose', 0.25), ('frequency_decompose_1', 0.5), ('frequency_decompose_dc', 0.5)):
+        assert (freq.decompose(x, kind, size).sum(0) - x).abs().max() < 1e-5
+
+
+def test_masks_hermitian_and_single_filter():
+    for kind, size, n in (('frequency_decompose', 0.25, 64), ('frequency_decompose_1', 0.5, 128)):
+        idx = freq.band_index_map(kind, size, n, n)
+        flipped = torch.roll(idx.flip(0, 1), (1, 1), (0, 1))
+        assert torch.equal(idx, flipped)
+        assert idx.min() >= 0
+    x = torch.rand(2, 4, 64, 64)
+    coef = torch.tensor([0.0, 0.3, -0.7])
+    y = freq.band_filter(x, 'frequency_decompose_1', 0.5, coef.view(3, 1, 1))
+    gain = 1 + coef[freq.band_index_map('frequency_decompose_1', 0.5, 64, 64)]
+    y2 = torch.fft.irfft2(torch.fft.rfft2(x) * gain[:, :33], s=(64, 64))
+    assert (y - y2).abs().max() < 1e-5
+
+
+def _state(spec_name):
+    return detfill.make_state(load_spec(spec_name))
+
+
+def test_airnet_uformer_eval():
+    g = load_golden('airnet_uu_eval.npz')
+    sd = _state('spec_airnet_uformer_uformer_L3.json')
+    xq, _, _ = synth.noisy_batch(2, 25)
+    with torch.no_grad():
+        y = airnet.airnet_uformer_forward(sd, xq[:1], xq[:1], training=False)
+        _, _, inter = uformer.encoder_forward(sd, 'E.E.encoder_q.', xq[:1])
+    assert (torch.stack(inter) - t(g['inter'])).abs().max() < 2e-4
+    assert (y - t(g['restored'])).abs().max() < 2e-4
+
+
+def test_airnet_uformer_train_step():
+    g = load_golden('airnet_uu_train.npz')
+    spec = load_spec('spec_airnet_uformer_uformer_L3.json')
+    sd = detfill.make_state(spec)
+    pnames = [k[len('E.E.encoder_q.'):] for k in sd if k.startswith('E.E.encoder_q.')
+              and not any(s in k for s in ('running_', 'num_batches', 'relative_position_index', 'mask_freq'))]
+    grads_on = [k for k in sd if sd[k].is_floating_point() and not k.startswith('E.E.encoder_k.')
+                and not any(s in k for s in ('running_', 'queue', 'mask_freq'))]
+    for k in grads_on:
+        sd[k].requires_grad_(True)
+    dp = {}
+    for k in g:
+        if k.startswith('dp/'):
+            _, blk, i = k.split('/')
+            dp.setdefault(blk, [None, None])[int(i)] = t(g[k])
+    xq, xk, clean = synth.noisy_batch(2, 25)
+    bn = {}
+    restored, logits, kout = airnet.airnet_uformer_forward(sd, xq, xk, True, dp=dp, bn_stats=bn, param_names=pnames)
+    assert (restored - t(g['restored'])).abs().max() < 5e-4
+    assert (torch.stack(logits) - t(g['logits'])).abs().max() < 5e-3
+    labels = torch.zeros(2, dtype=torch.long)
+    ce = sum(torch.nn.functional.cross_entropy(l, labels) for l in logits) / 3
+    l1 = (restored - clean).abs().mean()
+    loss = l1 + 0.6 * ce
+    assert abs(loss.item() - g['loss'][0]) < 1e-4
+    loss.backward()
+    checked = 0
+    for k in g:
+        if k.startswith('grad_head/'):
+            name = k[len('grad_head/'):]
+            gr = sd[name].grad.flatten()
+            ref = t(g[k])
+            scale = max(ref.abs().max().item(), 1e-6)
+            assert (gr[:256] - ref).abs().max().item() <= 2e-3 * scale + 1e-6, name
+            s = g['grad_sum/' + name]
+            assert abs(gr.abs().sum().item() - s[1]) <= 2e-3 * s[1] + 1e-6, name
+            checked += 1
+    assert checked > 20
+    # momentum-updated key encoder (moco.py:45-50)
+    for k in g:
+        if k.startswith('kparam/'):
+            assert (sd[k[len('kparam/'):]] - t(g[k])).abs().max() < 1e-6
+    # BatchNorm running statistics after one train forward (momentum 0.1, unbiased var)
+    for k in g:
+        if k.startswith('bn/') and k.endswith('running_mean'):
+            name = k[3:-len('.running_mean')]
+            m0 = detfill.det_tensor(name + '.running_mean', g[k].shape)
+            mean, var_u = bn[name]
+            assert (0.9 * m0 + 0.1 * mean - t(g[k])).abs().max() < 1e-4, name
+
+
+@pytest.mark.parametrize('method,L', [('all_DC', 3), ('all_2_bands', 2)])
+def test_decoder_variants(method, L):
+    g = load_golden(f'dec_{method}.npz')
+    sd = _state(f'spec_dec_{method}.json')
+    xq, _, _ = synth.noisy_batch(2, 25)
+    with torch.no_grad():
+        y = uformer.decoder_forward(sd, '', xq[:1], tuple(t(g['inter'])), method)
+    assert (y - t(g['restored'])).abs().max() < 2e-4
+
+
+def test_encoder_origin_msa():
+    g = load_golden('enc_origin_eval.npz')
+    sd = _state('spec_enc_origin.json')
+    xq, _, _ = synth.noisy_batch(2, 25)
+    with torch.no_grad():
+        _, out, inter = uformer.encoder_forward(sd, '', xq[:1], msa='origin')
+    assert (torch.stack(inter) - t(g['inter'])).abs().max() < 2e-4
+    assert (torch.stack(out) - t(g['out'])).abs().max() < 2e-4
+
+
+def test_resnet_encoder_and_dgrn():
+    g = load_golden('resnet_dgrn.npz')
+    se, sdg = _state('spec_resnet_encoder.json'), _state('spec_dgrn64.json')
+    xq, _, _ = synth.noisy_batch(2, 25)
+    x1 = xq[:1, :, :64, :64].contiguous()
+    with torch.no_grad():
+        fea, out, inter = airnet.resnet_encoder_forward(se, '', x1)
+        y = airnet.dgrn_forward(sdg, '', x1, inter)
+        tf, tout, _ = airnet.resnet_encoder_forward(se, '', xq, training=True)
+    assert (inter - t(g['inter'])).abs().max() < 1e-4
+    assert (out[0] - t(g['out'])).abs().max() < 1e-4
+    assert (tout[0] - t(g['train_out'])).abs().max() < 1e-4
+    # DCN: oracle restatement vs torchvision stand-in that produced the golden (parity unpinned upstream)
+    assert (y - t(g['restored'])).abs().max() < 5e-4
+
+
+def test_vit_encoder():
+    g = load_golden('vit_encoder.npz')
+    sd = _state('spec_vit_encoder_ed64.json')
+    xq, _, _ = synth.noisy_batch(2, 25)
+    with torch.no_grad():
+        fea, out, inter = airnet.vit_encoder_forward(sd, '', xq, 64, decompose_type='4_bands')
+    assert (fea - t(g['fea'])).abs().max() < 1e-4
+    assert (out[0] - t(g['out'])).abs().max() < 1e-4
+    assert (inter[:, :4, :8, :] - t(g['inter_head'])).abs().max() < 1e-4
+
+
+def test_dcn_known_answers():
+    # zero offsets & mask 0.5 == 0.5 * conv2d (deform_conv.py:52-54 zero-inits the offset conv)
+    x = torch.randn(1, 4, 9, 10)
+    w = torch.randn(5, 4, 3, 3)
+    off = torch.zeros(1, 18, 9, 10)
+    m = torch.full((1, 9, 9, 10), 0.5)
+    y = airnet.modulated_deform_conv2d(x, off, m, w)
+    assert (y - 0.5 * torch.nn.functional.conv2d(x, w, padding=1)).abs().max() < 1e-5
+    tv = pytest.importorskip('torchvision.ops')
+    off = torch.randn(1, 18, 9, 10) * 1.5
+    m = torch.rand(1, 9, 9, 10)
+    y = airnet.modulated_deform_conv2d(x, off, m, w)
+    y2 = tv.deform_conv2d(x, off, w, None, padding=1, mask=m)
+    assert (y - y2).abs().max() < 1e-4
