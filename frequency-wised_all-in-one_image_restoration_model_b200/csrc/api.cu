@@ -1,0 +1,98 @@
+// Library-level entry points: version, error string, launch counter, per-class in-stream timing.
+#include <stdarg.h>
+#include <vector>
+#include "freqair_internal.h"
+
+static thread_local char g_err[512] = "";
+static int g_prof_cls = 0;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+static int64_t g_launches = 0;
+
+void fa_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void fa_count_launch(int) { ++g_launches; }
+
+FaProfScope::FaProfScope(int cls_, cudaStream_t st_) : cls(cls_), st(st_), e0(nullptr), on(false) {
+  ++g_launches;
+  if (g_prof_cls != 0 && g_prof_cls == cls) {
+    on = true;
+    cudaEventCreate(&e0);
+    cudaEventRecord(e0, st);
+  }
+}
+FaProfScope::~FaProfScope() {
+  if (on) {
+    cudaEvent_t e1;
+    cudaEventCreate(&e1);
+    cudaEventRecord(e1, st);
+    g_prof_events.emplace_back(e0, e1);
+  }
+}
+
+extern "C" {
+
+const char* fa_version(void) { return "freqair 0.1 (sm_100a)"; }
+const char* fa_last_error_string(void) { return g_err; }
+
+int fa_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  FA_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  FA_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return FA_OK;
+}
+
+int fa_prof_begin(int kernel_class) {
+  for (auto& pr : g_prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  g_prof_events.clear();
+  g_prof_cls = kernel_class;
+  return FA_OK;
+}
+
+int fa_prof_end(double* total_ms, int64_t* launches) {
+  double tot = 0.0;
+  for (auto& pr : g_prof_events) {
+    cudaEventSynchronize(pr.second);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, pr.first, pr.second);
+    tot += ms;
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = (int64_t)g_prof_events.size();
+  g_prof_events.clear();
+  g_prof_cls = 0;
+  return FA_OK;
+}
+
+int64_t fa_launch_count(void) { return g_launches; }
+void fa_launch_count_reset(void) { g_launches = 0; }
+
+int fa_gemm(const float* A, const float* B, float* C, int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc,
+            int transA, int transB, const FaGemmEpilogue* epi, int backend, fa_stream_t stream) {
+  FA_REQUIRE(A && B && C, "fa_gemm: null operand");
+  FA_REQUIRE(M >= 0 && N >= 0 && K >= 0, "fa_gemm: negative dimension");
+  FA_REQUIRE(backend >= 0 && backend <= 2, "fa_gemm: backend must be 0, 1 or 2");
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_GEMM, st);
+  if (backend != 1) {
+    int rc = fa_gemm_tc_launch(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, epi, st, false);
+    if (rc != FA_ERR_UNSUPPORTED) return rc;
+    if (backend == 2) {
+      fa_set_error("fa_gemm: shape M=%d N=%d K=%d tA=%d tB=%d not eligible for the tcgen05 path", M, N, K, transA, transB);
+      return FA_ERR_UNSUPPORTED;
+    }
+  }
+  return fa_gemm_simt_launch(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, epi, st);
+}
+
+}  // extern "C"

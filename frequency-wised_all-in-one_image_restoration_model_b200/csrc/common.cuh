@@ -1,0 +1,103 @@
+// Shared helpers for the freqair sm_100a kernels (device + host side of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#define FA_OK 0
+#define FA_ERR_ARG 1
+#define FA_ERR_CUDA 2
+#define FA_ERR_UNSUPPORTED 3
+
+void fa_set_error(const char* fmt, ...);
+
+#define FA_REQUIRE(cond, ...)                                   \
+  do {                                                          \
+    if (!(cond)) {                                              \
+      fa_set_error(__VA_ARGS__);                                \
+      return FA_ERR_ARG;                                        \
+    }                                                           \
+  } while (0)
+
+#define FA_LAUNCH_CHECK(name)                                              \
+  do {                                                                     \
+    cudaError_t e__ = cudaGetLastError();                                  \
+    if (e__ != cudaSuccess) {                                              \
+      fa_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+      return FA_ERR_CUDA;                                                  \
+    }                                                                      \
+  } while (0)
+
+#define FA_CUDA(call)                                                         \
+  do {                                                                        \
+    cudaError_t e__ = (call);                                                 \
+    if (e__ != cudaSuccess) {                                                 \
+      fa_set_error("%s failed: %s", #call, cudaGetErrorString(e__));          \
+      return FA_ERR_CUDA;                                                     \
+    }                                                                         \
+  } while (0)
+
+// ---- optional in-stream timing of one kernel class (bench.py roofline leg) ----
+// Each public launcher names its class; when profiling of that class is on, the
+// launcher brackets the launch with events on the launching stream.
+enum FaKernelClass {
+  FA_K_NONE = 0,
+  FA_K_GEMM = 1,
+  FA_K_WIN_ATTN = 2,
+  FA_K_JOINT_ATTN = 3,
+  FA_K_BAND_FILTER = 4,
+  FA_K_LAYERNORM = 5,
+  FA_K_DWCONV = 6,
+  FA_K_IM2COL = 7,
+  FA_K_BN = 8,
+  FA_K_OPTIM = 9,
+  FA_K_DCN = 10,
+  FA_K_ELEMWISE = 11,
+  FA_K_COUNT = 12
+};
+struct FaProfScope {
+  int cls; cudaStream_t st; cudaEvent_t e0; bool on;
+  FaProfScope(int cls_, cudaStream_t st_);
+  ~FaProfScope();
+};
+void fa_count_launch(int cls);
+
+#ifdef __CUDACC__
+constexpr int kNumSMs = 148;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// activations shared by GEMM epilogues / conv kernels
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_LRELU = 2, ACT_SIGMOID = 3 };
+
+__device__ __forceinline__ float gelu_f(float x) {           // exact erf GELU (nn.GELU default)
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+__device__ __forceinline__ float act_f(float x, int act, float p) {
+  if (act == ACT_GELU) return gelu_f(x);
+  if (act == ACT_LRELU) return x > 0.f ? x : x * p;
+  if (act == ACT_SIGMOID) return 1.0f / (1.0f + __expf(-x));
+  return x;
+}
+__device__ __forceinline__ float act_grad_f(float x, int act, float p) {   // d act / d x at pre-activation x
+  if (act == ACT_GELU) return gelu_grad_f(x);
+  if (act == ACT_LRELU) return x > 0.f ? 1.0f : p;
+  if (act == ACT_SIGMOID) { float s = 1.0f / (1.0f + __expf(-x)); return s * (1.0f - s); }
+  return 1.0f;
+}
+#endif

@@ -1,0 +1,359 @@
+// LayerNorm (tokens) and BatchNorm2d(+LeakyReLU+avgpool) on [B,C,S]; column sums for bias gradients.
+// HBM-bound kernels: one pass over the activations per call, 128-bit accesses where the row length allows,
+// grids sized in multiples of the SM count.
+#include "freqair_internal.h"
+
+namespace {
+
+// ---------------------------------------------------------------- LayerNorm
+template <int MAXJ>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, float* __restrict__ y,
+                                                     float* __restrict__ mean, float* __restrict__ rstd, int64_t rows,
+                                                     int C) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float invC = 1.0f / (float)C;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const float* xr = x + r * C;
+    float v[MAXJ];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      int c = j * 32 + lane;
+      v[j] = (c < C) ? xr[c] : 0.f;
+      s += v[j];
+    }
+    const float mu = warp_sum(s) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      int c = j * 32 + lane;
+      float d = (c < C) ? v[j] - mu : 0.f;
+      q += d * d;
+    }
+    const float rs = rsqrtf(warp_sum(q) * invC + 1e-5f);
+    float* yr = y + r * C;
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      int c = j * 32 + lane;
+      if (c < C) {
+        float xh = (v[j] - mu) * rs;
+        yr[c] = gamma ? xh * gamma[c] + (beta ? beta[c] : 0.f) : xh;
+      }
+    }
+    if (lane == 0) {
+      if (mean) mean[r] = mu;
+      if (rstd) rstd[r] = rs;
+    }
+  }
+}
+
+template <int MAXJ>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                     const float* __restrict__ gamma, const float* __restrict__ dres,
+                                                     float* __restrict__ dx, float* __restrict__ dgamma,
+                                                     float* __restrict__ dbeta, int64_t rows, int C) {
+  extern __shared__ float sm[];           // [2][C] block partials of dgamma / dbeta
+  float* sg = sm;
+  float* sb = sm + C;
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float invC = 1.0f / (float)C;
+  float ag[MAXJ], ab[MAXJ], gm[MAXJ];
+#pragma unroll
+  for (int j = 0; j < MAXJ; ++j) {
+    ag[j] = 0.f; ab[j] = 0.f;
+    int c = j * 32 + lane;
+    gm[j] = (gamma && c < C) ? gamma[c] : 1.0f;
+  }
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const float mu = mean[r], rs = rstd[r];
+    const float* xr = x + r * C;
+    const float* dr = dy + r * C;
+    float g[MAXJ], xh[MAXJ];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      int c = j * 32 + lane;
+      float d = (c < C) ? dr[c] : 0.f;
+      xh[j] = (c < C) ? (xr[c] - mu) * rs : 0.f;
+      g[j] = d * gm[j];
+      s1 += g[j];
+      s2 += g[j] * xh[j];
+      ag[j] += d * xh[j];
+      ab[j] += d;
+    }
+    const float a = warp_sum(s1) * invC, b = warp_sum(s2) * invC;
+    float* dxr = dx + r * C;
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      int c = j * 32 + lane;
+      if (c < C) {
+        float v = rs * (g[j] - a - xh[j] * b);
+        if (dres) v += dres[r * C + c];
+        dxr[c] = v;
+      }
+    }
+  }
+  if (dgamma || dbeta) {
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      int c = j * 32 + lane;
+      if (c < C) { atomicAdd(&sg[c], ag[j]); atomicAdd(&sb[c], ab[j]); }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (dgamma) atomicAdd(&dgamma[c], sg[c]);
+      if (dbeta) atomicAdd(&dbeta[c], sb[c]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- column sums
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, float* __restrict__ out, int M, int N,
+                                                     int64_t ld, const float* __restrict__ rowscale, int rps,
+                                                     int rows_per_block) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  const int m0 = blockIdx.y * rows_per_block;
+  const int m1 = min(M, m0 + rows_per_block);
+  float s = 0.f;
+  if (n < N) {
+    for (int m = m0 + ty; m < m1; m += 8) {
+      float v = X[(int64_t)m * ld + n];
+      if (rowscale) v *= rowscale[m / rps];
+      s += v;
+    }
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    atomicAdd(&out[n], t);
+  }
+}
+
+// ---------------------------------------------------------------- BatchNorm on [B,C,S]
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float t = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.f;
+  if (w == 0) t = warp_sum(t);
+  __syncthreads();
+  return t;       // valid in warp 0
+}
+
+constexpr int BN_CHUNK = 4096;
+
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, double* __restrict__ sums, int C,
+                                                       int64_t S, int chunks) {
+  __shared__ float sh[8];
+  const int64_t bc = blockIdx.x / chunks;
+  const int ch = blockIdx.x % chunks;
+  const int c = (int)(bc % C);
+  const int64_t s0 = (int64_t)ch * BN_CHUNK, s1 = min(S, s0 + BN_CHUNK);
+  const float* p = x + bc * S;
+  float a = 0.f, q = 0.f;
+  for (int64_t s = s0 + threadIdx.x; s < s1; s += blockDim.x) { float v = p[s]; a += v; q += v * v; }
+  a = block_sum(a, sh);
+  q = block_sum(q, sh);
+  if (threadIdx.x == 0) { atomicAdd(&sums[2 * c], (double)a); atomicAdd(&sums[2 * c + 1], (double)q); }
+}
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, float slope,
+                                                       float* __restrict__ y, float* __restrict__ pooled, int C,
+                                                       int64_t S) {
+  __shared__ float sh[8];
+  const int64_t bc = blockIdx.x;
+  const int c = (int)(bc % C);
+  const float sc = scale[c], sf = shift[c];
+  const float* p = x + bc * S;
+  float acc = 0.f;
+  for (int64_t s = threadIdx.x; s < S; s += blockDim.x) {
+    float z = p[s] * sc + sf;
+    z = z > 0.f ? z : z * slope;
+    if (y) y[bc * S + s] = z;
+    acc += z;
+  }
+  if (pooled) {
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) pooled[bc] = acc / (float)S;
+  }
+}
+
+// g = upstream * lrelu'(z); upstream = dy[b,c,s] if dy else dpooled[b,c]/S
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd,
+                                                            const float* __restrict__ scale,
+                                                            const float* __restrict__ shift, float slope,
+                                                            const float* __restrict__ dy,
+                                                            const float* __restrict__ dpooled, double* __restrict__ red,
+                                                            int C, int64_t S, int chunks) {
+  __shared__ float sh[8];
+  const int64_t bc = blockIdx.x / chunks;
+  const int ch = blockIdx.x % chunks;
+  const int c = (int)(bc % C);
+  const int64_t s0 = (int64_t)ch * BN_CHUNK, s1 = min(S, s0 + BN_CHUNK);
+  const float sc = scale[c], sf = shift[c], mu = mean[c], rs = rstd[c];
+  const float up = dpooled ? dpooled[bc] / (float)S : 0.f;
+  const float* p = x + bc * S;
+  float a = 0.f, q = 0.f;
+  for (int64_t s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+    float v = p[s];
+    float z = v * sc + sf;
+    float g = (dy ? dy[bc * S + s] : up) * (z > 0.f ? 1.0f : slope);
+    a += g;
+    q += g * (v - mu) * rs;
+  }
+  a = block_sum(a, sh);
+  q = block_sum(q, sh);
+  if (threadIdx.x == 0) { atomicAdd(&red[2 * c], (double)a); atomicAdd(&red[2 * c + 1], (double)q); }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd,
+                                                           const float* __restrict__ scale,
+                                                           const float* __restrict__ shift, float slope,
+                                                           const float* __restrict__ dy,
+                                                           const float* __restrict__ dpooled,
+                                                           const double* __restrict__ red, float* __restrict__ dx,
+                                                           int B, int C, int64_t S) {
+  const int64_t bc = blockIdx.x;
+  const int c = (int)(bc % C);
+  const float sc = scale[c], sf = shift[c], mu = mean[c], rs = rstd[c];
+  const float up = dpooled ? dpooled[bc] / (float)S : 0.f;
+  const double n = (double)B * (double)S;
+  const float r0 = red ? (float)(red[2 * c] / n) : 0.f;
+  const float r1 = red ? (float)(red[2 * c + 1] / n) : 0.f;
+  const float* p = x + bc * S;
+  for (int64_t s = threadIdx.x; s < S; s += blockDim.x) {
+    float v = p[s];
+    float z = v * sc + sf;
+    float g = (dy ? dy[bc * S + s] : up) * (z > 0.f ? 1.0f : slope);
+    float xh = (v - mu) * rs;
+    dx[bc * S + s] = sc * (g - r0 - xh * r1);
+  }
+}
+
+int ln_grid(int64_t rows) {
+  int64_t blocks = (rows + 7) / 8;
+  int64_t cap = (int64_t)kNumSMs * 8;
+  return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" {
+
+int fa_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                     int64_t rows, int C, fa_stream_t stream) {
+  FA_REQUIRE(x && y, "fa_layernorm_fwd: null pointer");
+  FA_REQUIRE(C >= 1 && C <= 1024, "fa_layernorm_fwd: C=%d unsupported (1..1024)", C);
+  if (rows == 0) return FA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_LAYERNORM, st);
+  const int grid = ln_grid(rows);
+  if (C <= 128) ln_fwd_kernel<4><<<grid, 256, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, C);
+  else if (C <= 256) ln_fwd_kernel<8><<<grid, 256, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, C);
+  else if (C <= 512) ln_fwd_kernel<16><<<grid, 256, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, C);
+  else ln_fwd_kernel<32><<<grid, 256, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, C);
+  FA_LAUNCH_CHECK("fa_layernorm_fwd");
+  return FA_OK;
+}
+
+int fa_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                     const float* dres, float* dx, float* dgamma, float* dbeta, int64_t rows, int C,
+                     fa_stream_t stream) {
+  FA_REQUIRE(dy && x && mean && rstd && dx, "fa_layernorm_bwd: null pointer");
+  FA_REQUIRE(C >= 1 && C <= 1024, "fa_layernorm_bwd: C=%d unsupported (1..1024)", C);
+  if (rows == 0) return FA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_LAYERNORM, st);
+  int grid = ln_grid(rows);
+  if (grid > 4 * kNumSMs) grid = 4 * kNumSMs;
+  const size_t smem = 2 * (size_t)C * sizeof(float);
+  if (C <= 128) ln_bwd_kernel<4><<<grid, 256, smem, st>>>(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, rows, C);
+  else if (C <= 256) ln_bwd_kernel<8><<<grid, 256, smem, st>>>(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, rows, C);
+  else if (C <= 512) ln_bwd_kernel<16><<<grid, 256, smem, st>>>(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, rows, C);
+  else ln_bwd_kernel<32><<<grid, 256, smem, st>>>(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, rows, C);
+  FA_LAUNCH_CHECK("fa_layernorm_bwd");
+  return FA_OK;
+}
+
+int fa_colsum(const float* X, float* out, int M, int N, int64_t ld, const float* rowscale, int rows_per_scale,
+              int accumulate, fa_stream_t stream) {
+  FA_REQUIRE(X && out, "fa_colsum: null pointer");
+  if (N <= 0) return FA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_ELEMWISE, st);
+  if (!accumulate) FA_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, st));
+  if (M <= 0) return FA_OK;
+  const int colblocks = (N + 31) / 32;
+  int rowblocks = (4 * kNumSMs + colblocks - 1) / colblocks;
+  int rpb = (M + rowblocks - 1) / rowblocks;
+  if (rpb < 64) rpb = 64;
+  rowblocks = (M + rpb - 1) / rpb;
+  colsum_kernel<<<dim3(colblocks, rowblocks), 256, 0, st>>>(X, out, M, N, ld, rowscale,
+                                                            rows_per_scale > 0 ? rows_per_scale : 1, rpb);
+  FA_LAUNCH_CHECK("fa_colsum");
+  return FA_OK;
+}
+
+int fa_bn_stats(const float* x, double* sums, int B, int C, int64_t S, fa_stream_t stream) {
+  FA_REQUIRE(x && sums && B > 0 && C > 0 && S > 0, "fa_bn_stats: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_BN, st);
+  const int chunks = (int)((S + BN_CHUNK - 1) / BN_CHUNK);
+  bn_stats_kernel<<<(unsigned)((int64_t)B * C * chunks), 256, 0, st>>>(x, sums, C, S, chunks);
+  FA_LAUNCH_CHECK("fa_bn_stats");
+  return FA_OK;
+}
+
+int fa_bn_apply(const float* x, const float* scale, const float* shift, float slope, float* y, float* pooled, int B,
+                int C, int64_t S, fa_stream_t stream) {
+  FA_REQUIRE(x && scale && shift && (y || pooled) && B > 0 && C > 0 && S > 0, "fa_bn_apply: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_BN, st);
+  bn_apply_kernel<<<(unsigned)((int64_t)B * C), 256, 0, st>>>(x, scale, shift, slope, y, pooled, C, S);
+  FA_LAUNCH_CHECK("fa_bn_apply");
+  return FA_OK;
+}
+
+int fa_bn_bwd_reduce(const float* x, const float* mean, const float* rstd, const float* scale, const float* shift,
+                     float slope, const float* dy, const float* dpooled, double* red, int B, int C, int64_t S,
+                     fa_stream_t stream) {
+  FA_REQUIRE(x && mean && rstd && scale && shift && red && (dy || dpooled), "fa_bn_bwd_reduce: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_BN, st);
+  const int chunks = (int)((S + BN_CHUNK - 1) / BN_CHUNK);
+  bn_bwd_reduce_kernel<<<(unsigned)((int64_t)B * C * chunks), 256, 0, st>>>(
+      x, mean, rstd, scale, shift, slope, dy, dpooled, red, C, S, chunks);
+  FA_LAUNCH_CHECK("fa_bn_bwd_reduce");
+  return FA_OK;
+}
+
+int fa_bn_bwd_apply(const float* x, const float* mean, const float* rstd, const float* scale, const float* shift,
+                    float slope, const float* dy, const float* dpooled, const double* red, float* dx, int B, int C,
+                    int64_t S, fa_stream_t stream) {
+  FA_REQUIRE(x && mean && rstd && scale && shift && dx && (dy || dpooled), "fa_bn_bwd_apply: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_BN, st);
+  bn_bwd_apply_kernel<<<(unsigned)((int64_t)B * C), 256, 0, st>>>(x, mean, rstd, scale, shift, slope, dy, dpooled,
+                                                                  red, dx, B, C, S);
+  FA_LAUNCH_CHECK("fa_bn_bwd_apply");
+  return FA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,423 @@
+// K2 (decoder form) - LeWin window multi-head self-attention with the frequency-band re-weighting of the
+// post-softmax attention map fused in.  One CTA (288 threads) per (image, window, head):
+//   gather the window's 64 tokens straight from image-order q / kv (cyclic shift folded into the index
+//   math, so roll + window_partition + window_reverse never touch HBM), S = scale*q.k^T + rel-pos bias
+//   + shift mask, softmax, P' = irfft2(rfft2(P)*(1+coef[band])) in shared memory (fft64.cuh), O = P'.V,
+//   scatter O back in image order.  The 64x64 map never leaves the SM; HBM traffic is q,k,v,o only.
+// Backward recomputes P instead of saving 1.2 GB of maps: the filter is self-adjoint, d(coef) comes from
+// Parseval on the two half-spectra, and the relative-position-bias gradient is reduced in shared memory
+// across all windows a CTA visits before one flush of 225 atomics.
+#include "freqair_internal.h"
+#include "fft64.cuh"
+
+namespace {
+
+constexpr int NTHR = 288;
+constexpr int WIN = 8;
+constexpr int NTOK = 64;
+
+struct WinGeom {
+  int B, H, W, heads, shift, nWy, nWx;
+};
+
+// token row (b*H*W + y*W + x) of window position p, and its SW-MSA region label
+__device__ __forceinline__ void token_of(const WinGeom& g, int b, int wy, int wx, int p, int& row, int& label) {
+  const int sy = wy * WIN + (p >> 3), sx = wx * WIN + (p & 7);
+  int y = sy + g.shift, x = sx + g.shift;
+  if (y >= g.H) y -= g.H;
+  if (x >= g.W) x -= g.W;
+  row = (b * g.H + y) * g.W + x;
+  const int ry = sy < g.H - WIN ? 0 : (sy < g.H - g.shift ? 1 : 2);
+  const int rx = sx < g.W - WIN ? 0 : (sx < g.W - g.shift ? 1 : 2);
+  label = g.shift > 0 ? ry * 3 + rx : 0;
+}
+
+template <int HD>
+struct Smem {
+  static constexpr int HS = HD + 1;
+  float q[NTOK * HS];
+  float k[NTOK * HS];
+  float v[NTOK * HS];
+  float p[NTOK * fft64::PSTR];
+  float2 sp[NTOK * fft64::SPSTR];
+  float bias[232];
+  float coef[16];
+  int row[NTOK];
+  int label[NTOK];
+  uint8_t band[NTOK * 33 + 8];
+};
+
+template <int HD>
+__device__ __forceinline__ void load_tile(float* dst, const float* __restrict__ src, int64_t ld, int col0,
+                                          const int* rows, int tid) {
+  constexpr int HS = HD + 1;
+  constexpr int V4 = HD / 4;
+  for (int i = tid; i < NTOK * V4; i += NTHR) {
+    const int t = i / V4, d = (i % V4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(src + (int64_t)rows[t] * ld + col0 + d);
+    float* o = dst + t * HS + d;
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+}
+
+// S[i][j] for i = ty+16*ii, j = tx+16*jj  ->  out[i*PSTR + j] = scale*dot(A_i, B_j) (+ bias + mask)
+template <int HD, bool BIASMASK>
+__device__ __forceinline__ void tile_abt(const float* A, const float* Bm, float* out, float scale, const float* bias,
+                                         const int* label, int tid) {
+  constexpr int HS = HD + 1;
+  if (tid >= 256) return;
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+  for (int d = 0; d < HD; ++d) {
+    float a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = A[(ty + 16 * i) * HS + d];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = Bm[(tx + 16 * j) * HS + d];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+#pragma unroll
+  for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int i = ty + 16 * ii, j = tx + 16 * jj;
+      float s = acc[ii][jj] * scale;
+      if (BIASMASK) {
+        s += bias[((i >> 3) - (j >> 3) + 7) * 15 + ((i & 7) - (j & 7) + 7)];
+        if (label[i] != label[j]) s += -100.0f;
+      }
+      out[i * fft64::PSTR + j] = s;
+    }
+}
+
+__device__ __forceinline__ void softmax_rows(float* P, int tid) {
+  if (tid >= 256) return;
+  const int w = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    float* row = P + (w * 8 + r) * fft64::PSTR;
+    const float a = row[lane], b = row[lane + 32];
+    const float m = warp_max(fmaxf(a, b));
+    const float ea = expf(a - m), eb = expf(b - m);
+    const float inv = 1.0f / warp_sum(ea + eb);
+    row[lane] = ea * inv;
+    row[lane + 32] = eb * inv;
+  }
+}
+
+// out[i][d] = sum_j P[i][j] * V[j][d]   (TRANS: sum_j P[j][i] * V[j][d]), written to global rows
+template <int HD, bool TRANS>
+__device__ __forceinline__ void tile_pv(const float* P, const float* V, float* __restrict__ out, int64_t ld, int col0,
+                                        const int* rows, float scale, int tid) {
+  constexpr int HS = HD + 1;
+  if (tid >= 256) return;
+  const int ty = tid >> 4, tx = tid & 15;
+  constexpr int ND = (HD + 15) / 16;
+  float acc[4][ND];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < ND; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+  for (int j = 0; j < NTOK; ++j) {
+    float p[4], v[ND];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = TRANS ? P[j * fft64::PSTR + ty + 16 * i] : P[(ty + 16 * i) * fft64::PSTR + j];
+#pragma unroll
+    for (int dd = 0; dd < ND; ++dd) { const int d = tx + 16 * dd; v[dd] = d < HD ? V[j * HS + d] : 0.f; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int dd = 0; dd < ND; ++dd) acc[i][dd] = fmaf(p[i], v[dd], acc[i][dd]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int dd = 0; dd < ND; ++dd) {
+      const int d = tx + 16 * dd;
+      if (d < HD) out[(int64_t)rows[ty + 16 * i] * ld + col0 + d] = acc[i][dd] * scale;
+    }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(NTHR) win_attn_fwd_kernel(const float* __restrict__ q, int64_t ldq,
+                                                            const float* __restrict__ kv, int64_t ldkv,
+                                                            float* __restrict__ o, WinGeom g, float scale,
+                                                            const float* __restrict__ table,
+                                                            const float* __restrict__ coef, int coef_bstride,
+                                                            const uint8_t* __restrict__ band_of_bin, int nbands) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  Smem<HD>& s = *reinterpret_cast<Smem<HD>*>(smraw);
+  const int tid = threadIdx.x;
+  const int C = g.heads * HD;
+  int id = blockIdx.x;
+  const int h = id % g.heads; id /= g.heads;
+  const int wx = id % g.nWx; id /= g.nWx;
+  const int wy = id % g.nWy;
+  const int b = id / g.nWy;
+
+  if (tid < NTOK) token_of(g, b, wy, wx, tid, s.row[tid], s.label[tid]);
+  for (int i = tid; i < 225; i += NTHR) s.bias[i] = table ? table[i * g.heads + h] : 0.f;
+  if (coef) {
+    for (int i = tid; i < NTOK * 33; i += NTHR) s.band[i] = band_of_bin[i];
+    if (tid < 16) s.coef[tid] = tid < nbands ? coef[((int64_t)b * coef_bstride + h) * nbands + tid] : 0.f;
+  }
+  __syncthreads();
+  load_tile<HD>(s.q, q, ldq, h * HD, s.row, tid);
+  load_tile<HD>(s.k, kv, ldkv, h * HD, s.row, tid);
+  load_tile<HD>(s.v, kv, ldkv, C + h * HD, s.row, tid);
+  __syncthreads();
+  tile_abt<HD, true>(s.q, s.k, s.p, scale, s.bias, s.label, tid);
+  __syncthreads();
+  softmax_rows(s.p, tid);
+  __syncthreads();
+  if (coef) fft64::filter_map(s.p, s.sp, s.band, s.coef, 1.0f, tid);
+  tile_pv<HD, false>(s.p, s.v, o, C, h * HD, s.row, 1.0f, tid);
+}
+
+// ------------------------------------------------------------------ backward
+template <int HD>
+struct SmemB {
+  static constexpr int HS = HD + 1;
+  float q[NTOK * HS];
+  float k[NTOK * HS];
+  float v[NTOK * HS];
+  float dO[NTOK * HS];
+  float p[NTOK * fft64::PSTR];       // P (softmax), kept for dS
+  float x[NTOK * fft64::PSTR];       // dP' -> P' -> dP -> dS
+  float2 spA[NTOK * fft64::SPSTR];
+  float2 spB[NTOK * fft64::SPSTR];
+  float bias[232];
+  float dbias[232];
+  float coef[16];
+  float ecoef[16];
+  int row[NTOK];
+  int label[NTOK];
+  uint8_t band[NTOK * 33 + 8];
+};
+
+template <int HD>
+__global__ void __launch_bounds__(NTHR) win_attn_bwd_kernel(const float* __restrict__ q, int64_t ldq,
+                                                            const float* __restrict__ kv, int64_t ldkv,
+                                                            const float* __restrict__ dout, float* __restrict__ dq,
+                                                            float* __restrict__ dkv, WinGeom g, float scale,
+                                                            const float* __restrict__ table, float* __restrict__ dtable,
+                                                            const float* __restrict__ coef, int coef_bstride,
+                                                            float* __restrict__ dcoef,
+                                                            const uint8_t* __restrict__ band_of_bin, int nbands,
+                                                            int total_items) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  SmemB<HD>& s = *reinterpret_cast<SmemB<HD>*>(smraw);
+  const int tid = threadIdx.x;
+  const int C = g.heads * HD;
+  // gridDim.x is a multiple of heads, so every item this CTA visits has the same head
+  const int h = blockIdx.x % g.heads;
+  for (int i = tid; i < 232; i += NTHR) { s.bias[i] = (table && i < 225) ? table[i * g.heads + h] : 0.f; s.dbias[i] = 0.f; }
+  if (coef) for (int i = tid; i < NTOK * 33; i += NTHR) s.band[i] = band_of_bin[i];
+
+  for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+    int id = item / g.heads;
+    const int wx = id % g.nWx; id /= g.nWx;
+    const int wy = id % g.nWy;
+    const int b = id / g.nWy;
+    __syncthreads();
+    if (tid < NTOK) token_of(g, b, wy, wx, tid, s.row[tid], s.label[tid]);
+    if (coef && tid < 16) {
+      s.coef[tid] = tid < nbands ? coef[((int64_t)b * coef_bstride + h) * nbands + tid] : 0.f;
+      s.ecoef[tid] = 0.f;
+    }
+    __syncthreads();
+    load_tile<HD>(s.q, q, ldq, h * HD, s.row, tid);
+    load_tile<HD>(s.k, kv, ldkv, h * HD, s.row, tid);
+    load_tile<HD>(s.v, kv, ldkv, C + h * HD, s.row, tid);
+    load_tile<HD>(s.dO, dout, C, h * HD, s.row, tid);
+    __syncthreads();
+    tile_abt<HD, true>(s.q, s.k, s.p, scale, s.bias, s.label, tid);     // S
+    tile_abt<HD, false>(s.dO, s.v, s.x, 1.0f, nullptr, nullptr, tid);   // dP' = dO.V^T
+    __syncthreads();
+    softmax_rows(s.p, tid);                                             // P
+    __syncthreads();
+    if (coef) {
+      // F(dP') -> spB
+      fft64::rows_forward(s.x, s.spB, tid);
+      __syncthreads();
+      {
+        const int col = min(tid >> 3, 32), l = tid & 7;
+        float2 a[8];
+        fft64::col_load(s.spB, a, col, l);
+        fft64::fft64_group<-1>(a, l);
+        __syncwarp();
+        if ((tid >> 3) <= 32) fft64::col_store(s.spB, a, col, l);
+      }
+      fft64::rows_forward(s.p, s.spA, tid);
+      __syncthreads();
+      {
+        // F(P): band energies against F(dP'), then gain and inverse columns -> spA
+        const int col = min(tid >> 3, 32), l = tid & 7;
+        const bool live = (tid >> 3) <= 32;
+        float2 a[8], bb[8];
+        fft64::col_load(s.spA, a, col, l);
+        fft64::col_load(s.spB, bb, col, l);
+        fft64::fft64_group<-1>(a, l);
+        const float wgt = (col == 0 || col == 32) ? 1.0f : 2.0f;
+        float e[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) e[t] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int bnd = s.band[(l + 8 * j) * 33 + col];
+          const float dot = wgt * (a[j].x * bb[j].x + a[j].y * bb[j].y);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) e[t] += (bnd == t) ? dot : 0.f;
+          const float gn = 1.0f + s.coef[bnd];
+          a[j].x *= gn; a[j].y *= gn;
+        }
+        fft64::fft64_group<1>(a, l);
+        __syncwarp();
+        if (live) fft64::col_store(s.spA, a, col, l);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          float v = live ? e[t] : 0.f;
+          v = warp_sum(v);
+          if ((tid & 31) == 0 && t < nbands) atomicAdd(&s.ecoef[t], v * (1.0f / 4096.0f));
+        }
+      }
+      __syncthreads();
+      fft64::rows_inverse(s.spA, s.x, 1.0f / 4096.0f, tid);             // x = P'
+      __syncthreads();
+      tile_pv<HD, true>(s.x, s.dO, dkv, 2 * C, C + h * HD, s.row, 1.0f, tid);   // dV = P'^T.dO
+      {
+        // dP = filter(dP'): gain on F(dP'), inverse columns
+        const int col = min(tid >> 3, 32), l = tid & 7;
+        float2 a[8];
+        fft64::col_load(s.spB, a, col, l);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float gn = 1.0f + s.coef[s.band[(l + 8 * j) * 33 + col]];
+          a[j].x *= gn; a[j].y *= gn;
+        }
+        fft64::fft64_group<1>(a, l);
+        __syncwarp();
+        if ((tid >> 3) <= 32) fft64::col_store(s.spB, a, col, l);
+      }
+      __syncthreads();                                                  // dV reads of x done, spB complete
+      fft64::rows_inverse(s.spB, s.x, 1.0f / 4096.0f, tid);             // x = dP
+      __syncthreads();
+      if (dcoef && tid < nbands) atomicAdd(&dcoef[((int64_t)b * coef_bstride + h) * nbands + tid], s.ecoef[tid]);
+    } else {
+      tile_pv<HD, true>(s.p, s.dO, dkv, 2 * C, C + h * HD, s.row, 1.0f, tid);   // dV = P^T.dO
+      __syncthreads();
+    }
+    // dS = P o (dP - rowsum(dP o P)) -> x ; bias gradient into shared memory
+    if (tid < 256) {
+      const int w = tid >> 5, lane = tid & 31;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int i = w * 8 + r;
+        float* xr = s.x + i * fft64::PSTR;
+        const float* pr = s.p + i * fft64::PSTR;
+        const float p0 = pr[lane], p1 = pr[lane + 32];
+        const float d0 = xr[lane], d1 = xr[lane + 32];
+        const float dotv = warp_sum(p0 * d0 + p1 * d1);
+        const float s0 = p0 * (d0 - dotv), s1 = p1 * (d1 - dotv);
+        xr[lane] = s0; xr[lane + 32] = s1;
+        if (dtable) {
+          const int j0 = lane, j1 = lane + 32;
+          atomicAdd(&s.dbias[((i >> 3) - (j0 >> 3) + 7) * 15 + ((i & 7) - (j0 & 7) + 7)], s0);
+          atomicAdd(&s.dbias[((i >> 3) - (j1 >> 3) + 7) * 15 + ((i & 7) - (j1 & 7) + 7)], s1);
+        }
+      }
+    }
+    __syncthreads();
+    tile_pv<HD, false>(s.x, s.k, dq, C, h * HD, s.row, scale, tid);        // dQ = scale * dS.K
+    tile_pv<HD, true>(s.x, s.q, dkv, 2 * C, h * HD, s.row, scale, tid);    // dK = scale * dS^T.Q
+  }
+  __syncthreads();
+  if (dtable) for (int i = tid; i < 225; i += NTHR) atomicAdd(&dtable[i * g.heads + h], s.dbias[i]);
+}
+
+template <int HD>
+int launch_fwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, float* o, const WinGeom& g, float scale,
+               const float* table, const float* coef, int cbs, const uint8_t* bob, int nbands, cudaStream_t st) {
+  const size_t smem = sizeof(Smem<HD>);
+  FA_CUDA(cudaFuncSetAttribute(win_attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int items = g.B * g.nWy * g.nWx * g.heads;
+  win_attn_fwd_kernel<HD><<<items, NTHR, smem, st>>>(q, ldq, kv, ldkv, o, g, scale, table, coef, cbs, bob, nbands);
+  FA_LAUNCH_CHECK("fa_win_attn_fwd");
+  return FA_OK;
+}
+
+template <int HD>
+int launch_bwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, const float* dout, float* dq, float* dkv,
+               const WinGeom& g, float scale, const float* table, float* dtable, const float* coef, int cbs,
+               float* dcoef, const uint8_t* bob, int nbands, cudaStream_t st) {
+  const size_t smem = sizeof(SmemB<HD>);
+  FA_CUDA(cudaFuncSetAttribute(win_attn_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int items = g.B * g.nWy * g.nWx * g.heads;
+  int grid = (4 * kNumSMs / g.heads) * g.heads;
+  if (grid < g.heads) grid = g.heads;
+  if (grid > items) grid = items;          // items is a multiple of heads
+  win_attn_bwd_kernel<HD><<<grid, NTHR, smem, st>>>(q, ldq, kv, ldkv, dout, dq, dkv, g, scale, table, dtable, coef, cbs,
+                                                   dcoef, bob, nbands, items);
+  FA_LAUNCH_CHECK("fa_win_attn_bwd");
+  return FA_OK;
+}
+
+int check_geom(const char* who, int B, int H, int W, int heads, int hd, int shift, int64_t ldq, int64_t ldkv,
+               const void* coef, const void* bob, int nbands, WinGeom& g) {
+  FA_REQUIRE(B > 0 && heads > 0, "%s: empty batch/heads", who);
+  FA_REQUIRE(H % WIN == 0 && W % WIN == 0, "%s: H=%d W=%d must be multiples of the 8x8 window", who, H, W);
+  FA_REQUIRE(hd == 28 || hd == 56 || hd == 64, "%s: head_dim=%d unsupported (28, 56, 64)", who, hd);
+  FA_REQUIRE(shift == 0 || shift == 4, "%s: shift=%d unsupported (0 or 4)", who, shift);
+  FA_REQUIRE(shift == 0 || (H > WIN && W > WIN), "%s: shifted windows need H,W > 8", who);
+  FA_REQUIRE(ldq % 4 == 0 && ldkv % 4 == 0, "%s: row strides must be multiples of 4 floats", who);
+  FA_REQUIRE((int64_t)B * H * W < (1ll << 31) / 64, "%s: too many tokens", who);
+  FA_REQUIRE(!coef || (bob && nbands >= 1 && nbands <= 8), "%s: coef needs band_of_bin and 1..8 bands", who);
+  g.B = B; g.H = H; g.W = W; g.heads = heads; g.shift = shift; g.nWy = H / WIN; g.nWx = W / WIN;
+  return FA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fa_win_attn_fwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, float* o, int B, int H, int W, int heads,
+                    int hd, int shift, float scale, const float* table, const float* coef, int coef_bstride,
+                    const uint8_t* band_of_bin, int nbands, fa_stream_t stream) {
+  FA_REQUIRE(q && kv && o, "fa_win_attn_fwd: null pointer");
+  FA_REQUIRE(((uintptr_t)q | (uintptr_t)kv | (uintptr_t)o) % 16 == 0, "fa_win_attn_fwd: pointers must be 16-byte aligned");
+  WinGeom g;
+  int rc = check_geom("fa_win_attn_fwd", B, H, W, heads, hd, shift, ldq, ldkv, coef, band_of_bin, nbands, g);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_WIN_ATTN, st);
+  if (hd == 56) return launch_fwd<56>(q, ldq, kv, ldkv, o, g, scale, table, coef, coef_bstride, band_of_bin, nbands, st);
+  if (hd == 28) return launch_fwd<28>(q, ldq, kv, ldkv, o, g, scale, table, coef, coef_bstride, band_of_bin, nbands, st);
+  return launch_fwd<64>(q, ldq, kv, ldkv, o, g, scale, table, coef, coef_bstride, band_of_bin, nbands, st);
+}
+
+int fa_win_attn_bwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, const float* dout, float* dq, float* dkv,
+                    int B, int H, int W, int heads, int hd, int shift, float scale, const float* table, float* dtable,
+                    const float* coef, int coef_bstride, float* dcoef, const uint8_t* band_of_bin, int nbands,
+                    fa_stream_t stream) {
+  FA_REQUIRE(q && kv && dout && dq && dkv, "fa_win_attn_bwd: null pointer");
+  FA_REQUIRE(((uintptr_t)q | (uintptr_t)kv | (uintptr_t)dout) % 16 == 0, "fa_win_attn_bwd: pointers must be 16-byte aligned");
+  WinGeom g;
+  int rc = check_geom("fa_win_attn_bwd", B, H, W, heads, hd, shift, ldq, ldkv, coef, band_of_bin, nbands, g);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_WIN_ATTN, st);
+  if (hd == 56) return launch_bwd<56>(q, ldq, kv, ldkv, dout, dq, dkv, g, scale, table, dtable, coef, coef_bstride, dcoef, band_of_bin, nbands, st);
+  if (hd == 28) return launch_bwd<28>(q, ldq, kv, ldkv, dout, dq, dkv, g, scale, table, dtable, coef, coef_bstride, dcoef, band_of_bin, nbands, st);
+  return launch_bwd<64>(q, ldq, kv, ldkv, dout, dq, dkv, g, scale, table, dtable, coef, coef_bstride, dcoef, band_of_bin, nbands, st);
+}
+
+}  // extern "C"

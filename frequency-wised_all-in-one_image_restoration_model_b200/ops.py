@@ -1,0 +1,348 @@
+"""Thin torch-tensor front end of the C ABI (``include/freqair.h``).
+
+Every function here only validates arguments, pulls raw pointers out of torch tensors and enqueues
+kernels on ``torch.cuda.current_stream()``.  PyTorch is the allocator and the stream owner; all
+arithmetic happens in ``libfreqair.so``.  Nothing here can run without a CUDA device.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import FaGemmEpilogue
+
+ACT_NONE, ACT_GELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
+K_GEMM, K_WIN_ATTN, K_JOINT_ATTN, K_BAND, K_LN, K_DWCONV, K_IM2COL, K_BN, K_OPTIM, K_DCN, K_ELEM = range(1, 12)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError('freqair ops need CUDA tensors: there is no CPU path')
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _f32(*ts):
+    for t in ts:
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+            raise RuntimeError(f'freqair: expected a contiguous float32 tensor, got {t.dtype} strides {t.stride()}')
+
+
+def _call(name, *args):
+    lib = _lib.load()
+    _lib.check(getattr(lib, name)(*args), name)
+
+
+def launch_count(reset=False):
+    lib = _lib.load()
+    n = lib.fa_launch_count()
+    if reset:
+        lib.fa_launch_count_reset()
+    return int(n)
+
+
+def prof_begin(kernel_class):
+    _call('fa_prof_begin', int(kernel_class))
+
+
+def prof_end():
+    ms, n = ctypes.c_double(0), ctypes.c_int64(0)
+    _call('fa_prof_end', ctypes.byref(ms), ctypes.byref(n))
+    return ms.value, n.value
+
+
+# ----------------------------------------------------------------------------- GEMM
+def _rows2d(t):
+    """(ptr, rows, cols, ld) of a 2-D row-major view whose last dim is dense."""
+    if t.dim() != 2 or t.stride(1) != 1 or t.dtype != torch.float32:
+        raise RuntimeError(f'freqair.gemm: need a 2-D float32 row-major view, got shape {tuple(t.shape)} strides {t.stride()}')
+    return t.shape[0], t.shape[1], (t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1]))
+
+
+def gemm(A, B, C, transA=False, transB=True, bias=None, act=ACT_NONE, act_param=0.0, aux=None, aux_act=ACT_NONE,
+         aux_param=0.0, rowscale=None, rows_per_scale=1, residual=None, accumulate=False, alpha=1.0, preact=None,
+         backend=0):
+    """C = epi(alpha * op(A) @ op(B)); see fa_gemm in include/freqair.h.  A, B, C, aux, residual, preact are 2-D
+    row-major views (row stride may exceed the width).  transB=True means B is an nn.Linear weight [N, K]."""
+    ar, ac, lda = _rows2d(A)
+    br, bc, ldb = _rows2d(B)
+    M, K = (ac, ar) if transA else (ar, ac)
+    Kb, N = (bc, br) if transB else (br, bc)
+    if K != Kb:
+        raise RuntimeError(f'freqair.gemm: inner dims differ ({K} vs {Kb})')
+    cr, cc, ldc = _rows2d(C)
+    if (cr, cc) != (M, N):
+        raise RuntimeError(f'freqair.gemm: C is {cr}x{cc}, expected {M}x{N}')
+    e = FaGemmEpilogue()
+    e.bias = bias.data_ptr() if bias is not None else None
+    e.act, e.act_param = act, act_param
+    if aux is not None:
+        _, _, e.ldaux = _rows2d(aux)
+        e.aux = aux.data_ptr()
+    e.aux_act, e.aux_param = aux_act, aux_param
+    if rowscale is not None:
+        e.rowscale = rowscale.data_ptr()
+    e.rows_per_scale = rows_per_scale
+    if residual is not None:
+        _, _, e.ldr = _rows2d(residual)
+        e.residual = residual.data_ptr()
+    e.accumulate = 1 if accumulate else 0
+    e.alpha = alpha
+    if preact is not None:
+        _, _, e.ldpre = _rows2d(preact)
+        e.preact = preact.data_ptr()
+    _call('fa_gemm', _p(A), _p(B), _p(C), M, N, K, lda, ldb, ldc, int(transA), int(transB), ctypes.byref(e), backend,
+          _stream())
+    return C
+
+
+def colsum(X, out, rowscale=None, rows_per_scale=1, accumulate=False):
+    M, N, ld = _rows2d(X)
+    _call('fa_colsum', _p(X), _p(out), M, N, ld, _p(rowscale), rows_per_scale, int(accumulate), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------- band filter (K1)
+def band_split(x, band_of_bin, nbands, mode=0):
+    _f32(x)
+    n = x.shape[-1]
+    nmaps = x.numel() // (n * n)
+    shape = (nbands,) + tuple(x.shape) + ((2,) if mode == 1 else ())
+    y = torch.empty(shape, device=x.device, dtype=torch.float32)
+    _call('fa_band_split', _p(x), _p(y), nmaps, n, _p(band_of_bin), nbands, mode, _stream())
+    return y
+
+
+def band_filter(x, band_of_bin, coef, maps_per_group, heads):
+    _f32(x, coef)
+    n = x.shape[-1]
+    nmaps = x.numel() // (n * n)
+    y = torch.empty_like(x)
+    _call('fa_band_filter', _p(x), _p(y), nmaps, n, _p(band_of_bin), coef.shape[-1], _p(coef), maps_per_group, heads,
+          _stream())
+    return y
+
+
+def band_energy(a, b, out, band_of_bin, maps_per_group, heads):
+    _f32(a, b, out)
+    n = a.shape[-1]
+    nmaps = a.numel() // (n * n)
+    _call('fa_band_energy', _p(a), _p(b), _p(out), nmaps, n, _p(band_of_bin), out.shape[-1], maps_per_group, heads,
+          _stream())
+    return out
+
+
+def dc_split(x):
+    _f32(x)
+    n = x.shape[-1]
+    y = torch.empty((2,) + tuple(x.shape), device=x.device, dtype=torch.float32)
+    _call('fa_dc_split', _p(x), _p(y), x.numel() // (n * n), n, _stream())
+    return y
+
+
+# ----------------------------------------------------------------------------- attention (K2)
+def win_attn_fwd(q, kv, o, B, H, W, heads, hd, shift, scale, table, coef, coef_bstride, band_of_bin, nbands):
+    _call('fa_win_attn_fwd', _p(q), q.stride(0), _p(kv), kv.stride(0), _p(o), B, H, W, heads, hd, shift, scale,
+          _p(table), _p(coef), coef_bstride, _p(band_of_bin), nbands, _stream())
+
+
+def win_attn_bwd(q, kv, dout, dq, dkv, B, H, W, heads, hd, shift, scale, table, dtable, coef, coef_bstride, dcoef,
+                 band_of_bin, nbands):
+    _f32(dout, dq, dkv)
+    _call('fa_win_attn_bwd', _p(q), q.stride(0), _p(kv), kv.stride(0), _p(dout), _p(dq), _p(dkv), B, H, W, heads, hd,
+          shift, scale, _p(table), _p(dtable), _p(coef), coef_bstride, _p(dcoef), _p(band_of_bin), nbands, _stream())
+
+
+def joint_attn_fwd(q, kv, o, L, B, H, W, heads, hd, shift, scale, tables, kind):
+    _call('fa_joint_attn_fwd', _p(q), q.stride(0), _p(kv), kv.stride(0), _p(o), L, B, H, W, heads, hd, shift, scale,
+          _p(tables), kind, _stream())
+
+
+def joint_attn_bwd(q, kv, dout, dq, dkv, L, B, H, W, heads, hd, shift, scale, tables, dtables, kind):
+    _f32(dout, dq, dkv)
+    _call('fa_joint_attn_bwd', _p(q), q.stride(0), _p(kv), kv.stride(0), _p(dout), _p(dq), _p(dkv), L, B, H, W, heads,
+          hd, shift, scale, _p(tables), _p(dtables), kind, _stream())
+
+
+# ----------------------------------------------------------------------------- norms
+def layernorm_fwd(x, gamma, beta, y=None, want_stats=True):
+    _f32(x, gamma, beta)
+    C = x.shape[-1]
+    rows = x.numel() // C
+    y = torch.empty_like(x) if y is None else y
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32) if want_stats else None
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if want_stats else None
+    _call('fa_layernorm_fwd', _p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), rows, C, _stream())
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dgamma, dbeta, dx=None):
+    _f32(dy, x, dres)
+    C = x.shape[-1]
+    rows = x.numel() // C
+    dx = torch.empty_like(x) if dx is None else dx
+    _call('fa_layernorm_bwd', _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dgamma), _p(dbeta),
+          rows, C, _stream())
+    return dx
+
+
+def bn_stats(x, B, C, S):
+    sums = torch.zeros(C, 2, device=x.device, dtype=torch.float64)
+    _call('fa_bn_stats', _p(x), _p(sums), B, C, S, _stream())
+    return sums
+
+
+def bn_apply(x, scale, shift, slope, B, C, S, want_y=False, want_pool=True):
+    y = torch.empty_like(x) if want_y else None
+    pooled = torch.empty(B, C, device=x.device, dtype=torch.float32) if want_pool else None
+    _call('fa_bn_apply', _p(x), _p(scale), _p(shift), slope, _p(y), _p(pooled), B, C, S, _stream())
+    return y, pooled
+
+
+def bn_bwd(x, mean, rstd, scale, shift, slope, dy, dpooled, B, C, S, training=True):
+    red = None
+    if training:
+        red = torch.zeros(C, 2, device=x.device, dtype=torch.float64)
+        _call('fa_bn_bwd_reduce', _p(x), _p(mean), _p(rstd), _p(scale), _p(shift), slope, _p(dy), _p(dpooled), _p(red),
+              B, C, S, _stream())
+    dx = torch.empty_like(x)
+    _call('fa_bn_bwd_apply', _p(x), _p(mean), _p(rstd), _p(scale), _p(shift), slope, _p(dy), _p(dpooled), _p(red),
+          _p(dx), B, C, S, _stream())
+    return dx, red
+
+
+# ----------------------------------------------------------------------------- conv pieces
+def dwconv_fwd(h1, w, b, B, H, W, C, want_act=True):
+    _f32(h1, w, b)
+    u2 = torch.empty_like(h1)
+    h2 = torch.empty_like(h1) if want_act else None
+    _call('fa_dwconv3x3_fwd', _p(h1), _p(w), _p(b), _p(u2), _p(h2), B, H, W, C, _stream())
+    return u2, h2
+
+
+def dwconv_bwd(du2, h1, u1, w, dw, db, B, H, W, C):
+    _f32(du2, h1, u1, w)
+    du1 = torch.empty_like(du2)
+    _call('fa_dwconv3x3_bwd', _p(du2), _p(h1), _p(u1), _p(w), _p(du1), _p(dw), _p(db), B, H, W, C, _stream())
+    return du1
+
+
+def im2col(x, B, H, W, C, kh, kw, stride, pad, nchw_in=False):
+    _f32(x)
+    Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    col = torch.empty(B * Ho * Wo, kh * kw * C, device=x.device, dtype=torch.float32)
+    _call('fa_im2col', _p(x), _p(col), B, H, W, C, kh, kw, stride, pad, int(nchw_in), _stream())
+    return col
+
+
+def col2im(col, B, H, W, C, kh, kw, stride, pad):
+    _f32(col)
+    dx = torch.empty(B, H * W, C, device=col.device, dtype=torch.float32)
+    _call('fa_col2im', _p(col), _p(dx), B, H, W, C, kh, kw, stride, pad, _stream())
+    return dx
+
+
+def pixel_shuffle2_fwd(g, y, B, H, W, Co):
+    _f32(g)
+    _call('fa_pixel_shuffle2_fwd', _p(g), _p(y), y.stride(0), B, H, W, Co, _stream())
+
+
+def pixel_shuffle2_bwd(dy, dg, B, H, W, Co):
+    _f32(dg)
+    _call('fa_pixel_shuffle2_bwd', _p(dy), dy.stride(0), _p(dg), B, H, W, Co, _stream())
+
+
+def copy2d(src, dst):
+    rows, cols, lds = _rows2d(src)
+    _, _, ldd = _rows2d(dst)
+    _call('fa_copy2d', _p(src), lds, _p(dst), ldd, rows, cols, _stream())
+
+
+def add2d(a, b, dst):
+    rows, cols, lda = _rows2d(a)
+    _, _, ldb = _rows2d(b)
+    _, _, ldd = _rows2d(dst)
+    _call('fa_add2d', _p(a), lda, _p(b), ldb, _p(dst), ldd, rows, cols, _stream())
+
+
+def tokens_to_nchw(t, res, B, HW, C):
+    _f32(t, res)
+    y = torch.empty(B, C, HW, device=t.device, dtype=torch.float32)
+    _call('fa_tokens_to_nchw', _p(t), _p(res), _p(y), B, HW, C, _stream())
+    return y
+
+
+def nchw_to_tokens(x, B, HW, C):
+    _f32(x)
+    t = torch.empty(B, HW, C, device=x.device, dtype=torch.float32)
+    _call('fa_nchw_to_tokens', _p(x), _p(t), B, HW, C, _stream())
+    return t
+
+
+# ----------------------------------------------------------------------------- DGRN pieces
+def dcn_im2col(x, om, B, H, W, C):
+    _f32(x, om)
+    col = torch.empty(B * H * W, 9 * C, device=x.device, dtype=torch.float32)
+    _call('fa_dcn_im2col', _p(x), _p(om), _p(col), B, H, W, C, _stream())
+    return col
+
+
+def dcn_col2im(x, om, dcol, B, H, W, C):
+    _f32(x, om, dcol)
+    dx = torch.zeros_like(x)
+    dom = torch.empty_like(om)
+    _call('fa_dcn_col2im', _p(x), _p(om), _p(dcol), _p(dx), _p(dom), B, H, W, C, _stream())
+    return dx, dom
+
+
+def sft_fuse_fwd(x, dcn, gamma, beta, slope):
+    _f32(x, dcn, gamma, beta)
+    out = torch.empty_like(x)
+    _call('fa_sft_fuse_fwd', _p(x), _p(dcn), _p(gamma), _p(beta), _p(out), x.numel(), slope, _stream())
+    return out
+
+
+def sft_fuse_bwd(x, dcn, gamma, beta, dout, slope):
+    _f32(x, dcn, gamma, beta, dout)
+    dx, ddcn, dgamma, dbeta = (torch.empty_like(x) for _ in range(4))
+    _call('fa_sft_fuse_bwd', _p(x), _p(dcn), _p(gamma), _p(beta), _p(dout), _p(dx), _p(ddcn), _p(dgamma), _p(dbeta),
+          x.numel(), slope, _stream())
+    return dx, ddcn, dgamma, dbeta
+
+
+# ----------------------------------------------------------------------------- elementwise / optimiser
+def act_fwd(x, act, p=0.0):
+    _f32(x)
+    y = torch.empty_like(x)
+    _call('fa_act_fwd', _p(x), _p(y), x.numel(), act, p, _stream())
+    return y
+
+
+def act_bwd(dy, x, act, p=0.0):
+    _f32(dy, x)
+    dx = torch.empty_like(x)
+    _call('fa_act_bwd', _p(dy), _p(x), _p(dx), x.numel(), act, p, _stream())
+    return dx
+
+
+def l1_loss(a, b, want_grad=True, gscale=1.0):
+    _f32(a, b)
+    loss = torch.zeros(1, device=a.device, dtype=torch.float32)
+    grad = torch.empty_like(a) if want_grad else None
+    _call('fa_l1_loss', _p(a), _p(b), _p(loss), _p(grad), a.numel(), gscale, _stream())
+    return loss, grad
+
+
+def momentum_update(k, q, m):
+    _f32(k, q)
+    _call('fa_momentum_update', _p(k), _p(q), k.numel(), m, _stream())
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    _f32(p, g, m, v)
+    _call('fa_adam_step', _p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, step, grad_scale, _stream())

@@ -204,20 +204,17 @@ def decoder_forward(sd, p, x, all_inter, method='all_3_bands', dp=None):
 
 
 # ----------------------------------------------------------------------------- encoder
-def enc_freq_attention(sd, p, x, heads, mask, L, kind):
-    """FrequencyWindowAttention.forward (encoder_Uformer.py:256-310): joint attention over
-    the L band copies of one window; ``kind`` 'intra' masks off-band pairs, 'inter' same-band pairs."""
-    B_, N, C = x.shape                                       # B_ = (l b nw)
-    hd = C // heads
-    q, k, v = qkv_heads(sd, p + '.qkv', x, heads)
+def joint_attention_core(q, k, v, tables, mask, L, kind):
+    """Attention core of FrequencyWindowAttention.forward (encoder_Uformer.py:259-300) on per-head
+    q, k, v [(l bnw), heads, 64, hd]; ``tables``: the L*L bias tables [225, heads] -> [(l bnw), heads, 64, hd]."""
+    B_, heads, N, hd = q.shape
 
     def join(t):                                             # (l bnw) h t d -> bnw h (l t) d
-        return t.view(L, B_ // L, heads, N, hd).permute(1, 2, 0, 3, 4).reshape(B_ // L, heads, L * N, hd)
+        return t.reshape(L, B_ // L, heads, N, hd).permute(1, 2, 0, 3, 4).reshape(B_ // L, heads, L * N, hd)
     q, k, v = join(q), join(k), join(v)
     attn = (q * hd ** -0.5) @ k.transpose(-2, -1)
     ri = rel_index().view(-1)
-    bias = torch.stack([sd[f'{p}.relative_position_bias_table.{i}'][ri].view(N, N, -1).permute(2, 0, 1)
-                        for i in range(L * L)], 0)           # [(l1 l2), h, t1, t2]
+    bias = torch.stack([tables[i][ri].view(N, N, -1).permute(2, 0, 1) for i in range(L * L)], 0)   # [(l1 l2), h, t1, t2]
     bias = bias.view(L, L, heads, N, N).permute(2, 0, 3, 1, 4).reshape(1, heads, L * N, L * N)
     same = torch.eye(L).repeat_interleave(N, 0).repeat_interleave(N, 1)
     mfreq = (1 - same) * -100.0 if kind == 'intra' else same * -100.0          # :246-254
@@ -228,7 +225,16 @@ def enc_freq_attention(sd, p, x, heads, mask, L, kind):
         attn = (attn.view(-1, nW, heads, L * N, L * N) + big.unsqueeze(1).unsqueeze(0)).view(-1, heads, L * N, L * N)
     attn = attn.softmax(-1)
     o = attn @ v                                             # bnw h (l t) d
-    o = o.view(B_ // L, heads, L, N, hd).permute(2, 0, 1, 3, 4).reshape(B_, heads, N, hd)
+    return o.view(B_ // L, heads, L, N, hd).permute(2, 0, 1, 3, 4).reshape(B_, heads, N, hd)
+
+
+def enc_freq_attention(sd, p, x, heads, mask, L, kind):
+    """FrequencyWindowAttention.forward (encoder_Uformer.py:256-310): joint attention over
+    the L band copies of one window; ``kind`` 'intra' masks off-band pairs, 'inter' same-band pairs."""
+    B_, N, C = x.shape                                       # B_ = (l b nw)
+    q, k, v = qkv_heads(sd, p + '.qkv', x, heads)
+    tables = [sd[f'{p}.relative_position_bias_table.{i}'] for i in range(L * L)]
+    o = joint_attention_core(q, k, v, tables, mask, L, kind)
     return lin(sd, p + '.proj', o.transpose(1, 2).reshape(B_, N, C))
 
 

@@ -1,0 +1,415 @@
+"""GPU parity of every C-ABI kernel against the CPU oracle / plain fp32 torch on the same seeded inputs.
+Tolerances: fp32 SIMT kernels 1e-4 relative to the tensor's scale (reduction-order noise only)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import PKG_NAME
+from oracle import airnet, freq, uformer
+
+pytestmark = pytest.mark.gpu
+import importlib
+
+
+@pytest.fixture(scope='module')
+def ops():
+    return importlib.import_module(PKG_NAME + '.ops')
+
+
+def dev(t):
+    return t.cuda().contiguous()
+
+
+def close(a, b, tol=1e-4, what=''):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    scale = max(b.abs().max().item(), 1e-6)
+    err = (a - b).abs().max().item()
+    assert err <= tol * scale + 1e-7, f'{what}: max err {err:.3e} vs scale {scale:.3e}'
+
+
+def gen(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return torch.randn(*shape, generator=g) * scale
+
+
+# ----------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize('M,N,K', [(1, 1, 1), (64, 56, 56), (300, 224, 56), (257, 129, 27), (1024, 448, 3584),
+                                   (70, 3, 1008), (33, 65, 200)])
+@pytest.mark.parametrize('tA,tB', [(False, True), (False, False), (True, False), (True, True)])
+def test_gemm_plain(ops, M, N, K, tA, tB):
+    A = gen(K, M) if tA else gen(M, K)
+    B = gen(N, K, seed=1) if tB else gen(K, N, seed=1)
+    C = torch.empty(M, N, device='cuda')
+    ops.gemm(dev(A), dev(B), C, transA=tA, transB=tB, backend=1)
+    ref = (A.t() if tA else A).double() @ (B.t() if tB else B).double()
+    close(C, ref.float(), 2e-5 * math.sqrt(K), f'gemm {M}x{N}x{K}')
+
+
+def test_gemm_epilogues(ops):
+    M, N, K = 192, 224, 56
+    A, W, b = gen(M, K), gen(N, K, seed=1), gen(N, seed=2)
+    R, aux = gen(M, N, seed=3), gen(M, N, seed=4)
+    rs = torch.tensor([0.0, 1.0 / 0.9, 1.0 / 0.9])
+    base = A @ W.t() + b
+    # bias + GELU + pre-activation output
+    C = torch.empty(M, N, device='cuda'); pre = torch.empty(M, N, device='cuda')
+    ops.gemm(dev(A), dev(W), C, bias=dev(b), act=ops.ACT_GELU, preact=pre, backend=1)
+    close(pre, base, 1e-4, 'preact'); close(C, F.gelu(base), 1e-4, 'gelu')
+    # bias + leaky relu
+    ops.gemm(dev(A), dev(W), C, bias=dev(b), act=ops.ACT_LRELU, act_param=0.1, backend=1)
+    close(C, F.leaky_relu(base, 0.1), 1e-4, 'lrelu')
+    # residual + per-sample row scale (DropPath): R + s * (A W^T + b)
+    ops.gemm(dev(A), dev(W), C, bias=dev(b), rowscale=dev(rs), rows_per_scale=64, residual=dev(R), backend=1)
+    close(C, R + rs.repeat_interleave(64)[:, None] * base, 1e-4, 'residual+rowscale')
+    # multiply by GELU'(aux)
+    ag = aux.clone().requires_grad_(True)
+    F.gelu(ag).sum().backward()
+    ops.gemm(dev(A), dev(W), C, aux=dev(aux), aux_act=ops.ACT_GELU, backend=1)
+    close(C, (A @ W.t()) * ag.grad, 1e-4, 'dgelu')
+    # accumulate + strided output view
+    big = torch.zeros(M, 2 * N, device='cuda'); big[:, N:] = dev(R)
+    ops.gemm(dev(A), dev(W), big[:, N:], accumulate=True, alpha=0.5, backend=1)
+    close(big[:, N:], R + 0.5 * (A @ W.t()), 1e-4, 'accumulate strided')
+    assert big[:, :N].abs().max().item() == 0
+
+
+def test_gemm_splitk_weight_grad(ops):
+    M, N, K = 20000, 56, 224          # dW[N,K] = dY^T[N,M] X[M,K], reduction over M
+    dY, X = gen(M, N, scale=0.1), gen(M, K, seed=1)
+    G0 = gen(N, K, seed=2)
+    G = dev(G0)
+    ops.gemm(dev(dY), dev(X), G, transA=True, transB=False, accumulate=True, backend=1)
+    close(G, G0 + (dY.double().t() @ X.double()).float(), 1e-4, 'split-k')
+
+
+def test_colsum(ops):
+    X = gen(1000, 70)
+    rs = torch.rand(10)
+    out = torch.empty(70, device='cuda')
+    ops.colsum(dev(X), out, rowscale=dev(rs), rows_per_scale=100)
+    close(out, (X * rs.repeat_interleave(100)[:, None]).sum(0), 1e-4, 'colsum')
+    ops.colsum(dev(X), out, accumulate=True)
+    close(out, (X * rs.repeat_interleave(100)[:, None]).sum(0) + X.sum(0), 1e-4, 'colsum acc')
+
+
+# ----------------------------------------------------------------------------- norms
+@pytest.mark.parametrize('C', [28, 56, 112, 448, 768, 896])
+def test_layernorm(ops, C):
+    rows = 333
+    x = gen(rows, C).requires_grad_(True)
+    g, b = (1 + 0.1 * gen(C, seed=1)).requires_grad_(True), gen(C, seed=2).requires_grad_(True)
+    dy, dres = gen(rows, C, seed=3), gen(rows, C, seed=4)
+    y = F.layer_norm(x, (C,), g, b)
+    y.backward(dy)
+    yk, mean, rstd = ops.layernorm_fwd(dev(x.detach()), dev(g.detach()), dev(b.detach()))
+    close(yk, y, 1e-5, 'ln fwd')
+    dg, db = torch.zeros(C, device='cuda'), torch.zeros(C, device='cuda')
+    dx = ops.layernorm_bwd(dev(dy), dev(x.detach()), mean, rstd, dev(g.detach()), dev(dres), dg, db)
+    close(dx, x.grad + dres, 1e-4, 'ln dx'); close(dg, g.grad, 1e-4, 'ln dgamma'); close(db, b.grad, 1e-4, 'ln dbeta')
+
+
+def test_batchnorm_head(ops):
+    B, C, S = 3, 8, 5000
+    x = (gen(B, C, S) * 2 + 0.5).requires_grad_(True)
+    w, b = (1 + 0.1 * gen(C, seed=1)).requires_grad_(True), gen(C, seed=2).requires_grad_(True)
+    dpool = gen(B, C, seed=3)
+    y = F.leaky_relu(F.batch_norm(x, None, None, w, b, training=True, eps=1e-5), 0.1)
+    pooled = y.mean(2)
+    pooled.backward(dpool)
+    xd = dev(x.detach())
+    sums = ops.bn_stats(xd, B, C, S)
+    n = B * S
+    mean = sums[:, 0] / n
+    var = sums[:, 1] / n - mean * mean
+    close(mean, x.detach().mean((0, 2)), 1e-5, 'bn mean'); close(var, x.detach().var((0, 2), unbiased=False), 1e-4, 'bn var')
+    rstd = torch.rsqrt(var + 1e-5).float(); mean = mean.float()
+    scale = dev(w.detach()) * rstd
+    shift = dev(b.detach()) - mean * scale
+    yk, pk = ops.bn_apply(xd, scale, shift, 0.1, B, C, S, want_y=True)
+    close(yk, y, 1e-4, 'bn y'); close(pk, pooled, 1e-4, 'bn pooled')
+    dx, red = ops.bn_bwd(xd, mean, rstd, scale, shift, 0.1, None, dev(dpool), B, C, S)
+    close(dx, x.grad, 1e-3, 'bn dx')
+    close(red[:, 1].float(), w.grad, 1e-3, 'bn dweight'); close(red[:, 0].float(), b.grad, 1e-3, 'bn dbias')
+
+
+# ----------------------------------------------------------------------------- conv pieces
+def test_dwconv(ops):
+    B, H, W, C = 2, 16, 16, 40
+    u1 = gen(B, H * W, C).requires_grad_(True)
+    w, b = (gen(C, 1, 3, 3, seed=1) * 0.3).requires_grad_(True), gen(C, seed=2).requires_grad_(True)
+    dh2 = gen(B, H * W, C, seed=3)
+    h1 = F.gelu(u1)
+    u2 = F.conv2d(h1.transpose(1, 2).reshape(B, C, H, W), w, b, padding=1, groups=C).flatten(2).transpose(1, 2)
+    h2 = F.gelu(u2)
+    h2.backward(dh2)
+    h1d = dev(h1.detach())
+    u2k, h2k = ops.dwconv_fwd(h1d, dev(w.detach()), dev(b.detach()), B, H, W, C)
+    close(u2k, u2, 1e-5, 'dw u2'); close(h2k, h2, 1e-5, 'dw h2')
+    du2 = ops.act_bwd(dev(dh2), u2k, ops.ACT_GELU)
+    dw, db = torch.zeros(C, 1, 3, 3, device='cuda'), torch.zeros(C, device='cuda')
+    du1 = ops.dwconv_bwd(du2, h1d, dev(u1.detach()), dev(w.detach()), dw, db, B, H, W, C)
+    close(du1, u1.grad, 1e-4, 'dw du1'); close(dw, w.grad, 1e-4, 'dw dw'); close(db, b.grad, 1e-4, 'dw db')
+
+
+@pytest.mark.parametrize('C,k,s,p', [(8, 4, 2, 1), (12, 3, 1, 1), (3, 3, 1, 1)])
+def test_im2col_col2im(ops, C, k, s, p):
+    B, H, W = 2, 16, 16
+    x = gen(B, C, H, W)
+    tok = x.flatten(2).transpose(1, 2).contiguous()
+    col = ops.im2col(dev(tok), B, H, W, C, k, k, s, p)
+    ref = F.unfold(x, k, padding=p, stride=s)                       # [B, C*k*k, L] with (c, ky, kx) order
+    L = ref.shape[-1]
+    ref = ref.view(B, C, k * k, L).permute(0, 3, 2, 1).reshape(B * L, k * k * C)
+    close(col, ref, 1e-6, 'im2col')
+    col2 = ops.im2col(dev(x), B, H, W, C, k, k, s, p, nchw_in=True)
+    close(col2, ref, 1e-6, 'im2col nchw')
+    g = gen(*ref.shape, seed=5)
+    dx = ops.col2im(dev(g), B, H, W, C, k, k, s, p)
+    gref = g.view(B, L, k * k, C).permute(0, 3, 2, 1).reshape(B, C * k * k, L)
+    dref = F.fold(gref, (H, W), k, padding=p, stride=s).flatten(2).transpose(1, 2)
+    close(dx, dref, 1e-5, 'col2im')
+
+
+def test_pixel_shuffle_and_layout(ops):
+    B, H, W, Ci, Co = 2, 4, 4, 16, 8
+    x = gen(B, H * W, Ci)
+    w, b = gen(Ci, Co, 2, 2, seed=1), gen(Co, seed=2)
+    ref = F.conv_transpose2d(x.transpose(1, 2).reshape(B, Ci, H, W), w, b, stride=2).flatten(2).transpose(1, 2)
+    wk = w.permute(2, 3, 1, 0).reshape(4 * Co, Ci).contiguous()     # [(ky,kx,co), ci]
+    g = torch.empty(B * H * W, 4 * Co, device='cuda')
+    ops.gemm(dev(x.view(-1, Ci)), dev(wk), g, bias=dev(b.repeat(4)), backend=1)
+    y = torch.zeros(B * 4 * H * W, 2 * Co, device='cuda')
+    ops.pixel_shuffle2_fwd(g, y[:, :Co], B, H, W, Co)
+    close(y[:, :Co], ref.reshape(-1, Co), 1e-5, 'deconv via gemm+shuffle')
+    dg = torch.empty_like(g)
+    ops.pixel_shuffle2_bwd(y[:, :Co], dg, B, H, W, Co)
+    close(dg, g, 0, 'shuffle adjoint')
+    t = gen(B, 100, 3)
+    res = gen(B, 3, 100, seed=7)
+    close(ops.tokens_to_nchw(dev(t), dev(res), B, 100, 3), t.transpose(1, 2) + res, 1e-6, 'tokens->nchw')
+    xx = gen(B, 64, 77)
+    close(ops.nchw_to_tokens(dev(xx), B, 77, 64), xx.transpose(1, 2), 0, 'nchw->tokens')
+    a, bb = gen(50, 24), gen(50, 24, seed=3)
+    dst = torch.zeros(50, 48, device='cuda')
+    ops.copy2d(dev(a), dst[:, 24:]); ops.add2d(dev(a), dev(bb), dst[:, :24])
+    close(dst, torch.cat([a + bb, a], 1), 0, 'copy/add 2d')
+
+
+# ----------------------------------------------------------------------------- K1 band filter
+def _bob(kind, size, n):
+    return freq.band_index_map(kind, size, n, n)[:, :n // 2 + 1].to(torch.uint8).contiguous()
+
+
+@pytest.mark.parametrize('kind,size,n', [('frequency_decompose_1', 0.5, 64), ('frequency_decompose', 0.25, 64),
+                                         ('frequency_decompose_1', 0.5, 128), ('frequency_decompose', 0.125, 32),
+                                         ('frequency_decompose_1', 1.0, 16), ('frequency_decompose', 0.5, 8)])
+def test_band_split(ops, kind, size, n):
+    x = torch.rand(3, 2, n, n, generator=torch.Generator().manual_seed(n))
+    nb = freq.num_bands(kind, size)
+    y = ops.band_split(dev(x), dev(_bob(kind, size, n)), nb, 0)
+    close(y, freq.decompose(x, kind, size, True), 2e-5, f'band_split {kind} {n}')
+    if n != 64:
+        ys = ops.band_split(dev(x), dev(_bob(kind, size, n)), nb, 1)
+        close(ys, freq.decompose(x, kind, size, False), 2e-5, f'band spectrum {kind} {n}')
+
+
+@pytest.mark.parametrize('n', [64, 32])
+def test_band_filter_and_energy(ops, n):
+    B, nW, heads, nb = 2, 3, 2, 3
+    x = torch.rand(B * nW, heads, n, n, generator=torch.Generator().manual_seed(3)).softmax(-1)
+    coef = gen(B, heads, nb) * 0.5
+    bob = dev(_bob('frequency_decompose_1', 0.5, n))
+    y = ops.band_filter(dev(x), bob, dev(coef), nW * heads, heads)
+    cf = coef.permute(2, 0, 1).repeat_interleave(nW, 1)                 # [nb, B*nW, heads]
+    ref = freq.band_filter(x, 'frequency_decompose_1', 0.5, cf)
+    close(y, ref, 2e-5, 'band_filter')
+    # self-adjoint and coef gradient
+    a = gen(B * nW, heads, n, n, seed=9)
+    xg = x.clone().requires_grad_(True); cg = coef.clone().requires_grad_(True)
+    (freq.band_filter(xg, 'frequency_decompose_1', 0.5, cg.permute(2, 0, 1).repeat_interleave(nW, 1)) * a).sum().backward()
+    close(ops.band_filter(dev(a), bob, dev(coef), nW * heads, heads), xg.grad, 2e-5, 'band_filter adjoint')
+    e = torch.zeros(B, heads, nb, device='cuda')
+    ops.band_energy(dev(a), dev(x), e, bob, nW * heads, heads)
+    close(e, cg.grad, 1e-4, 'band_energy')
+
+
+def test_dc_split(ops):
+    x = gen(5, 3, 64, 64)
+    close(ops.dc_split(dev(x)), freq.decompose(x, 'frequency_decompose_dc', 0.5), 1e-5, 'dc_split')
+
+
+# ----------------------------------------------------------------------------- K2 attention
+def ref_win_attn(q, kv, B, H, W, heads, hd, shift, scale, table, coef, nW_img):
+    C = heads * hd
+
+    def win(t):
+        t = t.view(B, H, W, -1)
+        if shift:
+            t = torch.roll(t, (-shift, -shift), (1, 2))
+        return uformer.partition(t).reshape(-1, 64, t.shape[-1])
+    qw, kvw = win(q), win(kv)
+    qh = qw.view(-1, 64, heads, hd).transpose(1, 2)
+    kh = kvw[..., :C].reshape(-1, 64, heads, hd).transpose(1, 2)
+    vh = kvw[..., C:].reshape(-1, 64, heads, hd).transpose(1, 2)
+    attn = (qh * scale) @ kh.transpose(-1, -2)
+    if table is not None:
+        attn = attn + table[uformer.rel_index().view(-1)].view(64, 64, heads).permute(2, 0, 1)
+    if shift:
+        m = uformer.shift_mask(H, W)
+        attn = (attn.view(B, -1, heads, 64, 64) + m[None, :, None]).view(-1, heads, 64, 64)
+    attn = attn.softmax(-1)
+    if coef is not None:
+        cf = coef.permute(2, 0, 1).repeat_interleave(nW_img, 1)
+        attn = freq.band_filter(attn, 'frequency_decompose_1', 0.5, cf)
+    o = (attn @ vh).transpose(1, 2).reshape(-1, 8, 8, C)
+    o = uformer.reverse(o, H, W)
+    if shift:
+        o = torch.roll(o, (shift, shift), (1, 2))
+    return o.reshape(B * H * W, C)
+
+
+@pytest.mark.parametrize('H,heads,hd,shift,use_coef', [(16, 2, 56, 0, True), (16, 1, 56, 4, True), (24, 2, 28, 4, False),
+                                                       (8, 3, 64, 0, True), (16, 2, 56, 4, False)])
+def test_win_attn(ops, H, heads, hd, shift, use_coef):
+    B, W, C, nb = 2, H, heads * hd, 3
+    nW = (H // 8) * (W // 8)
+    T = B * H * W
+    qkv = gen(T, 3 * C, scale=0.5)
+    table = gen(225, heads, seed=1, scale=0.3) if hd != 64 else None
+    coef = torch.cat([torch.zeros(B, heads, 1), gen(B, heads, nb - 1, seed=2) * 0.5], -1) if use_coef else None
+    dO = gen(T, C, seed=3)
+    scale = hd ** -0.5
+    leaves = [qkv.clone().requires_grad_(True)]
+    tb = table.clone().requires_grad_(True) if table is not None else None
+    cf = coef.clone().requires_grad_(True) if coef is not None else None
+    ref = ref_win_attn(leaves[0][:, :C], leaves[0][:, C:], B, H, W, heads, hd, shift, scale, tb, cf, nW)
+    ref.backward(dO)
+    qkvd = dev(qkv)
+    bob = dev(_bob('frequency_decompose_1', 0.5, 64))
+    o = torch.empty(T, C, device='cuda')
+    args = (B, H, W, heads, hd, shift, scale)
+    tbd = dev(table) if table is not None else None
+    cfd = dev(coef) if coef is not None else None
+    ops.win_attn_fwd(qkvd[:, :C], qkvd[:, C:], o, *args, tbd, cfd, heads, bob, nb)
+    close(o, ref, 5e-5, 'win_attn fwd')
+    dqkv = torch.empty(T, 3 * C, device='cuda')
+    dq = torch.empty(T, C, device='cuda'); dkv = torch.empty(T, 2 * C, device='cuda')
+    dtab = torch.zeros(225, heads, device='cuda') if table is not None else None
+    dcf = torch.zeros(B, heads, nb, device='cuda') if coef is not None else None
+    ops.win_attn_bwd(qkvd[:, :C], qkvd[:, C:], dev(dO), dq, dkv, *args, tbd, dtab, cfd, heads, dcf, bob, nb)
+    g = leaves[0].grad
+    close(dq, g[:, :C], 2e-4, 'win_attn dq'); close(dkv, g[:, C:], 2e-4, 'win_attn dkv')
+    if table is not None:
+        close(dtab, tb.grad, 2e-4, 'win_attn dtable')
+    if coef is not None:
+        close(dcf[..., 1:], cf.grad[..., 1:], 5e-4, 'win_attn dcoef')
+
+
+@pytest.mark.parametrize('H,heads,shift,kind,L', [(16, 2, 0, 'intra', 3), (16, 1, 4, 'inter', 3), (8, 2, 0, 'inter', 2)])
+def test_joint_attn(ops, H, heads, shift, kind, L):
+    B, W, hd = 2, H, 28
+    C = heads * hd
+    T = L * B * H * W
+    qkv = gen(T, 3 * C, scale=0.5).requires_grad_(True)
+    tables = (gen(L * L, 225, heads, seed=1) * 0.3).requires_grad_(True)
+    dO = gen(T, C, seed=3)
+    # reference: the oracle's joint attention core on the gathered windows
+    def win(t):
+        t = t.view(L * B, H, W, -1)
+        if shift:
+            t = torch.roll(t, (-shift, -shift), (1, 2))
+        return uformer.partition(t).reshape(-1, 64, t.shape[-1])
+
+    def heads_of(t):
+        return t.reshape(t.shape[0], 64, heads, hd).permute(0, 2, 1, 3)
+    w = win(qkv)
+    mask = uformer.shift_mask(H, W) if shift else None
+    a = uformer.joint_attention_core(heads_of(w[..., :C]), heads_of(w[..., C:2 * C]), heads_of(w[..., 2 * C:]),
+                                     [tables[i] for i in range(L * L)], mask, L, kind)
+    a = a.transpose(1, 2).reshape(-1, 64, C)
+    ref = uformer.reverse(a.view(-1, 8, 8, C), H, W)
+    if shift:
+        ref = torch.roll(ref, (shift, shift), (1, 2))
+    ref = ref.reshape(T, C)
+    ref.backward(dO)
+    qd = dev(qkv.detach())
+    o = torch.empty(T, C, device='cuda')
+    kd = 0 if kind == 'intra' else 1
+    td = dev(tables.detach())
+    ops.joint_attn_fwd(qd[:, :C], qd[:, C:], o, L, B, H, W, heads, hd, shift, hd ** -0.5, td, kd)
+    close(o, ref, 5e-5, 'joint fwd')
+    dq = torch.empty(T, C, device='cuda'); dkv = torch.empty(T, 2 * C, device='cuda')
+    dt = torch.zeros_like(td)
+    ops.joint_attn_bwd(qd[:, :C], qd[:, C:], dev(dO), dq, dkv, L, B, H, W, heads, hd, shift, hd ** -0.5, td, dt, kd)
+    close(dq, qkv.grad[:, :C], 2e-4, 'joint dq'); close(dkv, qkv.grad[:, C:], 2e-4, 'joint dkv')
+    close(dt, tables.grad, 2e-4, 'joint dtables')
+
+
+# ----------------------------------------------------------------------------- DGRN pieces
+def test_dcn(ops):
+    B, H, W, C, Co = 2, 12, 10, 8, 6
+    x = gen(B, C, H, W).requires_grad_(True)
+    om = (gen(B, 27, H, W, seed=1) * 1.5).requires_grad_(True)
+    w = gen(Co, C, 3, 3, seed=2).requires_grad_(True)
+    dout = gen(B, Co, H, W, seed=3)
+    o1, o2, m = torch.chunk(om, 3, 1)
+    ref = airnet.modulated_deform_conv2d(x, torch.cat((o1, o2), 1), torch.sigmoid(m), w)
+    ref.backward(dout)
+    xt = dev(x.detach().flatten(2).transpose(1, 2))
+    omt = dev(om.detach().flatten(2).transpose(1, 2))
+    col = ops.dcn_im2col(xt, omt, B, H, W, C)
+    wk = dev(w.detach().permute(0, 2, 3, 1).reshape(Co, 9 * C))
+    out = torch.empty(B * H * W, Co, device='cuda')
+    ops.gemm(col, wk, out, backend=1)
+    close(out.view(B, H * W, Co).transpose(1, 2).reshape(B, Co, H, W), ref, 1e-4, 'dcn fwd')
+    dot = dev(dout.flatten(2).transpose(1, 2).reshape(-1, Co))
+    dcol = torch.empty_like(col)
+    ops.gemm(dot, wk, dcol, transB=False, backend=1)
+    dx, dom = ops.dcn_col2im(xt, omt, dcol, B, H, W, C)
+    close(dx.transpose(1, 2).reshape(B, C, H, W), x.grad, 2e-4, 'dcn dx')
+    close(dom.transpose(1, 2).reshape(B, 27, H, W), om.grad, 2e-3, 'dcn dom')
+
+
+def test_sft_fuse(ops):
+    n = 5000
+    x, d, g, b, do = (gen(n, seed=i).requires_grad_(True) for i in range(5))
+    out = F.leaky_relu(x + d + x * g + b, 0.1)
+    out.backward(do.detach())
+    xs = [dev(t.detach()) for t in (x, d, g, b)]
+    close(ops.sft_fuse_fwd(*xs, 0.1), out, 1e-6, 'sft fwd')
+    grads = ops.sft_fuse_bwd(*xs, dev(do.detach()), 0.1)
+    for k, t in zip(grads, (x, d, g, b)):
+        close(k, t.grad, 1e-6, 'sft bwd')
+
+
+# ----------------------------------------------------------------------------- elementwise / optimiser
+def test_act_l1_momentum_adam(ops):
+    n = 10007
+    x, dy = gen(n), gen(n, seed=1)
+    for act, fn in ((ops.ACT_GELU, F.gelu), (ops.ACT_LRELU, lambda t: F.leaky_relu(t, 0.1))):
+        xr = x.clone().requires_grad_(True)
+        fn(xr).backward(dy)
+        close(ops.act_fwd(dev(x), act, 0.1), fn(x), 1e-6, 'act fwd'); close(ops.act_bwd(dev(dy), dev(x), act, 0.1), xr.grad, 1e-5, 'act bwd')
+    a, b = gen(n, seed=2), gen(n, seed=3)
+    loss, grad = ops.l1_loss(dev(a), dev(b))
+    close(loss, (a - b).abs().mean().view(1), 1e-5, 'l1'); close(grad, torch.sign(a - b) / n, 1e-6, 'l1 grad')
+    k, q = dev(a), dev(b)
+    ops.momentum_update(k, q, 0.999)
+    close(k, a * 0.999 + b * (1 - 0.999), 1e-6, 'momentum')
+    p, g = gen(n, seed=4), gen(n, seed=5) * 0.01
+    m, v = torch.zeros(n), torch.zeros(n)
+    pd, md, vd = dev(p), dev(m), dev(v)
+    for step in (1, 2, 3):
+        p, m, v = airnet.adam_step(p, g, m, v, step, 2e-4)
+        ops.adam_step(pd, dev(g), md, vd, 2e-4, 0.9, 0.999, 1e-8, step)
+    close(pd, p, 1e-6, 'adam p'); close(vd, v, 1e-5, 'adam v')
+    # against torch.optim.Adam itself
+    pt = torch.nn.Parameter(gen(n, seed=4).clone())
+    opt = torch.optim.Adam([pt], lr=2e-4)
+    for _ in range(3):
+        pt.grad = g.clone()
+        opt.step()
+    close(pd, pt.detach(), 1e-6, 'adam vs torch.optim')
