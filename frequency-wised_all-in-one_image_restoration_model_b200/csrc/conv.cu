@@ -236,12 +236,14 @@ __global__ void __launch_bounds__(256) pixshuf_kernel(const float* __restrict__ 
 // ------------------------------------------------------------------ strided copy / add
 __global__ void __launch_bounds__(256) copy2d_kernel(const float* __restrict__ a, int64_t lda,
                                                      const float* __restrict__ b, int64_t ldb, float* __restrict__ d,
-                                                     int64_t ldd, int64_t rows, int cols) {
+                                                     int64_t ldd, int64_t rows, int cols,
+                                                     const float* __restrict__ rowscale, int rps) {
   const int64_t total = rows * cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cols;
     const int c = (int)(i % cols);
     float v = a[r * lda + c];
+    if (rowscale) v *= rowscale[r / rps];
     if (b) v += b[r * ldb + c];
     d[r * ldd + c] = v;
   }
@@ -371,7 +373,7 @@ int fa_copy2d(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t ro
   cudaStream_t st = (cudaStream_t)stream;
   FaProfScope prof(FA_K_ELEMWISE, st);
   if (rows * cols == 0) return FA_OK;
-  copy2d_kernel<<<ew_grid(rows * cols), 256, 0, st>>>(src, lds, nullptr, 0, dst, ldd, rows, cols);
+  copy2d_kernel<<<ew_grid(rows * cols), 256, 0, st>>>(src, lds, nullptr, 0, dst, ldd, rows, cols, nullptr, 1);
   FA_LAUNCH_CHECK("fa_copy2d");
   return FA_OK;
 }
@@ -382,8 +384,19 @@ int fa_add2d(const float* a, int64_t lda, const float* b, int64_t ldb, float* ds
   cudaStream_t st = (cudaStream_t)stream;
   FaProfScope prof(FA_K_ELEMWISE, st);
   if (rows * cols == 0) return FA_OK;
-  copy2d_kernel<<<ew_grid(rows * cols), 256, 0, st>>>(a, lda, b, ldb, dst, ldd, rows, cols);
+  copy2d_kernel<<<ew_grid(rows * cols), 256, 0, st>>>(a, lda, b, ldb, dst, ldd, rows, cols, nullptr, 1);
   FA_LAUNCH_CHECK("fa_add2d");
+  return FA_OK;
+}
+
+int fa_scale_rows(const float* src, const float* rowscale, int rows_per_scale, float* dst, int64_t rows, int cols,
+                  fa_stream_t stream) {
+  FA_REQUIRE(src && dst && rowscale && rows_per_scale > 0, "fa_scale_rows: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_ELEMWISE, st);
+  if (rows * cols == 0) return FA_OK;
+  copy2d_kernel<<<ew_grid(rows * cols), 256, 0, st>>>(src, cols, nullptr, 0, dst, cols, rows, cols, rowscale, rows_per_scale);
+  FA_LAUNCH_CHECK("fa_scale_rows");
   return FA_OK;
 }
 

@@ -247,6 +247,121 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
   }
 }
 
+// ---------------------------------------------------------------- BatchNorm on tokens [T, C] (NHWC)
+// block = 32 channels x 8 row lanes; rows_per_block rows per block; double atomics on the [C][2] result.
+__global__ void __launch_bounds__(256) bnt_stats_kernel(const float* __restrict__ x, double* __restrict__ sums,
+                                                        int64_t T, int C, int rows_per_block) {
+  __shared__ float ra[8][33], rq[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(T, r0 + rows_per_block);
+  float a = 0.f, q = 0.f;
+  if (c < C)
+    for (int64_t r = r0 + ty; r < r1; r += 8) { const float v = x[r * C + c]; a += v; q += v * v; }
+  ra[ty][tx] = a; rq[ty][tx] = q;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float sa = 0.f, sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sa += ra[i][tx]; sq += rq[i][tx]; }
+    atomicAdd(&sums[2 * c], (double)sa);
+    atomicAdd(&sums[2 * c + 1], (double)sq);
+  }
+}
+
+// y = act(x*scale[c] + shift[c] + res)
+__global__ void __launch_bounds__(256) bnt_apply_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                        const float* __restrict__ shift,
+                                                        const float* __restrict__ res, float slope,
+                                                        float* __restrict__ y, int64_t total, int C) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    float z = x[i] * scale[c] + shift[c];
+    if (res) z += res[i];
+    y[i] = z > 0.f ? z : z * slope;
+  }
+}
+
+// g = dy * act'(y);  red[c] += {sum g, sum g*xhat}
+__global__ void __launch_bounds__(256) bnt_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd,
+                                                             const float* __restrict__ yout, float slope,
+                                                             const float* __restrict__ dy, double* __restrict__ red,
+                                                             int64_t T, int C, int rows_per_block) {
+  __shared__ float ra[8][33], rq[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(T, r0 + rows_per_block);
+  float a = 0.f, q = 0.f;
+  if (c < C) {
+    const float mu = mean[c], rs = rstd[c];
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      const int64_t i = r * C + c;
+      float g = dy[i];
+      if (yout && !(yout[i] > 0.f)) g *= slope;
+      a += g;
+      q += g * (x[i] - mu) * rs;
+    }
+  }
+  ra[ty][tx] = a; rq[ty][tx] = q;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float sa = 0.f, sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sa += ra[i][tx]; sq += rq[i][tx]; }
+    atomicAdd(&red[2 * c], (double)sa);
+    atomicAdd(&red[2 * c + 1], (double)sq);
+  }
+}
+
+__global__ void __launch_bounds__(256) bnt_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd,
+                                                            const float* __restrict__ scale,
+                                                            const float* __restrict__ yout, float slope,
+                                                            const float* __restrict__ dy, const double* __restrict__ red,
+                                                            float* __restrict__ dx, float* __restrict__ dres,
+                                                            int64_t T, int C) {
+  const int64_t total = T * C;
+  const double n = (double)T;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    float g = dy[i];
+    if (yout && !(yout[i] > 0.f)) g *= slope;
+    if (dres) dres[i] = g;
+    const float xh = (x[i] - mean[c]) * rstd[c];
+    const float r0 = red ? (float)(red[2 * c] / n) : 0.f, r1 = red ? (float)(red[2 * c + 1] / n) : 0.f;
+    dx[i] = scale[c] * (g - r0 - xh * r1);
+  }
+}
+
+// out[b][c] = mean_t x[b][t][c]   /   dx[b][t][c] = dy[b][c] / HW
+__global__ void __launch_bounds__(256) token_mean_kernel(const float* __restrict__ x, float* __restrict__ out, int HW,
+                                                         int C) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int b = blockIdx.y;
+  float a = 0.f;
+  if (c < C)
+    for (int t = ty; t < HW; t += 8) a += x[((int64_t)b * HW + t) * C + c];
+  red[ty][tx] = a;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][tx];
+    out[(int64_t)b * C + c] = s / (float)HW;
+  }
+}
+__global__ void __launch_bounds__(256) token_mean_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx,
+                                                             int64_t total, int HW, int C) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t b = i / ((int64_t)HW * C);
+    dx[i] = dy[b * C + c] / (float)HW;
+  }
+}
+
 int ln_grid(int64_t rows) {
   int64_t blocks = (rows + 7) / 8;
   int64_t cap = (int64_t)kNumSMs * 8;
@@ -353,6 +468,77 @@ int fa_bn_bwd_apply(const float* x, const float* mean, const float* rstd, const 
   bn_bwd_apply_kernel<<<(unsigned)((int64_t)B * C), 256, 0, st>>>(x, mean, rstd, scale, shift, slope, dy, dpooled,
                                                                   red, dx, B, C, S);
   FA_LAUNCH_CHECK("fa_bn_bwd_apply");
+  return FA_OK;
+}
+
+static void bnt_grid(int64_t T, int C, dim3& grid, int& rpb) {
+  const int cb = (C + 31) / 32;
+  int rb = (4 * kNumSMs + cb - 1) / cb;
+  rpb = (int)((T + rb - 1) / rb);
+  if (rpb < 64) rpb = 64;
+  rb = (int)((T + rpb - 1) / rpb);
+  grid = dim3(cb, rb);
+}
+static int ew_blocks(int64_t total) {
+  int64_t b = (total + 255) / 256;
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  return (int)(b > cap ? cap : (b > 0 ? b : 1));
+}
+
+int fa_bn_tokens_stats(const float* x, double* sums, int64_t T, int C, fa_stream_t stream) {
+  FA_REQUIRE(x && sums && T > 0 && C > 0, "fa_bn_tokens_stats: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_BN, st);
+  dim3 grid; int rpb;
+  bnt_grid(T, C, grid, rpb);
+  bnt_stats_kernel<<<grid, 256, 0, st>>>(x, sums, T, C, rpb);
+  FA_LAUNCH_CHECK("fa_bn_tokens_stats");
+  return FA_OK;
+}
+
+int fa_bn_tokens_apply(const float* x, const float* scale, const float* shift, const float* res, float slope, float* y,
+                       int64_t T, int C, fa_stream_t stream) {
+  FA_REQUIRE(x && scale && shift && y && T > 0 && C > 0, "fa_bn_tokens_apply: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_BN, st);
+  bnt_apply_kernel<<<ew_blocks(T * C), 256, 0, st>>>(x, scale, shift, res, slope, y, T * C, C);
+  FA_LAUNCH_CHECK("fa_bn_tokens_apply");
+  return FA_OK;
+}
+
+int fa_bn_tokens_bwd(const float* x, const float* mean, const float* rstd, const float* scale, const float* yout,
+                     float slope, const float* dy, double* red, float* dx, float* dres, int64_t T, int C, int training,
+                     fa_stream_t stream) {
+  FA_REQUIRE(x && mean && rstd && scale && dy && red && dx && T > 0 && C > 0, "fa_bn_tokens_bwd: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_BN, st);
+  dim3 grid; int rpb;
+  bnt_grid(T, C, grid, rpb);
+  bnt_bwd_reduce_kernel<<<grid, 256, 0, st>>>(x, mean, rstd, yout, slope, dy, red, T, C, rpb);
+  FA_LAUNCH_CHECK("fa_bn_tokens_bwd(reduce)");
+  fa_count_launch(FA_K_BN);
+  bnt_bwd_apply_kernel<<<ew_blocks(T * C), 256, 0, st>>>(x, mean, rstd, scale, yout, slope, dy, training ? red : nullptr,
+                                                        dx, dres, T, C);
+  FA_LAUNCH_CHECK("fa_bn_tokens_bwd(apply)");
+  return FA_OK;
+}
+
+int fa_token_mean_fwd(const float* x, float* out, int B, int HW, int C, fa_stream_t stream) {
+  FA_REQUIRE(x && out && B > 0 && HW > 0 && C > 0, "fa_token_mean_fwd: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_ELEMWISE, st);
+  token_mean_kernel<<<dim3((C + 31) / 32, B), 256, 0, st>>>(x, out, HW, C);
+  FA_LAUNCH_CHECK("fa_token_mean_fwd");
+  return FA_OK;
+}
+
+int fa_token_mean_bwd(const float* dy, float* dx, int B, int HW, int C, fa_stream_t stream) {
+  FA_REQUIRE(dy && dx && B > 0 && HW > 0 && C > 0, "fa_token_mean_bwd: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_ELEMWISE, st);
+  const int64_t total = (int64_t)B * HW * C;
+  token_mean_bwd_kernel<<<ew_blocks(total), 256, 0, st>>>(dy, dx, total, HW, C);
+  FA_LAUNCH_CHECK("fa_token_mean_bwd");
   return FA_OK;
 }
 

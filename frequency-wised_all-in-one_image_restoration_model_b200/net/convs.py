@@ -1,0 +1,198 @@
+"""Dense convolutions of the Uformer path as autograd nodes over libfreqair kernels.
+
+All of them keep activations in token layout [B, H*W, C] (NHWC), so the NCHW<->NLC transposes the
+reference performs around every conv (decoder_Uformer.py:428-429,447-448,469,495) disappear: a conv is
+a patch gather (fa_im2col) + GEMM with the bias / LeakyReLU epilogue, ConvTranspose 2x2 s2 is a GEMM +
+pixel shuffle written straight into the skip-concat buffer.
+Weights are consumed as [Cout, (ky,kx,ci)] matrices; the permutation from the reference's
+[Cout,Cin,kh,kw] parameter layout is a tiny host-side view+copy that autograd differentiates.
+"""
+import torch
+
+from .. import ops
+from .lewin import _z
+
+
+class InputProjFn(torch.autograd.Function):
+    """Conv2d 3x3 s1 p1 on an NCHW image + LeakyReLU -> tokens (InputProj, decoder_Uformer.py:453-472)."""
+
+    @staticmethod
+    def forward(ctx, x, wk, b, slope):
+        B, Ci, H, W = x.shape
+        col = ops.im2col(x.contiguous(), B, H, W, Ci, 3, 3, 1, 1, nchw_in=True)
+        y = torch.empty(B * H * W, wk.shape[0], device=x.device, dtype=torch.float32)
+        ops.gemm(col, wk, y, bias=b, act=ops.ACT_LRELU, act_param=slope)
+        ctx.save_for_backward(col, y)
+        ctx.slope = slope
+        ctx.wshape = wk.shape
+        return y.view(B, H * W, -1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        col, y = ctx.saved_tensors
+        g = ops.act_bwd(dy.reshape(y.shape).contiguous(), y, ops.ACT_LRELU, ctx.slope)
+        dW = torch.zeros(ctx.wshape, device=g.device)
+        db = torch.empty(ctx.wshape[0], device=g.device)
+        ops.colsum(g, db)
+        ops.gemm(g, col, dW, transA=True, transB=False, accumulate=True)
+        return None, dW, db, None          # the input image never needs a gradient on this path
+
+
+class DownsampleFn(torch.autograd.Function):
+    """Conv2d k x k, stride s, pad p on tokens (Downsample 4x4 s2 p1, decoder_Uformer.py:414-430; also the
+    generic token conv used by DGRN / ResNet 3x3 s1 p1)."""
+
+    @staticmethod
+    def forward(ctx, x, wk, b, H, W, k, s, p, act, act_param):
+        B, _, C = x.shape
+        col = ops.im2col(x.contiguous(), B, H, W, C, k, k, s, p)
+        y = torch.empty(col.shape[0], wk.shape[0], device=x.device, dtype=torch.float32)
+        ops.gemm(col, wk, y, bias=b, act=act, act_param=act_param)
+        ctx.geom = (B, H, W, C, k, s, p, act, act_param)
+        ctx.has_bias = b is not None
+        ctx.save_for_backward(col, wk, y if act != ops.ACT_NONE else None)
+        return y.view(B, -1, wk.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        col, wk, y = ctx.saved_tensors
+        B, H, W, C, k, s, p, act, act_param = ctx.geom
+        g = dy.reshape(-1, wk.shape[0]).contiguous()
+        if act != ops.ACT_NONE:
+            g = ops.act_bwd(g, y, act, act_param)      # LeakyReLU only: sign(out) == sign(pre)
+        dW = _z(wk)
+        db = torch.empty(wk.shape[0], device=g.device) if ctx.has_bias else None
+        if db is not None:
+            ops.colsum(g, db)
+        ops.gemm(g, col, dW, transA=True, transB=False, accumulate=True)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dcol = torch.empty_like(col)
+            ops.gemm(g, wk, dcol, transB=False)
+            dx = ops.col2im(dcol, B, H, W, C, k, k, s, p)
+        return dx, dW, db, None, None, None, None, None, None, None
+
+
+class UpsampleCatFn(torch.autograd.Function):
+    """ConvTranspose2d k2 s2 on tokens, concatenated with the skip tensor along channels
+    (Upsample decoder_Uformer.py:434-449 + torch.cat :1162) -> [B, 4*H*W, Co + Cs]."""
+
+    @staticmethod
+    def forward(ctx, x, wk, b4, skip, H, W):
+        B, _, Ci = x.shape
+        Co = wk.shape[0] // 4
+        Cs = skip.shape[-1]
+        x2 = x.reshape(-1, Ci).contiguous()
+        g = torch.empty(x2.shape[0], 4 * Co, device=x.device, dtype=torch.float32)
+        ops.gemm(x2, wk, g, bias=b4)
+        out = torch.empty(B * 4 * H * W, Co + Cs, device=x.device, dtype=torch.float32)
+        ops.pixel_shuffle2_fwd(g, out[:, :Co], B, H, W, Co)
+        ops.copy2d(skip.reshape(-1, Cs), out[:, Co:])
+        ctx.geom = (B, H, W, Ci, Co, Cs)
+        ctx.save_for_backward(x2, wk)
+        return out.view(B, 4 * H * W, Co + Cs)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, wk = ctx.saved_tensors
+        B, H, W, Ci, Co, Cs = ctx.geom
+        d2 = dout.reshape(-1, Co + Cs).contiguous()
+        dg = torch.empty(B * H * W, 4 * Co, device=d2.device, dtype=torch.float32)
+        ops.pixel_shuffle2_bwd(d2[:, :Co], dg, B, H, W, Co)
+        dskip = torch.empty(B * 4 * H * W, Cs, device=d2.device, dtype=torch.float32)
+        ops.copy2d(d2[:, Co:], dskip)
+        dW, db4 = _z(wk), torch.empty(4 * Co, device=d2.device)
+        ops.colsum(dg, db4)
+        ops.gemm(dg, x2, dW, transA=True, transB=False, accumulate=True)
+        dx = torch.empty_like(x2)
+        ops.gemm(dg, wk, dx, transB=False)
+        return dx.view(B, H * W, Ci), dW, db4, dskip.view(B, 4 * H * W, Cs), None, None
+
+
+class OutputProjFn(torch.autograd.Function):
+    """Conv2d 3x3 s1 p1 tokens -> NCHW image, plus the global residual x + y
+    (OutputProj decoder_Uformer.py:476-499 and :1171)."""
+
+    @staticmethod
+    def forward(ctx, t, wk, b, ximg, H, W):
+        B, _, C = t.shape
+        col = ops.im2col(t.contiguous(), B, H, W, C, 3, 3, 1, 1)
+        Co = wk.shape[0]
+        y = torch.empty(B * H * W, Co, device=t.device, dtype=torch.float32)
+        ops.gemm(col, wk, y, bias=b)
+        out = ops.tokens_to_nchw(y, ximg.contiguous().view(B, Co, H * W) if ximg is not None else None, B, H * W, Co)
+        ctx.geom = (B, H, W, C, Co)
+        ctx.save_for_backward(col, wk)
+        return out.view(B, Co, H, W)
+
+    @staticmethod
+    def backward(ctx, dout):
+        col, wk = ctx.saved_tensors
+        B, H, W, C, Co = ctx.geom
+        g = ops.nchw_to_tokens(dout.contiguous(), B, H * W, Co).view(-1, Co)
+        dW, db = _z(wk), torch.empty(Co, device=g.device)
+        ops.colsum(g, db)
+        ops.gemm(g, col, dW, transA=True, transB=False, accumulate=True)
+        dcol = torch.empty_like(col)
+        ops.gemm(g, wk, dcol, transB=False)
+        dt = ops.col2im(dcol, B, H, W, C, 3, 3, 1, 1)
+        return dt, dW, db, (dout if ctx.needs_input_grad[3] else None), None, None
+
+
+def conv_weight_matrix(w):
+    """[Co, Ci, kh, kw] -> [Co, (ky, kx, ci)]"""
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+
+
+def deconv_weight_matrix(w):
+    """ConvTranspose2d weight [Ci, Co, 2, 2] -> [(ky, kx, co), ci]"""
+    return w.permute(2, 3, 1, 0).reshape(-1, w.shape[0])
+
+
+class BNHeadFn(torch.autograd.Function):
+    """BatchNorm2d -> LeakyReLU(0.1) -> global average pool on a [B, C, S] view
+    (encoder_Uformer.py:980-982, encoder_ViT.py:197-199; encoder_ResNet.py's final pool).
+    Returns pooled [B, C] (and the activated map when ``want_map``).  Training mode uses batch statistics
+    and updates the running buffers in place (momentum 0.1, unbiased variance), eval mode the buffers."""
+
+    @staticmethod
+    def forward(ctx, y, weight, bias, running_mean, running_var, training, slope, want_map):
+        B, C, S = y.shape
+        y = y.contiguous()
+        if training:
+            sums = ops.bn_stats(y, B, C, S)
+            n = B * S
+            mean64 = sums[:, 0] / n
+            var64 = (sums[:, 1] / n - mean64 * mean64).clamp_min_(0)
+            mean, var = mean64.float(), var64.float()
+            with torch.no_grad():
+                running_mean.mul_(0.9).add_(0.1 * mean)
+                running_var.mul_(0.9).add_(0.1 * var * (n / max(n - 1, 1)))
+        else:
+            mean, var = running_mean, running_var
+        rstd = torch.rsqrt(var + 1e-5)
+        scale = weight * rstd
+        shift = bias - mean * scale
+        act, pooled = ops.bn_apply(y, scale, shift, slope, B, C, S, want_y=want_map, want_pool=True)
+        ctx.geom = (B, C, S, slope, training, want_map)
+        ctx.save_for_backward(y, mean, rstd, scale, shift)
+        if want_map:
+            return pooled, act
+        return pooled, None
+
+    @staticmethod
+    def backward(ctx, dpooled, dmap):
+        y, mean, rstd, scale, shift = ctx.saved_tensors
+        B, C, S, slope, training, want_map = ctx.geom
+        if dmap is not None and dpooled is not None:
+            dy_in = (dmap + (dpooled / S).unsqueeze(-1)).contiguous()   # host-side combine of the two consumers
+            dp_in = None
+        elif dmap is not None:
+            dy_in, dp_in = dmap.contiguous(), None
+        else:
+            dy_in, dp_in = None, dpooled.contiguous()
+        # d/dweight, d/dbias always come from the full reduction, also in eval mode
+        dx, red = ops.bn_bwd(y, mean, rstd, scale, shift, slope, dy_in, dp_in, B, C, S, training=True)
+        if not training:
+            dx, _ = ops.bn_bwd(y, mean, rstd, scale, shift, slope, dy_in, dp_in, B, C, S, training=False)
+        return dx, red[:, 1].float(), red[:, 0].float(), None, None, None, None, None

@@ -1,0 +1,218 @@
+"""UformerDecoder - drop-in for the reference's net/decoder_Uformer.py (class name, ``__init__(opt)``,
+``forward(x, inter) -> restored`` and every state_dict key), running on libfreqair kernels.
+
+Supported configuration = what runs at reference HEAD:
+``opt.degradation_embedding_method`` in {['all_<n>_bands'], ['all_DC']}, ``opt.frequency_decompose_type ==
+'none'``, ``opt.learnable_modulator`` False, ``opt.debug_mode`` False.  Anything else raises (the reference
+itself crashes on those: decoder_Uformer.py:155,1124,1148), never a silent fallback.
+
+Per LeWin block the band re-weighting of the post-softmax attention map (decoder_Uformer.py:275-288) is
+collapsed to ONE real filter irfft2(rfft2(P) * (1 + sum_i lambda_i M_i)) evaluated in shared memory inside
+the attention kernel; the lambda predictor (:178-193,280-284) is 0.04 GFLOP/crop of [B,448] work and stays
+on the host side of the ABI, with LayerNorm statistics shared across the 44 blocks:
+mean_t(LN_affine(x)) @ W^T == (gamma * mean_t(xhat) + beta) @ W^T.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .lewin import DecoderBlockFn
+from .uformer_parts import (WIN, Downsample, InputProj, LinearProjection, OutputProj, Upsample, draw_drop_path,
+                            init_uformer_weights, leff_params, relative_position_index, trunc_normal_)
+from .utils.frequency_decompose import half_band_map
+from .utils.leff import LeFF
+
+
+class WindowAttention(nn.Module):
+    """Parameter holder + lambda predictor of the decoder's WindowAttention (decoder_Uformer.py:128-233)."""
+
+    def __init__(self, input_resolution, dim, win_size, num_heads, all_degradation_embedding_method=()):
+        super().__init__()
+        self.input_resolution, self.dim, self.win_size, self.num_heads = input_resolution, dim, win_size, num_heads
+        self.num_win = input_resolution[0] // win_size[0] * input_resolution[1] // win_size[1]
+        self.scale = (dim // num_heads) ** -0.5
+        self.num_bands = 0
+        self.band_kind = None
+        for t in all_degradation_embedding_method:
+            if t.split('_')[-1] == 'bands':
+                self.num_bands = int(t.split('_')[-2])
+                self.band_kind = ('frequency_decompose_1', 1. / (self.num_bands - 1))
+            elif t.split('_')[-1] == 'DC':
+                # mean / residual split == {DC bin, every other bin} (frequency_decompose.py:109-118)
+                self.num_bands = 2
+                self.band_kind = ('frequency_decompose_1', 1.0)
+        if self.num_bands:
+            encoder_embed_dim = 28                            # hard-coded upstream, decoder_Uformer.py:176
+            nb = self.num_bands
+            self.mlp_head = nn.ModuleList([nn.Sequential(nn.LayerNorm(encoder_embed_dim * 16),
+                                                         nn.Linear(encoder_embed_dim * 16, num_heads))
+                                           if i > 0 else None for i in range(nb)])
+            self.avg = nn.ModuleList([nn.AdaptiveAvgPool1d(1) if i > 0 else None for i in range(nb)])
+            self.mlp = nn.ModuleList([nn.Sequential(nn.Linear(num_heads, num_heads), nn.LeakyReLU(0.1, True),
+                                                    nn.Linear(num_heads, num_heads))
+                                      if i > 0 else None for i in range(nb)])
+        self.relative_position_bias_table = nn.Parameter(
+            torch.zeros((2 * win_size[0] - 1) * (2 * win_size[1] - 1), num_heads))
+        self.register_buffer('relative_position_index', relative_position_index(win_size[0]))
+        trunc_normal_(self.relative_position_bias_table, std=.02)
+        self.qkv = LinearProjection(dim, num_heads, dim // num_heads, bias=True)
+        self.proj = nn.Linear(dim, dim)
+
+    def band_coefficients(self, inter_stats):
+        """[B, heads, num_bands] filter coefficients (band 0 unused -> 0) from the shared per-band
+        token-mean of the normalised encoder features ``inter_stats[i]`` [B, 448]."""
+        if not self.num_bands:
+            return None
+        cols = [torch.zeros_like(inter_stats[1][:, :1]).expand(-1, self.num_heads)]
+        for i in range(1, self.num_bands):
+            ln, fc = self.mlp_head[i][0], self.mlp_head[i][1]
+            e = F.linear(inter_stats[i] * ln.weight + ln.bias, fc.weight, fc.bias)          # [B, heads]
+            e = self.mlp[i][2](F.leaky_relu(self.mlp[i][0](e), 0.1))
+            cols.append(e)
+        return torch.stack(cols, -1).contiguous()
+
+
+class LeWinTransformerBlock(nn.Module):
+    def __init__(self, dim, input_resolution, num_heads, win_size=8, shift_size=0, mlp_ratio=4., drop_path=0.,
+                 all_degradation_embedding_method=()):
+        super().__init__()
+        self.dim, self.input_resolution, self.num_heads = dim, input_resolution, num_heads
+        self.win_size, self.shift_size, self.mlp_ratio = win_size, shift_size, mlp_ratio
+        if min(input_resolution) <= win_size:
+            self.shift_size = 0
+            self.win_size = min(input_resolution)
+        assert self.win_size == WIN, 'freqair: 8x8 windows only (all reference geometries)'
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn = WindowAttention(input_resolution, dim, (self.win_size, self.win_size), num_heads,
+                                    all_degradation_embedding_method)
+        self.drop_path_prob = float(drop_path)
+        self.drop_path = nn.Identity()                        # kept for attribute parity; scales are drawn in forward
+        self.norm2 = nn.LayerNorm(dim)
+        self.mlp = LeFF(dim, int(dim * mlp_ratio))
+        self.forced_dp = None                                 # tests: (s_attn, s_mlp) per-sample scale vectors
+        self._bob = None
+
+    def _band_map(self, device):
+        if self.attn.band_kind is None:
+            return None
+        if self._bob is None or self._bob.device != device:
+            self._bob = half_band_map(self.attn.band_kind[0], self.attn.band_kind[1], WIN * WIN).to(device)
+        return self._bob
+
+    def forward(self, x, inter=None, inter_kv=None, all_inter=None, mask=None):
+        assert mask is None
+        B, L, C = x.shape
+        H = W = int(math.sqrt(L))
+        coef = self.attn.band_coefficients(all_inter) if all_inter is not None else None
+        if self.forced_dp is not None:
+            dp_a, dp_m = self.forced_dp
+        else:
+            dp_a = draw_drop_path(x, self.drop_path_prob, self.training)
+            dp_m = draw_drop_path(x, self.drop_path_prob, self.training)
+        a = self.attn
+        cfg = (B, H, W, self.num_heads, self.shift_size, self._band_map(x.device) if coef is not None else None,
+               a.num_bands)
+        return DecoderBlockFn.apply(cfg, x, coef, dp_a, dp_m, self.norm1.weight, self.norm1.bias,
+                                    a.relative_position_bias_table, a.qkv.to_q.weight, a.qkv.to_q.bias,
+                                    a.qkv.to_kv.weight, a.qkv.to_kv.bias, a.proj.weight, a.proj.bias,
+                                    self.norm2.weight, self.norm2.bias, *leff_params(self.mlp))
+
+
+class BasicUformerLayer(nn.Module):
+    def __init__(self, dim, input_resolution, depth, num_heads, win_size, mlp_ratio, drop_path,
+                 all_degradation_embedding_method):
+        super().__init__()
+        self.dim, self.input_resolution, self.depth = dim, input_resolution, depth
+        self.blocks = nn.ModuleList([
+            LeWinTransformerBlock(dim=dim, input_resolution=input_resolution, num_heads=num_heads, win_size=win_size,
+                                  shift_size=0 if (i % 2 == 0) else win_size // 2, mlp_ratio=mlp_ratio,
+                                  drop_path=drop_path[i] if isinstance(drop_path, list) else drop_path,
+                                  all_degradation_embedding_method=all_degradation_embedding_method)
+            for i in range(depth)])
+
+    def forward(self, x, inter=None, inter_kv=None, all_inter=None, mask=None):
+        for blk in self.blocks:
+            x = blk(x, inter, inter_kv, all_inter, mask)
+        return x, []
+
+
+class UformerDecoder(nn.Module):
+    def __init__(self, opt, img_size=128, in_chans=3, out_chans=3, depths=[2, 2, 8, 8, 2, 8, 8, 2, 2],
+                 num_heads=[1, 2, 4, 8, 16, 16, 8, 4, 2], win_size=8, mlp_ratio=4., drop_path_rate=0.1, **kwargs):
+        super().__init__()
+        self.opt = opt
+        methods = list(opt.degradation_embedding_method)
+        alls = [t for t in methods if 'all' in t]
+        if getattr(opt, 'debug_mode', False):
+            raise NotImplementedError('freqair: debug_mode (spectrum visualisation) is outside the accelerated path')
+        if getattr(opt, 'frequency_decompose_type', 'none') != 'none':
+            raise NotImplementedError('freqair: the Uformer decoder asserts frequency_decompose_type == none '
+                                      '(reference decoder_Uformer.py:155)')
+        if len(alls) != len(methods) or len(alls) > 1:
+            raise NotImplementedError(f'freqair: degradation_embedding_method={methods} does not run at reference HEAD '
+                                      '(decoder_Uformer.py:1124); use all_<n>_bands or all_DC')
+        if getattr(opt, 'learnable_modulator', False):
+            raise NotImplementedError('freqair: learnable_modulator is not part of the accelerated path')
+        embed_dim = opt.embed_dim
+        self.num_enc_layers = self.num_dec_layers = len(depths) // 2
+        self.embed_dim, self.mlp_ratio, self.win_size, self.reso, self.in_chans = embed_dim, mlp_ratio, win_size, img_size, in_chans
+        self.all_methods = alls
+        self.pos_drop = nn.Dropout(p=0.)
+        enc_dpr = [x.item() for x in torch.linspace(0, drop_path_rate, sum(depths[:self.num_enc_layers]))]
+        conv_dpr = [drop_path_rate] * depths[4]
+        dec_dpr = enc_dpr[::-1]
+
+        def layer(dim_mult, res_div, depth, heads, dpr):
+            return BasicUformerLayer(dim=embed_dim * dim_mult, input_resolution=(img_size // res_div, img_size // res_div),
+                                     depth=depth, num_heads=heads, win_size=win_size, mlp_ratio=mlp_ratio,
+                                     drop_path=dpr, all_degradation_embedding_method=alls)
+        self.input_proj = InputProj(in_channel=in_chans, out_channel=embed_dim, kernel_size=3, stride=1, act_layer=nn.LeakyReLU)
+        self.output_proj = OutputProj(in_channel=2 * embed_dim, out_channel=out_chans, kernel_size=3, stride=1)
+        self.encoderlayer_0 = layer(1, 1, depths[0], num_heads[0], enc_dpr[sum(depths[:0]):sum(depths[:1])])
+        self.dowsample_0 = Downsample(embed_dim, embed_dim * 2)
+        self.encoderlayer_1 = layer(2, 2, depths[1], num_heads[1], enc_dpr[sum(depths[:1]):sum(depths[:2])])
+        self.dowsample_1 = Downsample(embed_dim * 2, embed_dim * 4)
+        self.encoderlayer_2 = layer(4, 4, depths[2], num_heads[2], enc_dpr[sum(depths[:2]):sum(depths[:3])])
+        self.dowsample_2 = Downsample(embed_dim * 4, embed_dim * 8)
+        self.encoderlayer_3 = layer(8, 8, depths[3], num_heads[3], enc_dpr[sum(depths[:3]):sum(depths[:4])])
+        self.dowsample_3 = Downsample(embed_dim * 8, embed_dim * 16)
+        self.bottleneck_0 = layer(16, 16, depths[4], num_heads[4], conv_dpr)
+        self.bottleneck_1 = layer(16, 16, depths[4], num_heads[4], conv_dpr)
+        self.upsample_3 = Upsample(embed_dim * 16, embed_dim * 8)
+        self.decoderlayer_3 = layer(16, 8, depths[5], num_heads[5], dec_dpr[:depths[5]])
+        self.upsample_2 = Upsample(embed_dim * 16, embed_dim * 4)
+        self.decoderlayer_2 = layer(8, 4, depths[6], num_heads[6], dec_dpr[sum(depths[5:6]):sum(depths[5:7])])
+        self.upsample_1 = Upsample(embed_dim * 8, embed_dim * 2)
+        self.decoderlayer_1 = layer(4, 2, depths[7], num_heads[7], dec_dpr[sum(depths[5:7]):sum(depths[5:8])])
+        self.upsample_0 = Upsample(embed_dim * 4, embed_dim)
+        self.decoderlayer_0 = layer(2, 1, depths[8], num_heads[8], dec_dpr[sum(depths[5:8]):sum(depths[5:9])])
+        self.decoderlayer = [self.decoderlayer_0, self.decoderlayer_1, self.decoderlayer_2, self.decoderlayer_3]
+        self.upsample = [self.upsample_0, self.upsample_1, self.upsample_2, self.upsample_3]
+        self.apply(init_uformer_weights)
+
+    @staticmethod
+    def inter_statistics(all_inter):
+        """Token-mean of the affine-free LayerNorm of every band's encoder features: [B, 448] per band,
+        computed once per forward and shared by all 44 blocks' lambda predictors."""
+        return [F.layer_norm(t, (t.shape[-1],)).mean(1) for t in all_inter]
+
+    def forward(self, x, inter, mask=None):
+        assert mask is None
+        stats = self.inter_statistics(inter) if self.all_methods else None
+        y = self.input_proj(x)
+        skips = []
+        for i, (lay, down) in enumerate(((self.encoderlayer_0, self.dowsample_0), (self.encoderlayer_1, self.dowsample_1),
+                                         (self.encoderlayer_2, self.dowsample_2), (self.encoderlayer_3, self.dowsample_3))):
+            y, _ = lay(y, all_inter=stats)
+            skips.append(y)
+            y = down(y)
+        y, _ = self.bottleneck_0(y, all_inter=stats)
+        y, _ = self.bottleneck_1(y, all_inter=stats)
+        for i in reversed(range(self.num_dec_layers)):
+            y = self.upsample[i](y, skips[i])
+            y, _ = self.decoderlayer[i](y, all_inter=stats)
+        if self.in_chans == 3:
+            return self.output_proj(y, residual=x)
+        return self.output_proj(y)

@@ -1,0 +1,97 @@
+"""MoCo wrapper with the reference's interface and buffers (net/utils/moco.py:6-170): query / key encoders,
+momentum update m=0.999, L queues [L, dim, K], logits / labels, enqueue.
+
+What changes underneath: the key encoder's momentum update (99.7 M parameters streamed every step,
+moco.py:45-50 - 489 tiny kernels in the reference) is ONE fused kernel over two flat parameter buffers that
+the q / k parameters are views of.  The contrastive logits ([B, 1+K] per band) are a few KFLOP and stay on
+the host side of the ABI.  The dead DDP helpers of the reference (moco.py:69-113,175-185; never called) are
+not reproduced.
+"""
+import torch
+import torch.nn as nn
+
+from ... import ops
+
+
+def flatten_parameters(params):
+    """Re-home ``params`` (list of nn.Parameter) as views of one flat fp32 buffer; returns the buffer.
+    Values are preserved; 16-byte alignment of every view is kept by padding to 4 floats."""
+    params = list(params)
+    if not params:
+        return None
+    sizes = [(p.numel() + 3) // 4 * 4 for p in params]
+    flat = torch.empty(sum(sizes), device=params[0].device, dtype=torch.float32)
+    flat.zero_()
+    off = 0
+    for p, n in zip(params, sizes):
+        view = flat[off:off + p.numel()].view(p.shape)
+        view.copy_(p.data)
+        p.data = view
+        off += n
+    return flat
+
+
+class MoCo(nn.Module):
+    def __init__(self, opt, base_encoder, dim, K=3 * 256, m=0.999, T=0.07, mlp=False):
+        super().__init__()
+        self.num_losses = opt.L
+        self.opt = opt
+        self.K, self.m, self.T = K, m, T
+        self.encoder_q = base_encoder(opt)
+        self.encoder_k = base_encoder(opt)
+        for param_q, param_k in zip(self.encoder_q.parameters(), self.encoder_k.parameters()):
+            param_k.data.copy_(param_q.data)
+            param_k.requires_grad = False
+        self.register_buffer('queue', torch.randn(self.num_losses, dim, K))
+        for i in range(self.num_losses):
+            self.queue[i] = nn.functional.normalize(self.queue[i], dim=0)
+        self.register_buffer('queue_ptr', torch.zeros(1, dtype=torch.long))
+        self._flat_q = self._flat_k = None
+
+    def _ensure_flat(self):
+        pq = list(self.encoder_q.parameters())
+        ok = (self._flat_q is not None and self._flat_q.device == pq[0].device
+              and pq[0].data_ptr() == self._flat_q.data_ptr())
+        if not ok:
+            self._flat_q = flatten_parameters(pq)
+            self._flat_k = flatten_parameters(list(self.encoder_k.parameters()))
+        return self._flat_q, self._flat_k
+
+    @torch.no_grad()
+    def _momentum_update_key_encoder(self):
+        fq, fk = self._ensure_flat()
+        ops.momentum_update(fk, fq, self.m)
+
+    @torch.no_grad()
+    def _dequeue_and_enqueue(self, keys):
+        batch_size = keys[0].shape[0]
+        ptr = int(self.queue_ptr)
+        assert self.K % batch_size == 0
+        for i in range(self.num_losses):
+            self.queue[i][:, ptr:ptr + batch_size] = keys[i].transpose(0, 1)
+        self.queue_ptr[0] = (ptr + batch_size) % self.K
+
+    def forward(self, im_q, im_k):
+        if self.training:
+            embedding, q, inter = self.encoder_q(im_q)
+            n = min(self.num_losses, len(q))
+            q = [nn.functional.normalize(q[i], dim=1) for i in range(n)]
+            with torch.no_grad():
+                self._momentum_update_key_encoder()
+                _, k, _ = self.encoder_k(im_k)
+                k = [nn.functional.normalize(k[i], dim=1) for i in range(n)]
+            logits, labels = [], []
+            for i in range(n):
+                l_pos = torch.einsum('nc,nc->n', [q[i], k[i]]).unsqueeze(-1)
+                l_neg = torch.einsum('nc,ck->nk', [q[i], self.queue[i].clone().detach()])
+                lg = torch.cat([l_pos, l_neg], dim=1) / self.T
+                logits.append(lg)
+                labels.append(torch.zeros(lg.shape[0], dtype=torch.long, device=lg.device))
+            self._dequeue_and_enqueue(k)
+            return embedding, logits, labels, inter
+        # eval: the reference computes and discards the contrastive heads (moco.py:167-170); encoders that
+        # expose `trunk` skip them (11.3 GFLOP + 805 MB of activations per 16 tiles)
+        if hasattr(self.encoder_q, 'trunk') and getattr(self.encoder_q, 'embedding_is_none', True):
+            return None, self.encoder_q.trunk(im_q)
+        embedding, _, inter = self.encoder_q(im_q)
+        return embedding, inter

@@ -216,6 +216,44 @@ def bn_bwd(x, mean, rstd, scale, shift, slope, dy, dpooled, B, C, S, training=Tr
     return dx, red
 
 
+def bn_tokens_stats(x, T, C):
+    sums = torch.zeros(C, 2, device=x.device, dtype=torch.float64)
+    _call('fa_bn_tokens_stats', _p(x), _p(sums), T, C, _stream())
+    return sums
+
+
+def bn_tokens_apply(x, scale, shift, res, slope, T, C):
+    _f32(x, res)
+    y = torch.empty_like(x)
+    _call('fa_bn_tokens_apply', _p(x), _p(scale), _p(shift), _p(res), slope, _p(y), T, C, _stream())
+    return y
+
+
+def bn_tokens_bwd(x, mean, rstd, scale, yout, slope, dy, T, C, training=True, want_dres=False):
+    _f32(x, dy, yout)
+    red = torch.zeros(C, 2, device=x.device, dtype=torch.float64)
+    dx = torch.empty_like(x)
+    dres = torch.empty_like(x) if want_dres else None
+    _call('fa_bn_tokens_bwd', _p(x), _p(mean), _p(rstd), _p(scale), _p(yout), slope, _p(dy), _p(red), _p(dx), _p(dres), T,
+          C, int(training), _stream())
+    return dx, dres, red
+
+
+def token_mean_fwd(x):
+    _f32(x)
+    B, HW, C = x.shape
+    out = torch.empty(B, C, device=x.device, dtype=torch.float32)
+    _call('fa_token_mean_fwd', _p(x), _p(out), B, HW, C, _stream())
+    return out
+
+
+def token_mean_bwd(dy, B, HW, C):
+    _f32(dy)
+    dx = torch.empty(B, HW, C, device=dy.device, dtype=torch.float32)
+    _call('fa_token_mean_bwd', _p(dy), _p(dx), B, HW, C, _stream())
+    return dx
+
+
 # ----------------------------------------------------------------------------- conv pieces
 def dwconv_fwd(h1, w, b, B, H, W, C, want_act=True):
     _f32(h1, w, b)
@@ -268,6 +306,17 @@ def add2d(a, b, dst):
     _, _, ldb = _rows2d(b)
     _, _, ldd = _rows2d(dst)
     _call('fa_add2d', _p(a), lda, _p(b), ldb, _p(dst), ldd, rows, cols, _stream())
+
+
+def scale_rows(g, rowscale, rows_per_scale):
+    """g * rowscale[row // rows_per_scale]; returns g itself when rowscale is None."""
+    if rowscale is None:
+        return g
+    _f32(g, rowscale)
+    out = torch.empty_like(g)
+    cols = g.shape[-1]
+    _call('fa_scale_rows', _p(g), _p(rowscale), rows_per_scale, _p(out), g.numel() // cols, cols, _stream())
+    return out
 
 
 def tokens_to_nchw(t, res, B, HW, C):

@@ -133,6 +133,21 @@ int fa_bn_bwd_apply(const float* x, const float* mean, const float* rstd, const 
                     float slope, const float* dy, const float* dpooled, const double* red, float* dx, int B, int C,
                     int64_t S, fa_stream_t stream);
 
+/* The same BatchNorm on token layout [T, C] (NHWC; the ResNet encoder / DGRN path keeps NHWC throughout):
+ * apply: y = lrelu(x*scale[c] + shift[c] + res) (slope 1.0 = no activation; res may be NULL).
+ * bwd: g = dy * lrelu'(yout) (yout NULL: no activation); red[c] += {sum g, sum g*xhat} (doubles, caller zero-fills);
+ *      dx = scale*(g - red0/T - xhat*red1/T) (training) or scale*g (training=0); dres = g if dres != NULL.
+ * ref: nn.BatchNorm2d + LeakyReLU + residual add in ResBlock, encoder_ResNet.py:4-20. */
+int fa_bn_tokens_stats(const float* x, double* sums, int64_t T, int C, fa_stream_t stream);
+int fa_bn_tokens_apply(const float* x, const float* scale, const float* shift, const float* res, float slope, float* y,
+                       int64_t T, int C, fa_stream_t stream);
+int fa_bn_tokens_bwd(const float* x, const float* mean, const float* rstd, const float* scale, const float* yout,
+                     float slope, const float* dy, double* red, float* dx, float* dres, int64_t T, int C, int training,
+                     fa_stream_t stream);
+/* AdaptiveAvgPool2d(1) on tokens (encoder_ResNet.py:30): out[b][c] = mean_t x[b][t][c]; bwd broadcasts dy/HW */
+int fa_token_mean_fwd(const float* x, float* out, int B, int HW, int C, fa_stream_t stream);
+int fa_token_mean_bwd(const float* dy, float* dx, int B, int HW, int C, fa_stream_t stream);
+
 /* ------------------------------------------------------------------ convolutions on tokens (K4, K5)
  * depthwise 3x3 of LeFF in token layout with the second GELU fused (leff.py:85-86,100-112); the first GELU is the
  * producing GEMM's epilogue (which also stores the pre-activation u1 for the backward):
@@ -157,6 +172,9 @@ int fa_pixel_shuffle2_bwd(const float* dy, int64_t ldy, float* dg, int B, int H,
 int fa_copy2d(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols, fa_stream_t stream);
 int fa_add2d(const float* a, int64_t lda, const float* b, int64_t ldb, float* dst, int64_t ldd, int64_t rows, int cols,
              fa_stream_t stream);
+/* dst[r][c] = src[r][c] * rowscale[r / rows_per_scale]  (DropPath backward: per-sample scale of a gradient) */
+int fa_scale_rows(const float* src, const float* rowscale, int rows_per_scale, float* dst, int64_t rows, int cols,
+                  fa_stream_t stream);
 /* y[b][c][hw] = t[b][hw][c] (+ res[b][c][hw]); and the reverse */
 int fa_tokens_to_nchw(const float* t, const float* res, float* y, int B, int HW, int C, fa_stream_t stream);
 int fa_nchw_to_tokens(const float* x, float* t, int B, int HW, int C, fa_stream_t stream);
