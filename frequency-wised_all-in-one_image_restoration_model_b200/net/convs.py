@@ -38,28 +38,36 @@ class InputProjFn(torch.autograd.Function):
         return None, dW, db, None          # the input image never needs a gradient on this path
 
 
-class DownsampleFn(torch.autograd.Function):
-    """Conv2d k x k, stride s, pad p on tokens (Downsample 4x4 s2 p1, decoder_Uformer.py:414-430; also the
-    generic token conv used by DGRN / ResNet 3x3 s1 p1)."""
+class ConvTokFn(torch.autograd.Function):
+    """y = act(Conv2d k x k, stride s, pad p on tokens) (+ residual).  Downsample 4x4 s2 p1
+    (decoder_Uformer.py:414-430) and the 3x3 / 1x1 convs of DGRN and the ResNet encoder
+    (decoder_DGRN.py:5-6, encoder_ResNet.py:8-15).  ``col`` (optional) is a precomputed patch matrix of x."""
 
     @staticmethod
-    def forward(ctx, x, wk, b, H, W, k, s, p, act, act_param):
+    def forward(ctx, x, wk, b, H, W, k, s, p, act, act_param, residual):
         B, _, C = x.shape
-        col = ops.im2col(x.contiguous(), B, H, W, C, k, k, s, p)
+        xc = x.contiguous()
+        col = xc.view(-1, C) if (k == 1 and s == 1 and p == 0) else ops.im2col(xc, B, H, W, C, k, k, s, p)
         y = torch.empty(col.shape[0], wk.shape[0], device=x.device, dtype=torch.float32)
-        ops.gemm(col, wk, y, bias=b, act=act, act_param=act_param)
+        r2 = residual.reshape(y.shape).contiguous() if residual is not None else None
+        ops.gemm(col, wk, y, bias=b, act=act, act_param=act_param, residual=r2)
+        assert act in (ops.ACT_NONE, ops.ACT_LRELU) and not (act != ops.ACT_NONE and residual is not None)
         ctx.geom = (B, H, W, C, k, s, p, act, act_param)
-        ctx.has_bias = b is not None
-        ctx.save_for_backward(col, wk, y if act != ops.ACT_NONE else None)
+        ctx.has_bias, ctx.has_res = b is not None, residual is not None
+        # the patch matrix is rebuilt in backward (one streaming pass) instead of being kept alive
+        ctx.save_for_backward(xc, wk, y if act != ops.ACT_NONE else None)
         return y.view(B, -1, wk.shape[0])
 
     @staticmethod
     def backward(ctx, dy):
-        col, wk, y = ctx.saved_tensors
+        xc, wk, y = ctx.saved_tensors
         B, H, W, C, k, s, p, act, act_param = ctx.geom
         g = dy.reshape(-1, wk.shape[0]).contiguous()
+        dres = dy if ctx.has_res else None
         if act != ops.ACT_NONE:
             g = ops.act_bwd(g, y, act, act_param)      # LeakyReLU only: sign(out) == sign(pre)
+        one = (k == 1 and s == 1 and p == 0)
+        col = xc.view(-1, C) if one else ops.im2col(xc, B, H, W, C, k, k, s, p)
         dW = _z(wk)
         db = torch.empty(wk.shape[0], device=g.device) if ctx.has_bias else None
         if db is not None:
@@ -67,10 +75,110 @@ class DownsampleFn(torch.autograd.Function):
         ops.gemm(g, col, dW, transA=True, transB=False, accumulate=True)
         dx = None
         if ctx.needs_input_grad[0]:
-            dcol = torch.empty_like(col)
+            dcol = torch.empty_like(col) if not one else torch.empty(col.shape, device=g.device)
             ops.gemm(g, wk, dcol, transB=False)
-            dx = ops.col2im(dcol, B, H, W, C, k, k, s, p)
-        return dx, dW, db, None, None, None, None, None, None, None
+            dx = dcol.view(B, H * W, C) if one else ops.col2im(dcol, B, H, W, C, k, k, s, p)
+        return dx, dW, db, None, None, None, None, None, None, None, dres
+
+
+def conv_tokens(x, conv, H, W, act=ops.ACT_NONE, act_param=0.0, residual=None):
+    """Apply an nn.Conv2d parameter holder (square kernel, symmetric stride/pad) to tokens [B, H*W, C]."""
+    k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+    return ConvTokFn.apply(x, conv_weight_matrix(conv.weight), conv.bias, H, W, k, s, p, act, act_param, residual)
+
+
+class Im2colFn(torch.autograd.Function):
+    """3x3 s1 p1 patch matrix of a token tensor, as a differentiable value (shared by the 50 offset convs of
+    DGRN, whose second input half - the degradation map - never changes inside one forward)."""
+
+    @staticmethod
+    def forward(ctx, x, H, W):
+        B, _, C = x.shape
+        ctx.geom = (B, H, W, C)
+        return ops.im2col(x.contiguous(), B, H, W, C, 3, 3, 1, 1)
+
+    @staticmethod
+    def backward(ctx, dcol):
+        B, H, W, C = ctx.geom
+        return ops.col2im(dcol.contiguous(), B, H, W, C, 3, 3, 1, 1), None, None
+
+
+class BNTokensFn(torch.autograd.Function):
+    """y = lrelu(BatchNorm(x) + res) on tokens [.., C]; slope 1.0 = no activation (encoder_ResNet.py:4-20)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, training, slope, res):
+        C = x.shape[-1]
+        xc = x.contiguous()
+        T = xc.numel() // C
+        if training:
+            sums = ops.bn_tokens_stats(xc, T, C)
+            mean64 = sums[:, 0] / T
+            var64 = (sums[:, 1] / T - mean64 * mean64).clamp_min_(0)
+            mean, var = mean64.float(), var64.float()
+            with torch.no_grad():
+                running_mean.mul_(0.9).add_(0.1 * mean)
+                running_var.mul_(0.9).add_(0.1 * var * (T / max(T - 1, 1)))
+        else:
+            mean, var = running_mean, running_var
+        rstd = torch.rsqrt(var + 1e-5)
+        scale = weight * rstd
+        shift = bias - mean * scale
+        y = ops.bn_tokens_apply(xc, scale, shift, res.contiguous() if res is not None else None, slope, T, C)
+        ctx.geom = (T, C, slope, training, res is not None)
+        ctx.save_for_backward(xc, mean, rstd, scale, y if slope != 1.0 else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, mean, rstd, scale, y = ctx.saved_tensors
+        T, C, slope, training, has_res = ctx.geom
+        dx, dres, red = ops.bn_tokens_bwd(xc, mean, rstd, scale, y, slope, dy.contiguous(), T, C, training, has_res)
+        return dx, red[:, 1].float(), red[:, 0].float(), None, None, None, None, dres
+
+
+def bn_tokens(x, bn, training, slope=1.0, res=None):
+    if training:
+        bn.num_batches_tracked += 1
+    return BNTokensFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, slope, res)
+
+
+class TokenMeanFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = x.shape
+        return ops.token_mean_fwd(x.contiguous())
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, HW, C = ctx.shape
+        return ops.token_mean_bwd(dy.contiguous(), B, HW, C)
+
+
+class NchwToTokensFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        B, C, H, W = x.shape
+        ctx.shape = x.shape
+        return ops.nchw_to_tokens(x.contiguous(), B, H * W, C)
+
+    @staticmethod
+    def backward(ctx, dt):
+        B, C, H, W = ctx.shape
+        return ops.tokens_to_nchw(dt.contiguous(), None, B, H * W, C).view(B, C, H, W)
+
+
+class TokensToNchwFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t, H, W):
+        B, HW, C = t.shape
+        ctx.geom = (B, HW, C)
+        return ops.tokens_to_nchw(t.contiguous(), None, B, HW, C).view(B, C, H, W)
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, HW, C = ctx.geom
+        return ops.nchw_to_tokens(dy.contiguous(), B, HW, C), None, None
 
 
 class UpsampleCatFn(torch.autograd.Function):

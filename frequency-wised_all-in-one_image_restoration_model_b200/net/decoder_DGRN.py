@@ -1,6 +1,198 @@
-from torch import nn
+"""DGRN - drop-in for the reference's net/decoder_DGRN.py (``DGRN(opt)``, ``forward(x, inter) -> restored``,
+identical state_dict keys): head conv -> 5 DGG x 5 DGB x 2 DGM (= 50 DCNv2 + 50 SFT) -> tail conv.
+
+One autograd node per DGM (decoder_DGRN.py:22-32): offset/mask conv, DCNv2 gather + contraction, the two
+SFT 1x1-conv MLPs, ``x + dcn + x*gamma + beta`` and the LeakyReLU that DGB applies next (:79,81) fused.
+The degradation map's half of every offset conv input (``cat([x, inter])``, deform_conv.py:57-59) is the same
+for all 50 DGMs, so its 3x3 patch matrix is gathered once per forward and each DGM contracts it with its own
+weight half.  Everything runs on NHWC tokens; NCHW only at the module boundary.
+"""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .convs import Im2colFn, NchwToTokensFn, TokensToNchwFn, conv_tokens, conv_weight_matrix
+from .lewin import _z
+from .utils.deform_conv import DCN_layer
+
+
+def default_conv(in_channels, out_channels, kernel_size, bias=True):
+    return nn.Conv2d(in_channels, out_channels, kernel_size, padding=(kernel_size // 2), bias=bias)
+
+
+class DGMFn(torch.autograd.Function):
+    """out = lrelu_slope(x + DCN(x, inter) + SFT(x, inter)); slope 1.0 = the bare DGM."""
+
+    @staticmethod
+    def forward(ctx, x, it, col_i, wom_x, wom_i, bom, wdcn, wg0, wg2, wb0, wb2, H, W, slope):
+        B, HW, C = x.shape
+        T = B * HW
+        x2 = x.reshape(T, C).contiguous()
+        it2 = it.reshape(T, -1)
+        colx = ops.im2col(x2, B, H, W, C, 3, 3, 1, 1)
+        om = torch.empty(T, 27, device=x.device, dtype=torch.float32)
+        ops.gemm(colx, wom_x, om, bias=bom)
+        ops.gemm(col_i, wom_i, om, accumulate=True)
+        dcol = ops.dcn_im2col(x2, om, B, H, W, C)
+        Co = wdcn.shape[0]
+        dcn = torch.empty(T, Co, device=x.device, dtype=torch.float32)
+        ops.gemm(dcol, wdcn, dcn)
+        g1 = torch.empty(T, Co, device=x.device, dtype=torch.float32)
+        gamma = torch.empty_like(g1)
+        b1 = torch.empty_like(g1)
+        beta = torch.empty_like(g1)
+        ops.gemm(it2, wg0, g1, act=ops.ACT_LRELU, act_param=0.1)
+        ops.gemm(g1, wg2, gamma)
+        ops.gemm(it2, wb0, b1, act=ops.ACT_LRELU, act_param=0.1)
+        ops.gemm(b1, wb2, beta)
+        out = ops.sft_fuse_fwd(x2, dcn, gamma, beta, slope)
+        ctx.geom = (B, H, W, C, slope)
+        ctx.save_for_backward(x2, it2, col_i, om, dcn, g1, gamma, b1, beta, wom_x, wom_i, wdcn, wg0, wg2, wb0, wb2)
+        return out.view(B, HW, Co)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x2, it2, col_i, om, dcn, g1, gamma, b1, beta, wom_x, wom_i, wdcn, wg0, wg2, wb0, wb2) = ctx.saved_tensors
+        B, H, W, C, slope = ctx.geom
+        T = x2.shape[0]
+        dev = x2.device
+        dxa, ddcn, dgamma, dbeta = ops.sft_fuse_bwd(x2, dcn, gamma, beta, dout.reshape(T, -1).contiguous(), slope)
+        # SFT MLPs
+        dit = torch.empty_like(it2)
+
+        def mlp_bwd(dy, h, w0, w2, first):
+            dw2 = _z(w2)
+            ops.gemm(dy, h, dw2, transA=True, transB=False, accumulate=True)
+            dh = torch.empty_like(h)
+            ops.gemm(dy, w2, dh, transB=False, aux=h, aux_act=ops.ACT_LRELU, aux_param=0.1)
+            dw0 = _z(w0)
+            ops.gemm(dh, it2, dw0, transA=True, transB=False, accumulate=True)
+            ops.gemm(dh, w0, dit, transB=False, accumulate=not first)
+            return dw0, dw2
+        dwg0, dwg2 = mlp_bwd(dgamma, g1, wg0, wg2, True)
+        dwb0, dwb2 = mlp_bwd(dbeta, b1, wb0, wb2, False)
+        # DCN contraction and gather (patch matrices rebuilt instead of stored)
+        dcol = ops.dcn_im2col(x2, om, B, H, W, C)
+        dwdcn = _z(wdcn)
+        ops.gemm(ddcn, dcol, dwdcn, transA=True, transB=False, accumulate=True)
+        ddcol = dcol                                        # reuse the buffer for the gradient
+        ops.gemm(ddcn, wdcn, ddcol, transB=False)
+        dxb, dom = ops.dcn_col2im(x2, om, ddcol, B, H, W, C)
+        # offset / mask conv
+        dbom = torch.empty(27, device=dev)
+        ops.colsum(dom, dbom)
+        colx = ops.im2col(x2, B, H, W, C, 3, 3, 1, 1)
+        dwom_x, dwom_i = _z(wom_x), _z(wom_i)
+        ops.gemm(dom, colx, dwom_x, transA=True, transB=False, accumulate=True)
+        ops.gemm(dom, col_i, dwom_i, transA=True, transB=False, accumulate=True)
+        ops.gemm(dom, wom_x, colx, transB=False)            # colx buffer becomes d(colx)
+        dxc = ops.col2im(colx, B, H, W, C, 3, 3, 1, 1).view(T, C)
+        dcol_i = None
+        if ctx.needs_input_grad[2]:
+            dcol_i = torch.empty_like(col_i)
+            ops.gemm(dom, wom_i, dcol_i, transB=False)
+        dx = torch.empty_like(x2)
+        ops.add2d(dxa, dxb, dx)
+        ops.add2d(dx, dxc, dx)
+        return (dx.view(B, H * W, C), dit.view(B, H * W, -1), dcol_i, dwom_x, dwom_i, dbom, dwdcn, dwg0, dwg2, dwb0,
+                dwb2, None, None, None)
+
+
+class SFT_layer(nn.Module):
+    def __init__(self, channels_in, channels_out):
+        super().__init__()
+        self.conv_gamma = nn.Sequential(nn.Conv2d(channels_in, channels_out, 1, 1, 0, bias=False), nn.LeakyReLU(0.1, True),
+                                        nn.Conv2d(channels_out, channels_out, 1, 1, 0, bias=False))
+        self.conv_beta = nn.Sequential(nn.Conv2d(channels_in, channels_out, 1, 1, 0, bias=False), nn.LeakyReLU(0.1, True),
+                                       nn.Conv2d(channels_out, channels_out, 1, 1, 0, bias=False))
+
+
+class DGM(nn.Module):
+    def __init__(self, channels_in, channels_out, kernel_size):
+        super().__init__()
+        self.channels_in, self.channels_out, self.kernel_size = channels_in, channels_out, kernel_size
+        self.dcn = DCN_layer(channels_in, channels_out, kernel_size, padding=(kernel_size - 1) // 2, bias=False)
+        self.sft = SFT_layer(channels_in, channels_out)
+        self.relu = nn.LeakyReLU(0.1, True)
+
+    def forward_tokens(self, x, it, col_i, H, W, slope=1.0):
+        C = self.channels_in
+        wom = self.dcn.conv_offset_mask.weight                                    # [27, 2C, 3, 3]
+        wom_x = wom[:, :C].permute(0, 2, 3, 1).reshape(27, -1)
+        wom_i = wom[:, C:].permute(0, 2, 3, 1).reshape(27, -1)
+        s = self.sft
+
+        def m(conv):
+            return conv.weight.view(conv.weight.shape[0], -1)
+        return DGMFn.apply(x, it, col_i, wom_x, wom_i, self.dcn.conv_offset_mask.bias, conv_weight_matrix(self.dcn.weight),
+                           m(s.conv_gamma[0]), m(s.conv_gamma[2]), m(s.conv_beta[0]), m(s.conv_beta[2]), H, W, slope)
+
+
+class DGB(nn.Module):
+    def __init__(self, conv, n_feat, kernel_size):
+        super().__init__()
+        self.dgm1 = DGM(n_feat, n_feat, kernel_size)
+        self.dgm2 = DGM(n_feat, n_feat, kernel_size)
+        self.conv1 = conv(n_feat, n_feat, kernel_size)
+        self.conv2 = conv(n_feat, n_feat, kernel_size)
+        self.relu = nn.LeakyReLU(0.1, True)
+
+    def forward_tokens(self, x, it, col_i, H, W):
+        out = self.dgm1.forward_tokens(x, it, col_i, H, W, slope=0.1)             # relu(dgm1(x))  :79
+        out = conv_tokens(out, self.conv1, H, W, ops.ACT_LRELU, 0.1)              # relu(conv1)    :80
+        out = self.dgm2.forward_tokens(out, it, col_i, H, W, slope=0.1)           # relu(dgm2)     :81
+        return conv_tokens(out, self.conv2, H, W, residual=x)                     # conv2 + x      :82
+
+
+class DGG(nn.Module):
+    def __init__(self, conv, n_feat, kernel_size, n_blocks):
+        super().__init__()
+        self.n_blocks = n_blocks
+        body = [DGB(conv, n_feat, kernel_size) for _ in range(n_blocks)]
+        body.append(conv(n_feat, n_feat, kernel_size))
+        self.body = nn.Sequential(*body)
+
+    def forward_tokens(self, x, it, col_i, H, W):
+        res = x
+        for i in range(self.n_blocks):
+            res = self.body[i].forward_tokens(res, it, col_i, H, W)
+        return conv_tokens(res, self.body[-1], H, W, residual=x)
 
 
 class DGRN(nn.Module):
-    def __init__(self, opt):
-        raise NotImplementedError('DGRN: pending')
+    def __init__(self, opt, conv=default_conv):
+        super().__init__()
+        self.n_groups = 5
+        n_blocks = 5
+        if opt.encoder_type == 'ResNet':
+            n_feats = opt.encoder_dim // 4
+        elif opt.encoder_type == 'ViT':
+            n_feats = opt.encoder_dim
+        else:
+            raise NotImplementedError('freqair: DGRN is defined for the ResNet and ViT encoders only (the reference '
+                                      'leaves n_feats undefined otherwise, decoder_DGRN.py:120-129)')
+        if n_feats % 4:
+            raise NotImplementedError(f'freqair: DGRN n_feats={n_feats} must be a multiple of 4 (128-bit NHWC gathers); '
+                                      'use --encoder_dim 64 with the ViT encoder as the ViT runs of the reference authors do')
+        self.n_feats = n_feats
+        kernel_size = 3
+        self.head = nn.Sequential(conv(3, n_feats, kernel_size))
+        body = [DGG(default_conv, n_feats, kernel_size, n_blocks) for _ in range(self.n_groups)]
+        body.append(conv(n_feats, n_feats, kernel_size))
+        self.body = nn.Sequential(*body)
+        self.tail = nn.Sequential(conv(n_feats, 3, kernel_size))
+
+    def forward(self, x, inter):
+        B, _, H, W = x.shape
+        it = getattr(inter, '_fa_tokens', None)
+        if it is None:
+            it = NchwToTokensFn.apply(inter)
+        col_i = Im2colFn.apply(it, H, W)
+        t = NchwToTokensFn.apply(x)
+        h = conv_tokens(t, self.head[0], H, W)
+        res = h
+        for i in range(self.n_groups):
+            res = self.body[i].forward_tokens(res, it, col_i, H, W)
+        res = conv_tokens(res, self.body[-1], H, W, residual=h)
+        out = conv_tokens(res, self.tail[0], H, W)
+        return TokensToNchwFn.apply(out, H, W)

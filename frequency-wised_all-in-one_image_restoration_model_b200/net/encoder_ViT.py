@@ -1,6 +1,188 @@
+"""ViTEncoder - drop-in for the reference's net/encoder_ViT.py (``ViTEncoder(opt)``, ``forward(x) -> (fea, [out],
+inter)``, identical state_dict keys): patch 16 -> dim out_channels*256, depth 12, 12 heads, mlp 3072.
+
+Each attention layer is the K2 window-attention kernel run on the single 8x8 grid of patch tokens (64 tokens,
+head_dim 64, no bias table, no shift) with the band re-weighting ``attn + sum_i lamb_i * band_i(attn)``
+(encoder_ViT.py:85-92) fused as one real filter in shared memory; ``lamb`` [nb, 1|B, heads] is the learned part.
+Linear / LayerNorm / FFN run on the GEMM + LN kernels with residual adds in the GEMM epilogue.
+Dropout (p=0.1, encoder_ViT.py:128-129) is an RNG-dependent elementwise mask kept on the host side of the ABI
+in train mode; parity and throughput runs use eval mode or p=0.
+"""
+import torch
+import torch.nn.functional as F
 from torch import nn
+
+from .. import ops
+from .convs import BNHeadFn
+from .lewin import layer_norm, linear
+from .utils.frequency_decompose import half_band_map
+
+
+def pair(t):
+    return t if isinstance(t, tuple) else (t, t)
+
+
+class _AttnCoreFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, coef, cfg):
+        B, heads, hd, bob, nb, bstride = cfg
+        C = heads * hd
+        q2 = qkv.reshape(-1, 3 * C)
+        o = torch.empty(q2.shape[0], C, device=qkv.device, dtype=torch.float32)
+        ops.win_attn_fwd(q2[:, :C], q2[:, C:], o, B, 8, 8, heads, hd, 0, hd ** -0.5, None, coef, bstride, bob, nb)
+        ctx.cfg = cfg
+        ctx.save_for_backward(q2, coef)
+        return o.view(B, 64, C)
+
+    @staticmethod
+    def backward(ctx, do):
+        q2, coef = ctx.saved_tensors
+        B, heads, hd, bob, nb, bstride = ctx.cfg
+        C = heads * hd
+        T = q2.shape[0]
+        dq = torch.empty(T, C, device=q2.device)
+        dkv = torch.empty(T, 2 * C, device=q2.device)
+        dcoef = torch.zeros_like(coef) if coef is not None else None
+        ops.win_attn_bwd(q2[:, :C], q2[:, C:], do.reshape(T, C).contiguous(), dq, dkv, B, 8, 8, heads, hd, 0, hd ** -0.5,
+                         None, None, coef, bstride, dcoef, bob, nb)
+        dqkv = torch.empty(T, 3 * C, device=q2.device)
+        ops.copy2d(dq, dqkv[:, :C])
+        ops.copy2d(dkv, dqkv[:, C:])
+        return dqkv.view(B, 64, 3 * C), dcoef, None
+
+
+class PreNorm(nn.Module):
+    def __init__(self, dim, fn):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        self.fn = fn
+
+    def forward(self, x, **kwargs):
+        return self.fn(layer_norm(x, self.norm.weight, self.norm.bias), residual=x, **kwargs)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim, hidden_dim, dropout=0.):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(dim, hidden_dim), nn.GELU(), nn.Dropout(dropout), nn.Linear(hidden_dim, dim),
+                                 nn.Dropout(dropout))
+        self.p = dropout
+
+    def forward(self, x, residual=None):
+        h = linear(x, self.net[0].weight, self.net[0].bias, ops.ACT_GELU)
+        if self.training and self.p > 0:
+            h = F.dropout(h, self.p, True)
+            return F.dropout(linear(h, self.net[3].weight, self.net[3].bias), self.p, True) + residual
+        return linear(h, self.net[3].weight, self.net[3].bias, residual=residual)
+
+
+class Attention(nn.Module):
+    def __init__(self, dim, heads=8, dim_head=64, dropout=0., decompose_type='none', wised_batch=None):
+        super().__init__()
+        inner_dim = dim_head * heads
+        assert not (heads == 1 and dim_head == dim)
+        assert dim_head == 64, 'freqair: ViT attention kernel is built for head_dim 64 (out_channels 3)'
+        self.heads, self.dim_head, self.scale = heads, dim_head, dim_head ** -0.5
+        self.num_bands = None
+        self.band_kind = None
+        if not decompose_type == 'none':
+            if decompose_type.split('_')[-1] == 'bands':
+                self.num_bands = int(decompose_type.split('_')[0])
+                self.band_kind = ('frequency_decompose', 1. / self.num_bands)
+            elif decompose_type == 'DC':
+                self.num_bands = 2
+                self.band_kind = ('frequency_decompose_1', 1.0)
+            assert self.num_bands <= 8, 'freqair: at most 8 frequency bands'
+            self.lamb = nn.Parameter(torch.zeros(self.num_bands, 1 if wised_batch is None else wised_batch, heads))
+        self.p = dropout
+        self.dropout = nn.Dropout(dropout)
+        self.to_qkv = nn.Linear(dim, inner_dim * 3, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner_dim, dim), nn.Dropout(dropout))
+        self._bob = None
+
+    def forward(self, x, residual=None):
+        B, N, _ = x.shape
+        assert N == 64, 'freqair: 64 patch tokens (128x128 image, 16x16 patches) as in the reference'
+        qkv = linear(x, self.to_qkv.weight)
+        coef, bob, nb, bstride = None, None, 0, 0
+        if self.num_bands is not None:
+            if self._bob is None or self._bob.device != x.device:
+                self._bob = half_band_map(self.band_kind[0], self.band_kind[1], 64).to(x.device)
+            bob, nb = self._bob, self.num_bands
+            coef = self.lamb.permute(1, 2, 0).contiguous()             # [1|B, heads, nb]
+            bstride = self.heads if coef.shape[0] > 1 else 0
+        if self.training and self.p > 0:
+            raise NotImplementedError('freqair: attention-map dropout (encoder_ViT.py:94) is not fused; run the ViT '
+                                      'encoder with dropout=0 or in eval mode')
+        o = _AttnCoreFn.apply(qkv, coef, (B, self.heads, self.dim_head, bob, nb, bstride))
+        return linear(o, self.to_out[0].weight, self.to_out[0].bias, residual=residual)
+
+
+class Transformer(nn.Module):
+    def __init__(self, dim, depth, heads, dim_head, mlp_dim, dropout=0., decompose_type='none', wised_batch=None):
+        super().__init__()
+        self.layers = nn.ModuleList([])
+        for _ in range(depth):
+            self.layers.append(nn.ModuleList([
+                PreNorm(dim, Attention(dim, heads=heads, dim_head=dim_head, dropout=dropout,
+                                       decompose_type=decompose_type, wised_batch=wised_batch)),
+                PreNorm(dim, FeedForward(dim, mlp_dim, dropout=dropout))]))
+
+    def forward(self, x):
+        for attn, ff in self.layers:
+            x = attn(x)          # residual folded into the output GEMM's epilogue (encoder_ViT.py:115-116)
+            x = ff(x)
+        return x
 
 
 class ViTEncoder(nn.Module):
-    def __init__(self, opt):
-        raise NotImplementedError('ViTEncoder: pending')
+    embedding_is_none = False
+
+    def __init__(self, opt, image_size=128, patch_size=16, depth=12, heads=12, mlp_dim=3072, channels=3, dropout=0.1,
+                 emb_dropout=0.1):
+        super().__init__()
+        out_channels = opt.out_channels
+        dim = out_channels * patch_size * patch_size
+        self.opt, self.depth = opt, depth
+        dim_head = dim // heads
+        self.image_height, self.image_width = pair(image_size)
+        self.patch = patch_size
+        num_patches = (self.image_height // patch_size) * (self.image_width // patch_size)
+        patch_dim = channels * patch_size * patch_size
+        self.to_patch_embedding = nn.Sequential(nn.Identity(), nn.LayerNorm(patch_dim), nn.Linear(patch_dim, dim),
+                                                nn.LayerNorm(dim))
+        self.pos_embedding = nn.Parameter(torch.randn(1, num_patches, dim))
+        self.dropout = nn.Dropout(emb_dropout)
+        self.transformer = Transformer(dim, depth, heads, dim_head, mlp_dim, dropout,
+                                       decompose_type=opt.frequency_decompose_type,
+                                       wised_batch=opt.batch_size if opt.batch_wise_decompose else None)
+        self.mlp_head = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, dim // out_channels * opt.encoder_dim))
+        self.norm = nn.Sequential(nn.BatchNorm2d(opt.encoder_dim), nn.LeakyReLU(0.1, True))
+        self.avg = nn.AdaptiveAvgPool2d(1)
+        self.mlp = nn.Sequential(nn.Linear(opt.encoder_dim, opt.encoder_dim), nn.LeakyReLU(0.1, True),
+                                 nn.Linear(opt.encoder_dim, opt.encoder_dim))
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        p = self.patch
+        # 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)': a 196 KB/image host-side layout shuffle of the input
+        t = x.view(B, C, H // p, p, W // p, p).permute(0, 2, 4, 3, 5, 1).reshape(B, -1, p * p * C)
+        pe = self.to_patch_embedding
+        t = layer_norm(t, pe[1].weight, pe[1].bias)
+        t = linear(t, pe[2].weight, pe[2].bias)
+        t = layer_norm(t, pe[3].weight, pe[3].bias) + self.pos_embedding[:, :t.shape[1]]
+        if self.training and self.dropout.p > 0:
+            t = self.dropout(t)
+        t = self.transformer(t)
+        t = linear(layer_norm(t, self.mlp_head[0].weight, self.mlp_head[0].bias), self.mlp_head[1].weight,
+                   self.mlp_head[1].bias)
+        ed = self.opt.encoder_dim
+        bn = self.norm[0]
+        if self.training:
+            bn.num_batches_tracked += 1
+        flat = t.reshape(-1, ed, self.image_height * self.image_width)
+        fea, act = BNHeadFn.apply(flat, bn.weight, bn.bias, bn.running_mean, bn.running_var, self.training, 0.1, True)
+        inter = act.view(-1, ed, self.image_height, self.image_width)
+        out = linear(linear(fea, self.mlp[0].weight, self.mlp[0].bias, ops.ACT_LRELU, 0.1), self.mlp[2].weight,
+                     self.mlp[2].bias)
+        return fea, [out], inter

@@ -214,17 +214,19 @@ class EncoderBlockFn(torch.autograd.Function):
 
 # ----------------------------------------------------------------------------- dense layers as autograd nodes
 class LinearFn(torch.autograd.Function):
-    """y = act(x W^T + b) on the last dim (nn.Linear + optional LeakyReLU/GELU epilogue)."""
+    """y = act(x W^T + b) (+ residual) on the last dim (nn.Linear + optional LeakyReLU/GELU epilogue)."""
 
     @staticmethod
-    def forward(ctx, x, W, b, act, act_param):
+    def forward(ctx, x, W, b, act, act_param, residual):
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
         y = torch.empty(x2.shape[0], W.shape[0], device=x.device, dtype=torch.float32)
-        pre = torch.empty_like(y) if act == ops.ACT_GELU else None
-        ops.gemm(x2, W, y, bias=b, act=act, act_param=act_param, preact=pre)
+        pre = torch.empty_like(y) if (act == ops.ACT_GELU or (act != ops.ACT_NONE and residual is not None)) else None
+        r2 = residual.reshape(-1, W.shape[0]).contiguous() if residual is not None else None
+        ops.gemm(x2, W, y, bias=b, act=act, act_param=act_param, preact=pre, residual=r2)
         ctx.act = (act, act_param)
         ctx.has_bias = b is not None
-        ctx.save_for_backward(x2, W, pre if pre is not None else y)
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x2, W, pre if pre is not None else (y if act != ops.ACT_NONE else None))
         ctx.xshape = x.shape
         return y.view(*x.shape[:-1], W.shape[0])
 
@@ -233,17 +235,18 @@ class LinearFn(torch.autograd.Function):
         x2, W, pre = ctx.saved_tensors
         act, ap = ctx.act
         g = dy.reshape(-1, W.shape[0]).contiguous()
+        dres = dy if ctx.has_res else None
         if act != ops.ACT_NONE:
             # LeakyReLU: sign(out) == sign(pre-activation), so the saved output serves as aux
             g = ops.act_bwd(g, pre, act, ap)
         dW = _z(W)
         db = torch.empty(W.shape[0], device=g.device) if ctx.has_bias else None
         dx = linear_grads(g, x2, W, dW, db, want_dx=ctx.needs_input_grad[0])
-        return (dx.view(ctx.xshape) if dx is not None else None), dW, db, None, None
+        return (dx.view(ctx.xshape) if dx is not None else None), dW, db, None, None, dres
 
 
-def linear(x, W, b=None, act=ops.ACT_NONE, act_param=0.0):
-    return LinearFn.apply(x, W, b, act, act_param)
+def linear(x, W, b=None, act=ops.ACT_NONE, act_param=0.0, residual=None):
+    return LinearFn.apply(x, W, b, act, act_param, residual)
 
 
 class LayerNormFn(torch.autograd.Function):

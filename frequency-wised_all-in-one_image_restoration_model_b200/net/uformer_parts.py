@@ -7,7 +7,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from .convs import (DownsampleFn, InputProjFn, OutputProjFn, UpsampleCatFn, conv_weight_matrix,
+from .convs import (ConvTokFn, InputProjFn, OutputProjFn, UpsampleCatFn, conv_weight_matrix,
                     deconv_weight_matrix)
 from .utils.leff import LeFF
 
@@ -53,8 +53,8 @@ class Downsample(nn.Module):
         B, L, C = x.shape
         H = W = int(math.sqrt(L))
         c = self.conv[0]
-        return DownsampleFn.apply(x, conv_weight_matrix(c.weight), c.bias, H, W, self.k, self.s, self.p,
-                                  ops.ACT_NONE, 0.0)
+        return ConvTokFn.apply(x, conv_weight_matrix(c.weight), c.bias, H, W, self.k, self.s, self.p,
+                                  ops.ACT_NONE, 0.0, None)
 
 
 class Upsample(nn.Module):

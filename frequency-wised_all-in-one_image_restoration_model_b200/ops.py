@@ -12,6 +12,7 @@ from . import _lib
 from ._lib import FaGemmEpilogue
 
 ACT_NONE, ACT_GELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
+FLOP_COUNTER = [None]          # bench.py roofline leg: set to 0 to accumulate 2*M*N*K of every fa_gemm call
 K_GEMM, K_WIN_ATTN, K_JOINT_ATTN, K_BAND, K_LN, K_DWCONV, K_IM2COL, K_BN, K_OPTIM, K_DCN, K_ELEM = range(1, 12)
 
 
@@ -78,6 +79,8 @@ def gemm(A, B, C, transA=False, transB=True, bias=None, act=ACT_NONE, act_param=
     cr, cc, ldc = _rows2d(C)
     if (cr, cc) != (M, N):
         raise RuntimeError(f'freqair.gemm: C is {cr}x{cc}, expected {M}x{N}')
+    if FLOP_COUNTER[0] is not None:
+        FLOP_COUNTER[0] += 2 * M * N * K
     e = FaGemmEpilogue()
     e.bias = bias.data_ptr() if bias is not None else None
     e.act, e.act_param = act, act_param

@@ -1,0 +1,152 @@
+"""The training step of the reference's train.py (lines 80-96: zero_grad, forward, CE + L1 loss, backward,
+Adam) as one object, plus what a single 8xB200 box adds: batch-sharded data parallelism with a bucketed
+gradient all-reduce over NCCL/NVLink that overlaps the remaining backward.
+
+Memory layout: every trainable parameter is a view of one flat fp32 buffer per segment (query encoder,
+restorer); gradients, Adam m and v mirror that layout, so zero_grad is one memset, Adam is one fused kernel
+per segment (train.py:63,96 -> fa_adam_step) and all-reduce buckets are plain slices of the gradient buffer.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .losses import l1_loss
+
+
+def _offsets(params):
+    offs, off = [], 0
+    for p in params:
+        offs.append(off)
+        off += (p.numel() + 3) // 4 * 4
+    return offs, off
+
+
+def flatten_into(params):
+    """Make ``params`` views of one flat buffer (values preserved). Returns (flat, offsets)."""
+    params = list(params)
+    offs, total = _offsets(params)
+    flat = torch.zeros(total, device=params[0].device, dtype=torch.float32)
+    for p, o in zip(params, offs):
+        v = flat[o:o + p.numel()].view(p.shape)
+        v.copy_(p.data)
+        p.data = v
+    return flat, offs
+
+
+class Segment:
+    """A group of parameters sharing one flat buffer, with matching flat gradient / Adam state."""
+
+    def __init__(self, params, flat=None):
+        self.params = list(params)
+        offs, total = _offsets(self.params)
+        if flat is None or flat.numel() != total or self.params[0].data_ptr() != flat.data_ptr():
+            flat, offs = flatten_into(self.params)
+        self.flat, self.offs = flat, offs
+        self.grad = torch.zeros_like(flat)
+        self.m = torch.zeros_like(flat)
+        self.v = torch.zeros_like(flat)
+        for p, o in zip(self.params, offs):
+            p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+
+class BucketedAllReduce:
+    """Gradient mean over ranks in ~bucket_mb slices of the flat gradient buffers, launched from
+    post-accumulate-grad hooks on a side stream as soon as every parameter of a bucket has its gradient."""
+
+    def __init__(self, segments, bucket_mb=64, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.stream = torch.cuda.Stream()
+        self.buckets = []          # (tensor slice, n_params)
+        self.pending = []
+        self.handles = []
+        per = int(bucket_mb * (1 << 20) // 4)
+        for seg in segments:
+            n = seg.grad.numel()
+            nb = max(1, (n + per - 1) // per)
+            bounds = [min(n, i * per) for i in range(nb + 1)]
+            base = len(self.buckets)
+            counts = [0] * nb
+            owners = []
+            for p, o in zip(seg.params, seg.offs):
+                b = min(nb - 1, (o + p.numel() - 1) // per)      # bucket of the parameter's last element
+                counts[b] += 1
+                owners.append(base + b)
+            for i in range(nb):
+                self.buckets.append((seg.grad[bounds[i]:bounds[i + 1]], counts[i]))
+            for p, b in zip(seg.params, owners):
+                p.register_post_accumulate_grad_hook(self._make_hook(b))
+        self.reset()
+
+    def reset(self):
+        self.pending = [c for _, c in self.buckets]
+        self.handles = []
+        self.launched = [False] * len(self.buckets)
+
+    def _make_hook(self, b):
+        def hook(_param):
+            self.pending[b] -= 1
+            if self.pending[b] == 0:
+                self._launch(b)
+        return hook
+
+    def _launch(self, b):
+        if self.launched[b]:
+            return
+        self.launched[b] = True
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev)
+            self.handles.append(self.dist.all_reduce(self.buckets[b][0], op=self.dist.ReduceOp.AVG, group=self.group,
+                                                     async_op=True))
+
+    def finish(self):
+        for b, (_, c) in enumerate(self.buckets):
+            if not self.launched[b]:           # parameters that received no gradient this step
+                self._launch(b)
+        for h in self.handles:
+            h.wait()
+        torch.cuda.current_stream().wait_stream(self.stream)
+        self.reset()
+
+
+class TrainStep:
+    def __init__(self, net, lr=2e-4, contrast_loss_weight=0.6, betas=(0.9, 0.999), eps=1e-8, distributed=False,
+                 bucket_mb=64):
+        self.net = net
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.w = contrast_loss_weight
+        self.t = 0
+        moco = net.E.E
+        fq, _ = moco._ensure_flat()
+        enc_params = [p for p in moco.encoder_q.parameters()]
+        dec_params = [p for p in net.R.parameters()]
+        self.segments = [Segment(enc_params, fq), Segment(dec_params)]
+        moco._flat_q = self.segments[0].flat
+        self.ddp = BucketedAllReduce(self.segments, bucket_mb) if distributed else None
+        self.last = {}
+
+    def zero_grad(self):
+        for s in self.segments:
+            s.grad.zero_()
+
+    def loss(self, restored, logits, labels, clean):
+        n = len(logits)
+        ce = sum(F.cross_entropy(logits[i], labels[i]) for i in range(n)) / n        # train.py:88
+        l1 = l1_loss(restored, clean)                                                # train.py:89
+        return l1 + self.w * ce, l1, ce                                              # train.py:92
+
+    def step(self, x_query, x_key, clean):
+        """One optimisation step; returns the (device) loss tensor."""
+        self.zero_grad()
+        restored, logits, labels = self.net(x_query, x_key)
+        loss, l1, ce = self.loss(restored, logits, labels, clean)
+        loss.backward()
+        if self.ddp is not None:
+            self.ddp.finish()
+        self.t += 1
+        for s in self.segments:
+            ops.adam_step(s.flat, s.grad, s.m, s.v, self.lr, self.betas[0], self.betas[1], self.eps, self.t)
+        self.last = dict(loss=loss.detach(), l1=l1.detach(), ce=ce.detach())
+        return self.last['loss']

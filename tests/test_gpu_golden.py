@@ -128,3 +128,78 @@ def test_airnet_train_step(airnet):
     assert int(sd['E.E.queue_ptr']) == int(g['queue_ptr'][0])
     for blk in dp:
         airnet.get_submodule(blk).forced_dp = None
+
+
+# ----------------------------------------------------------------------------- ResNet encoder + DGRN (BASELINE config 1)
+def _grad_close(got, ref, name, tol=2e-3):
+    scale = max(ref.abs().max().item(), 1e-6)
+    err = (got.detach().float().cpu() - ref).abs().max().item()
+    assert err <= tol * scale + 1e-7, f'{name}: grad err {err:.3e} vs scale {scale:.3e}'
+
+
+def test_resnet_encoder_and_dgrn_golden():
+    renc_mod = importlib.import_module(PKG_NAME + '.net.encoder_ResNet')
+    dgrn_mod = importlib.import_module(PKG_NAME + '.net.decoder_DGRN')
+    g = load_golden('resnet_dgrn.npz')
+    o = make_opt(encoder_type='ResNet', decoder_type='ResNet', encoder_dim=256)
+    renc = load_det(renc_mod.ResNetEncoder(o), 'spec_resnet_encoder.json').cuda()
+    dgrn = load_det(dgrn_mod.DGRN(o), 'spec_dgrn64.json').cuda().eval()
+    xq, _, _ = synth.noisy_batch(2, 25)
+    x1 = xq[:1, :, :64, :64].contiguous().cuda()
+    renc.eval()
+    with torch.no_grad():
+        fea, out, inter = renc(x1)
+        y = dgrn(x1, inter)
+        y2 = dgrn(x1, inter.clone())              # NCHW-only entry (no token side channel)
+    assert maxerr(inter, t(g['inter'])) < 1e-3 and maxerr(fea, t(g['fea'])) < 1e-3 and maxerr(out[0], t(g['out'])) < 1e-3
+    assert maxerr(y, t(g['restored'])) < 1e-3 and maxerr(y2, t(g['restored'])) < 1e-3
+    renc.train()
+    fea, out, _ = renc(xq.cuda())
+    assert maxerr(fea, t(g['train_fea'])) < 1e-3 and maxerr(out[0], t(g['train_out'])) < 1e-3
+
+
+def test_resnet_dgrn_gradients_vs_oracle():
+    from oracle import airnet as oa
+    renc_mod = importlib.import_module(PKG_NAME + '.net.encoder_ResNet')
+    dgrn_mod = importlib.import_module(PKG_NAME + '.net.decoder_DGRN')
+    o = make_opt(encoder_type='ResNet', decoder_type='ResNet', encoder_dim=32)        # n_feats 8: small but complete
+    torch.manual_seed(3)
+    renc, dgrn = renc_mod.ResNetEncoder(o), dgrn_mod.DGRN(o)
+    detfill.fill_state(renc.state_dict()); detfill.fill_state(dgrn.state_dict())
+    se = {k: v.clone().requires_grad_(v.is_floating_point() and 'running' not in k) for k, v in renc.state_dict().items()}
+    sdg = {k: v.clone().requires_grad_(True) for k, v in dgrn.state_dict().items()}
+    x = torch.rand(2, 3, 16, 16)
+    w = torch.randn(2, 3, 16, 16)
+    fea, out, inter = oa.resnet_encoder_forward(se, '', x, training=True)
+    y = oa.dgrn_forward(sdg, '', x, inter)
+    ((y * w).sum() + out[0].square().sum()).backward()
+    renc, dgrn = renc.cuda().train(), dgrn.cuda().train()
+    fk, ok, ik = renc(x.cuda())
+    yk = dgrn(x.cuda(), ik)
+    assert maxerr(yk, y) < 1e-3 and maxerr(ok[0], out[0]) < 1e-3
+    ((yk * w.cuda()).sum() + ok[0].square().sum()).backward()
+    for name, p in list(dgrn.named_parameters()):
+        _grad_close(p.grad, sdg[name].grad, 'dgrn.' + name)
+    for name, p in list(renc.named_parameters()):
+        _grad_close(p.grad, se[name].grad, 'renc.' + name)
+
+
+# ----------------------------------------------------------------------------- ViT encoder
+def test_vit_encoder_golden_and_gradients():
+    from oracle import airnet as oa
+    vit_mod = importlib.import_module(PKG_NAME + '.net.encoder_ViT')
+    g = load_golden('vit_encoder.npz')
+    o = make_opt(encoder_type='ViT', encoder_dim=64, frequency_decompose_type='4_bands')
+    vit = load_det(vit_mod.ViTEncoder(o), 'spec_vit_encoder_ed64.json')
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and 'running' not in k) for k, v in vit.state_dict().items()}
+    vit = vit.cuda().eval()
+    xq, _, _ = synth.noisy_batch(2, 25)
+    fea, out, inter = vit(xq.cuda())
+    assert maxerr(fea, t(g['fea'])) < 1e-3 and maxerr(out[0], t(g['out'])) < 1e-3
+    assert maxerr(inter[:, :4, :8, :], t(g['inter_head'])) < 1e-3
+    w = torch.randn(inter.shape, generator=torch.Generator().manual_seed(1))
+    ((inter * w.cuda()).sum() * 1e-3 + out[0].square().sum()).backward()
+    rf, ro, ri = oa.vit_encoder_forward(sd, '', xq, 64, decompose_type='4_bands')
+    ((ri * w).sum() * 1e-3 + ro[0].square().sum()).backward()
+    for name, p in vit.named_parameters():
+        _grad_close(p.grad, sd[name].grad, 'vit.' + name, tol=3e-3)
