@@ -81,13 +81,13 @@ int fa_gemm(const float* A, const float* B, float* C, int M, int N, int K, int64
             int transA, int transB, const FaGemmEpilogue* epi, int backend, fa_stream_t stream) {
   FA_REQUIRE(A && B && C, "fa_gemm: null operand");
   FA_REQUIRE(M >= 0 && N >= 0 && K >= 0, "fa_gemm: negative dimension");
-  FA_REQUIRE(backend >= 0 && backend <= 2, "fa_gemm: backend must be 0, 1 or 2");
+  FA_REQUIRE(backend >= 0 && backend <= 3, "fa_gemm: backend must be 0, 1, 2 or 3");
   cudaStream_t st = (cudaStream_t)stream;
   FaProfScope prof(FA_K_GEMM, st);
   if (backend != 1) {
-    int rc = fa_gemm_tc_launch(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, epi, st, false);
+    int rc = fa_gemm_tc_launch(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, epi, st, backend == 3);
     if (rc != FA_ERR_UNSUPPORTED) return rc;
-    if (backend == 2) {
+    if (backend >= 2) {
       fa_set_error("fa_gemm: shape M=%d N=%d K=%d tA=%d tB=%d not eligible for the tcgen05 path", M, N, K, transA, transB);
       return FA_ERR_UNSUPPORTED;
     }

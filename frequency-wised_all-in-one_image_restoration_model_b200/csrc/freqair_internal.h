@@ -6,4 +6,4 @@ int fa_gemm_simt_launch(const float* A, const float* B, float* C, int M, int N, 
                         int64_t ldc, int transA, int transB, const FaGemmEpilogue* ep, cudaStream_t st);
 // returns FA_ERR_UNSUPPORTED (without setting the error string) when the shape is not eligible
 int fa_gemm_tc_launch(const float* A, const float* B, float* C, int M, int N, int K, int64_t lda, int64_t ldb,
-                      int64_t ldc, int transA, int transB, const FaGemmEpilogue* ep, cudaStream_t st, bool probe_only);
+                      int64_t ldc, int transA, int transB, const FaGemmEpilogue* ep, cudaStream_t st, bool single_pass);

@@ -1,13 +1,28 @@
-// K3 - TMA-fed tcgen05 GEMM (kind::tf32, fp32 operands read straight from HBM, fp32 accumulators in TMEM)
-// with the same fused epilogue as the SIMT kernel.  Covers the dense contractions of the LeWin / LeFF /
-// head path:
+// K3 - TMA-fed tcgen05 GEMM (fp32 operands read straight from HBM, fp32 accumulators in TMEM) with the same fused
+// epilogue as the SIMT kernel.  Covers the dense contractions of the LeWin / LeFF / head path:
 //   NT : C[M,N] = A[M,K] . W[N,K]^T           (both operands K-major: every nn.Linear forward)
 //   NN : C[M,N] = A[M,K] . B[K,N]             (B MN-major: dX = dY . W)
 //   TN : C[M,N] = A[K,M]^T . B[K,N]           (both MN-major: dW = dY^T . X, split over K with fp32 atomics)
-// One CTA = one 128 x BN output tile; 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc),
-// warps 2-5 epilogue (TMEM -> registers -> global).  smem ring of STAGES x {A 128x32, B BNx32} fp32 tiles in
-// the 128-byte-swizzled layout TMA writes and the UMMA descriptors read.  Every mbarrier wait is bounded:
-// a protocol bug traps instead of hanging the GPU.
+//
+// Precision.  kind::tf32 TRUNCATES each fp32 operand to a 10-bit mantissa; one pass costs ~1e-3 relative per product
+// and pushes the end-to-end restoration error to 4e-3..1.4e-2 (measured), outside north_star's 1e-3.  The default
+// (x3) is therefore the error-compensated 3-pass scheme: with hi = trunc_tf32(x) (what the tensor core sees when fed
+// x) and lo = x - hi (exact in fp32, <= 13 significant bits),
+//      A.B ~= A_lo.B + A.B_lo + A.B          (all three accumulate into the same fp32 TMEM tile)
+// where the tensor core again truncates lo to its top 11 bits; the dropped terms are O(2^-21) relative.  lo tiles are
+// produced on-chip by 4 "split" warps between TMA arrival and MMA issue (element-wise, so swizzle-agnostic); HBM
+// traffic is unchanged, and the layers that dominate the step are HBM-bound.
+// The tensor core also accumulates with truncation: the error of a length-k running sum grows ~4e-8*k^1.5 (measured:
+// 2.7e-2 at k=8192 on unit-variance data, 20x the fp32 SIMT kernel).  Accumulation in TMEM is therefore limited to
+// KC = 256 reduction elements; the epilogue warps promote each partial tile into fp32 registers (round-to-nearest)
+// while the MMA fills the other TMEM stage - the same ping-pong that overlaps epilogue and mainloop across tiles.
+//
+// Persistent, warp-specialised, one CTA per SM: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 2-5
+// split, warps 6-13 epilogue.  smem ring of `stages` x {A 128x32, B BNx32 (+ lo copies)} fp32 tiles in the swizzled
+// layouts TMA writes and the UMMA descriptors read.  Operand majors, x3 and the ring depth are runtime flags (they only
+// steer single-thread code); BN and the epilogue flavour are template parameters to keep each kernel's code inside
+// the instruction cache (a fully generic, fully unrolled epilogue measured ~40 % "no instruction" stalls).
+// Every mbarrier wait is bounded: a protocol bug traps instead of hanging the GPU.
 #include <cuda.h>
 #include "freqair_internal.h"
 
@@ -16,7 +31,23 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 32;              // floats per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 8;           // tf32
-constexpr int NTHREADS = 192;
+constexpr int KC_BLOCKS = 8;        // k-blocks accumulated inside TMEM before promotion to registers (KC = 256)
+constexpr int MAX_STAGES = 8;
+constexpr int SPLIT_WARPS = 4;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARP0 = 2 + SPLIT_WARPS;     // first epilogue warp (6: 6 % 4 == 2, quarters cycle 2,3,0,1,...)
+constexpr int NTHREADS = 32 * (2 + SPLIT_WARPS + EPI_WARPS);
+constexpr int A_BYTES = BM * BK * 4;
+
+// epilogue flavours
+enum { EPI_PLAIN = 0,   // alpha, accumulate, split-K atomics                         (dX, dW)
+       EPI_FWD = 1,     // bias, preact store, activation, row scale, residual        (nn.Linear forward)
+       EPI_BWD = 2,     // multiply by act'(aux), accumulate                          (dX through an activation)
+       EPI_ANY = 3 };   // every FaGemmEpilogue field (compact, not unrolled)
+
+// per-warp 32x32 fp32 transpose tile of the epilogue, 16-byte chunks XOR-swizzled by row so that both the
+// thread=row float4 writes and the lane=column(-quad) reads are bank-conflict-free without padding
+__device__ __forceinline__ int stg_idx(int r, int c) { return r * 32 + ((((c >> 2) ^ r) & 7) << 2) + (c & 3); }
 
 // ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -26,6 +57,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -38,13 +72,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __noinline__ void mbar_timeout() {
+  printf("freqair gemm_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) {          // ~2 s at 2 GHz: a pipeline protocol bug, never a legal wait
-      printf("freqair gemm_tc: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000ll) mbar_timeout();     // ~2 s: a pipeline protocol bug, never a legal wait
   }
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -66,6 +102,7 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread (thread = TMEM lane = output row)
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(
@@ -82,15 +119,38 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor):
-//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float lo1(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float4 lo4(float4 v) { return make_float4(lo1(v.x), lo1(v.y), lo1(v.z), lo1(v.w)); }
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout type
+// K-major tile  : box {32 k, rows} -> smem [rows][128 B], TMA swizzle 128B (16-byte chunks XOR row%8), layout 2,
+//                 SBO = 1024 B (8 rows), k-step = +32 B inside the swizzle row.
+// MN-major tile : box {32 mn, 32 k} per 32-wide MN slab -> smem [slab][32 k][128 B], TMA swizzle 128B_ATOM_32B
+//                 (32-byte chunks XOR row%4), layout 1 = SWIZZLE_128B_BASE32B - the ONLY layout the tensor core accepts
+//                 for MN-major 32-bit operands (cutlass sm100_common.inl) - LBO = slab stride 4096 B, SBO = atom stride
+//                 512 B (4 k-rows), k-step (8 rows) = +1024 B.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool mn_major) {
+  const uint32_t lbo = mn_major ? 4096u : 16u, sbo = mn_major ? 512u : 1024u, layout = mn_major ? 1u : 2u;
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 
@@ -101,39 +161,97 @@ struct EpiTC {
   const float* residual; int64_t ldr;
   int accumulate; float alpha; int atomic;
   float* preact; int64_t ldpre;
+  int vec;     // every epilogue array is 16-byte aligned with a row pitch that is a multiple of 4 floats, and N % 4 == 0
 };
 
-// A_MN / B_MN: operand is MN-major in global memory (the reduction index is the ROW of the row-major matrix).
-// K-major tile  : box {32 k, rows}  -> smem [rows][128 B], one TMA load, k-step = +32 B inside the swizzle row.
-// MN-major tile : box {32 mn, 32 k} per 32-wide MN slab -> smem [slab][32 k][128 B]; k-step (8 rows) = +1024 B,
-//                 LBO = slab stride = 4096 B, SBO = 1024 B.
-template <int BN, int STAGES, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                           const __grid_constant__ CUtensorMap tmB,
-                                                           float* __restrict__ C, int M, int N, int K, int64_t ldc,
-                                                           int k_chunk, EpiTC epi) {
-  constexpr int A_BYTES = BM * BK * 4;
+struct TcGeom {
+  int M, N, K;
+  int64_t ldc;
+  int k_chunk, splits, tiles_m, tiles_n;
+  int a_mn, b_mn, x3, stages;
+};
+
+__device__ __forceinline__ float4 act4(float4 x, int act, float p) {
+  return make_float4(act_f(x.x, act, p), act_f(x.y, act, p), act_f(x.z, act, p), act_f(x.w, act, p));
+}
+__device__ __forceinline__ float4 actg4(float4 a, int act, float p) {
+  return make_float4(act_grad_f(a.x, act, p), act_grad_f(a.y, act, p), act_grad_f(a.z, act, p), act_grad_f(a.w, act, p));
+}
+
+// one float4 (4 consecutive columns of one output row) through the epilogue
+template <int MODE>
+__device__ __forceinline__ void epi_vec(float4 x, const EpiTC& e, float4 b4, int row, int col, float* __restrict__ cp) {
+  if (MODE == EPI_PLAIN || MODE == EPI_ANY) {
+    if (e.atomic) {
+      atomicAdd(reinterpret_cast<float4*>(cp), make_float4(x.x * e.alpha, x.y * e.alpha, x.z * e.alpha, x.w * e.alpha));
+      return;
+    }
+  }
+  x.x = fmaf(x.x, e.alpha, b4.x); x.y = fmaf(x.y, e.alpha, b4.y);
+  x.z = fmaf(x.z, e.alpha, b4.z); x.w = fmaf(x.w, e.alpha, b4.w);
+  if (MODE == EPI_FWD || MODE == EPI_ANY) {
+    if (e.preact) *reinterpret_cast<float4*>(e.preact + (int64_t)row * e.ldpre + col) = x;
+    if (e.act != ACT_NONE) x = act4(x, e.act, e.act_p);
+  }
+  if (MODE == EPI_BWD || MODE == EPI_ANY) {
+    if (e.aux) {
+      const float4 g = actg4(__ldg(reinterpret_cast<const float4*>(e.aux + (int64_t)row * e.ldaux + col)), e.aux_act, e.aux_p);
+      x.x *= g.x; x.y *= g.y; x.z *= g.z; x.w *= g.w;
+    }
+  }
+  if (MODE == EPI_FWD || MODE == EPI_ANY) {
+    if (e.rowscale) {
+      const float rs = __ldg(e.rowscale + row / e.rows_per_scale);
+      x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs;
+    }
+    if (e.residual) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(e.residual + (int64_t)row * e.ldr + col));
+      x.x += a.x; x.y += a.y; x.z += a.z; x.w += a.w;
+    }
+  }
+  if (MODE != EPI_FWD) {
+    if (e.accumulate) {
+      const float4 a = *reinterpret_cast<const float4*>(cp);
+      x.x += a.x; x.y += a.y; x.z += a.z; x.w += a.w;
+    }
+  }
+  *reinterpret_cast<float4*>(cp) = x;
+}
+
+template <int BN, int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                              const __grid_constant__ CUtensorMap tmB,
+                                                              float* __restrict__ C, const TcGeom g, const EpiTC epi) {
   constexpr int B_BYTES = BN * BK * 4;
-  constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  constexpr int TMEM_COLS = 2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : 256);
+  constexpr int NCHUNK = BN / 32;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int STAGES = g.stages;
+  const bool X3 = g.x3 != 0, A_MN = g.a_mn != 0, B_MN = g.b_mn != 0;
   unsigned char* sA = smem;
-  unsigned char* sB = smem + STAGES * A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  unsigned char* sB = sA + STAGES * A_BYTES;
+  unsigned char* sAlo = sB + STAGES * B_BYTES;                                // x3 only
+  unsigned char* sBlo = sAlo + (X3 ? STAGES * A_BYTES : 0);
+  float* stg_all = reinterpret_cast<float*>(sBlo + (X3 ? STAGES * B_BYTES : 0));   // [EPI_WARPS][32][32]
+  uint64_t* full = reinterpret_cast<uint64_t*>(stg_all + EPI_WARPS * 32 * 32);
+  uint64_t* empty = full + MAX_STAGES;
+  uint64_t* ready = empty + MAX_STAGES;       // lo tiles written (x3)
+  uint64_t* tmem_full = ready + MAX_STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int kbeg = blockIdx.z * k_chunk;
-  const int kend = min(K, kbeg + k_chunk);
-  const int nkb = (kend - kbeg + BK - 1) / BK;
+  const int total_tiles = g.tiles_m * g.tiles_n * g.splits;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], SPLIT_WARPS * 32); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
@@ -147,23 +265,30 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
   if (warp == 0) {
     if (lane == 0) {
       // ---------------------------------------------------------------- TMA producer
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
-        const int k0 = kbeg + kb * BK;
-        if (!A_MN) {
-          tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], k0, m0);
-        } else {
+      uint32_t it = 0;
+      int s = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int sp = t % g.splits, rest = t / g.splits;
+        const int m0 = (rest / g.tiles_n) * BM, n0 = (rest % g.tiles_n) * BN;
+        const int kbeg = sp * g.k_chunk;
+        const int nkb = (min(g.K, kbeg + g.k_chunk) - kbeg + BK - 1) / BK;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+          mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+          const int k0 = kbeg + kb * BK;
+          if (!A_MN) {
+            tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], k0, m0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BM / 32; ++j) tma_load_2d(sA + s * A_BYTES + j * 4096, &tmA, &full[s], m0 + 32 * j, k0);
-        }
-        if (!B_MN) {
-          tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], k0, n0);
-        } else {
+            for (int j = 0; j < BM / 32; ++j) tma_load_2d(sA + s * A_BYTES + j * 4096, &tmA, &full[s], m0 + 32 * j, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], k0, n0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 32; ++j) tma_load_2d(sB + s * B_BYTES + j * 4096, &tmB, &full[s], n0 + 32 * j, k0);
+            for (int j = 0; j < BN / 32; ++j) tma_load_2d(sB + s * B_BYTES + j * 4096, &tmB, &full[s], n0 + 32 * j, k0);
+          }
+          if (++s == STAGES) s = 0;
         }
       }
     }
@@ -173,65 +298,163 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
       // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32, a=b=tf32, majors, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(sA + s * A_BYTES), b0 = smem_u32(sB + s * B_BYTES);
+      const uint32_t astep = A_MN ? 1024u : 32u, bstep = B_MN ? 1024u : 32u;
+      uint32_t it = 0, lu = 0;           // lu = accumulation units issued (a unit = up to KC_BLOCKS k-blocks of one tile)
+      int s = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int sp = t % g.splits;
+        const int kbeg = sp * g.k_chunk;
+        const int nkb = (min(g.K, kbeg + g.k_chunk) - kbeg + BK - 1) / BK;
+        for (int kb0 = 0; kb0 < nkb; kb0 += KC_BLOCKS, ++lu) {
+          const uint32_t as = lu & 1;
+          mbar_wait(&tmem_empty[as], ((lu >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + as * BN;
+          const int kb1 = min(nkb, kb0 + KC_BLOCKS);
+          for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            mbar_wait(X3 ? &ready[s] : &full[s], (it / STAGES) & 1);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(sA + s * A_BYTES), b0 = smem_u32(sB + s * B_BYTES);
+            const uint32_t al0 = smem_u32(sAlo + s * A_BYTES), bl0 = smem_u32(sBlo + s * B_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t ad = A_MN ? make_desc(a0 + k * 1024, 4096, 1024) : make_desc(a0 + k * 32, 16, 1024);
-          const uint64_t bd = B_MN ? make_desc(b0 + k * 1024, 4096, 1024) : make_desc(b0 + k * 32, 16, 1024);
-          tc_mma_tf32(tmem_base, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t ad = make_desc(a0 + k * astep, A_MN), bd = make_desc(b0 + k * bstep, B_MN);
+              const uint32_t acc0 = (kb > kb0 || k > 0) ? 1u : 0u;
+              if (X3) {
+                tc_mma_tf32(d_tmem, make_desc(al0 + k * astep, A_MN), bd, idesc, acc0);     // small terms first
+                tc_mma_tf32(d_tmem, ad, make_desc(bl0 + k * bstep, B_MN), idesc, 1u);
+                tc_mma_tf32(d_tmem, ad, bd, idesc, 1u);
+              } else {
+                tc_mma_tf32(d_tmem, ad, bd, idesc, acc0);
+              }
+            }
+            tc_commit(&empty[s]);                      // frees the smem slot when these MMAs retire
+            if (++s == STAGES) s = 0;
+          }
+          tc_commit(&tmem_full[as]);                   // partial accumulator complete
         }
-        tc_commit(&empty[s]);                      // frees the smem slot when these MMAs retire
       }
-      tc_commit(tmem_full);                        // accumulator complete
+    }
+  } else if (warp < EPI_WARP0) {
+    // ------------------------------------------------------------------ split warps: lo = x - trunc_tf32(x)
+    if (X3) {
+      const int st = threadIdx.x - 64;        // 0..127
+      uint32_t it = 0;
+      int s = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int sp = t % g.splits;
+        const int kbeg = sp * g.k_chunk;
+        const int nkb = (min(g.K, kbeg + g.k_chunk) - kbeg + BK - 1) / BK;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          mbar_wait(&full[s], (it / STAGES) & 1);
+          const float4* a = reinterpret_cast<const float4*>(sA + s * A_BYTES);
+          float4* al = reinterpret_cast<float4*>(sAlo + s * A_BYTES);
+#pragma unroll
+          for (int i = 0; i < A_BYTES / 16 / (SPLIT_WARPS * 32); ++i) al[st + i * SPLIT_WARPS * 32] = lo4(a[st + i * SPLIT_WARPS * 32]);
+          const float4* b = reinterpret_cast<const float4*>(sB + s * B_BYTES);
+          float4* bl = reinterpret_cast<float4*>(sBlo + s * B_BYTES);
+#pragma unroll
+          for (int i = 0; i < B_BYTES / 16 / (SPLIT_WARPS * 32); ++i) bl[st + i * SPLIT_WARPS * 32] = lo4(b[st + i * SPLIT_WARPS * 32]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to UMMA
+          mbar_arrive(&ready[s]);
+          if (++s == STAGES) s = 0;
+        }
+      }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue: warps 2..5 own TMEM lanes 32*(warp%4)..
+    // ------------------------------------------------------------------ epilogue: warp w owns TMEM lanes 32*(w%4)..+31
+    const int ew = warp - EPI_WARP0;          // 0..EPI_WARPS-1
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    const bool row_ok = row < M;
-    const float rs = (epi.rowscale && row_ok) ? epi.rowscale[row / epi.rows_per_scale] : 1.0f;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (!row_ok || n0 + c0 >= N) continue;
-      float* crow = C + (int64_t)row * ldc + n0 + c0;
-      const int nvalid = min(32, N - (n0 + c0));
-      if (epi.atomic) {
-        for (int j = 0; j < nvalid; ++j) atomicAdd(crow + j, v[j] * epi.alpha);
-        continue;
-      }
+    const int half = ew >> 2;                 // which interleaved set of 32-column chunks: half, half+2
+    float* stg = stg_all + ew * (32 * 32);
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;        // vector path: a warp instruction covers 4 rows x 32 columns
+    uint32_t lu = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int sp = t % g.splits, rest = t / g.splits;
+      const int m0 = (rest / g.tiles_n) * BM, n0 = (rest % g.tiles_n) * BN;
+      const int kbeg = sp * g.k_chunk;
+      const int nkb = (min(g.K, kbeg + g.k_chunk) - kbeg + BK - 1) / BK;
+      float v[2][32];
+      for (int kb0 = 0; kb0 < nkb; kb0 += KC_BLOCKS, ++lu) {
+        const uint32_t as = lu & 1;
+        mbar_wait(&tmem_full[as], (lu >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (j < nvalid) {
-          const int n = n0 + c0 + j;
-          float x = v[j] * epi.alpha;
-          if (epi.bias) x += epi.bias[n];
-          if (epi.preact) epi.preact[(int64_t)row * epi.ldpre + n] = x;
-          x = act_f(x, epi.act, epi.act_p);
-          if (epi.aux) x *= act_grad_f(epi.aux[(int64_t)row * epi.ldaux + n], epi.aux_act, epi.aux_p);
-          x *= rs;
-          if (epi.residual) x += epi.residual[(int64_t)row * epi.ldr + n];
-          if (epi.accumulate) x += crow[j];
-          v[j] = x;
+        for (int ci = 0; ci < 2; ++ci) {
+          if (half + 2 * ci < NCHUNK) {
+            if (kb0 == 0) {
+              tc_ld32(taddr + (uint32_t)((half + 2 * ci) * 32), v[ci]);
+            } else {
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                float tmp[16];
+                tc_ld16(taddr + (uint32_t)((half + 2 * ci) * 32 + hh * 16), tmp);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[ci][hh * 16 + j] += tmp[j];
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);           // this TMEM stage may be overwritten
+      }
+      const int row0 = m0 + q * 32;
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        const int c = half + 2 * ci;
+        if (c < NCHUNK && n0 + c * 32 < g.N) {
+          // transpose through smem: thread = row writes its 32 columns (8 x float4, conflict-free by the XOR swizzle)
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj)
+            *reinterpret_cast<float4*>(&stg[stg_idx(lane, 4 * jj)]) =
+                make_float4(v[ci][4 * jj], v[ci][4 * jj + 1], v[ci][4 * jj + 2], v[ci][4 * jj + 3]);
+          __syncwarp();
+          if (epi.vec) {
+            const int col = n0 + c * 32 + c4;
+            if (col < g.N) {                                    // N % 4 == 0 on this path: all four columns valid
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (MODE == EPI_FWD || MODE == EPI_ANY)
+                if (epi.bias) b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
+              float* cp0 = C + (int64_t)(row0 + rsub) * g.ldc + col;
+#pragma unroll(MODE == EPI_ANY ? 1 : 4)
+              for (int it = 0; it < 8; ++it) {
+                const int r = it * 4 + rsub;
+                if (row0 + r < g.M)
+                  epi_vec<MODE>(*reinterpret_cast<const float4*>(&stg[stg_idx(r, c4)]), epi, b4, row0 + r, col,
+                                cp0 + (int64_t)it * 4 * g.ldc);
+              }
+            }
+          } else {
+            // scalar fallback (ragged N or unaligned rows): lane = column, every FaGemmEpilogue field honoured
+            const int col = n0 + c * 32 + lane;
+            const bool colok = col < g.N;
+            const float bias_v = (epi.bias && colok) ? epi.bias[col] : 0.f;
+            const int nrows = min(32, g.M - row0);
+#pragma unroll 1
+            for (int r = 0; r < nrows; ++r) {
+              const int row = row0 + r;
+              float x = stg[stg_idx(r, lane)] * epi.alpha;
+              if (!colok) continue;
+              float* cp = C + (int64_t)row * g.ldc + col;
+              if (epi.atomic) { atomicAdd(cp, x); continue; }
+              x += bias_v;
+              if (epi.preact) epi.preact[(int64_t)row * epi.ldpre + col] = x;
+              x = act_f(x, epi.act, epi.act_p);
+              if (epi.aux) x *= act_grad_f(epi.aux[(int64_t)row * epi.ldaux + col], epi.aux_act, epi.aux_p);
+              if (epi.rowscale) x *= epi.rowscale[row / epi.rows_per_scale];
+              if (epi.residual) x += epi.residual[(int64_t)row * epi.ldr + col];
+              if (epi.accumulate) x += *cp;
+              *cp = x;
+            }
+          }
+          __syncwarp();
         }
       }
-      if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      } else {
-        for (int j = 0; j < nvalid; ++j) crow[j] = v[j];
-      }
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -259,7 +482,8 @@ EncodeTiledFn get_encode() {
 }
 
 // row-major matrix [rows, cols] with row stride ld (floats); box = {box_cols (inner), box_rows}
-bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+              bool mn_major) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -267,51 +491,56 @@ bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
-template <int BN, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int M, int N, int K, int64_t ldc, int splits,
-           int k_chunk, const EpiTC& e, cudaStream_t st) {
-  constexpr int STAGES = (BN >= 128) ? 3 : 4;
-  constexpr size_t SMEM = 1024 + STAGES * (BM * BK * 4 + BN * BK * 4) + (2 * STAGES + 1) * 8 + 16;
-  auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN>;
+template <int BN, int MODE>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, float* C, TcGeom g, const EpiTC& e, cudaStream_t st) {
+  // one persistent CTA per SM; the operand ring takes what the 227 KB leave after the 32 KB epilogue transpose tiles
+  const int stage_bytes = (A_BYTES + BN * BK * 4) * (g.x3 ? 2 : 1);
+  const int tail_bytes = EPI_WARPS * 32 * 32 * 4 + (3 * MAX_STAGES + 4) * 8 + 16;
+  const int budget = 227 * 1024 - 1024 - tail_bytes;
+  int stages = budget / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  g.stages = stages;
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + tail_bytes;
+  auto kern = gemm_tc_kernel<BN, MODE>;
   static bool attr_done = false;
   if (!attr_done) {
-    FA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    FA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
-  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
-  kern<<<grid, NTHREADS, SMEM, st>>>(ta, tb, C, M, N, K, ldc, k_chunk, e);
+  const int64_t total = (int64_t)g.tiles_m * g.tiles_n * g.splits;
+  const int grid = (int)(total < kNumSMs ? total : kNumSMs);
+  kern<<<grid, NTHREADS, smem, st>>>(ta, tb, C, g, e);
   FA_LAUNCH_CHECK("fa_gemm(tcgen05)");
   return FA_OK;
 }
 
-template <bool A_MN, bool B_MN>
-int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, float* C, int M, int N, int K, int64_t ldc,
-                int splits, int k_chunk, const EpiTC& e, cudaStream_t st) {
+template <int MODE>
+int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, float* C, const TcGeom& g, const EpiTC& e,
+                cudaStream_t st) {
   switch (bn) {
-    case 32: return launch<32, A_MN, B_MN>(ta, tb, C, M, N, K, ldc, splits, k_chunk, e, st);
-    case 64: return launch<64, A_MN, B_MN>(ta, tb, C, M, N, K, ldc, splits, k_chunk, e, st);
-    case 96: return launch<96, A_MN, B_MN>(ta, tb, C, M, N, K, ldc, splits, k_chunk, e, st);
-    default: return launch<128, A_MN, B_MN>(ta, tb, C, M, N, K, ldc, splits, k_chunk, e, st);
+    case 32: return launch<32, MODE>(ta, tb, C, g, e, st);
+    case 64: return launch<64, MODE>(ta, tb, C, g, e, st);
+    case 96: return launch<96, MODE>(ta, tb, C, g, e, st);
+    default: return launch<128, MODE>(ta, tb, C, g, e, st);
   }
 }
 
 }  // namespace
 
 int fa_gemm_tc_launch(const float* A, const float* B, float* C, int M, int N, int K, int64_t lda, int64_t ldb,
-                      int64_t ldc, int transA, int transB, const FaGemmEpilogue* ep, cudaStream_t st, bool probe_only) {
+                      int64_t ldc, int transA, int transB, const FaGemmEpilogue* ep, cudaStream_t st, bool single_pass) {
   // eligibility: 16-byte aligned bases and row pitches (TMA), a tile-sized problem, driver entry point present
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (!al16(A) || !al16(B) || (lda % 4) || (ldb % 4)) return FA_ERR_UNSUPPORTED;
-  if (M < 64 || N < 16 || K < 8) return FA_ERR_UNSUPPORTED;
+  if (M < 8 || N < 8 || K < 8) return FA_ERR_UNSUPPORTED;
   const bool a_mn = transA != 0;          // op(A)[m,k] = A[k*lda+m]: reduction index is the row -> MN-major
   const bool b_mn = transB == 0;          // op(B)[k,n] = B[k*ldb+n]
   if (!get_encode()) return FA_ERR_UNSUPPORTED;
-  if (probe_only) return FA_OK;
 
   EpiTC e;
   memset(&e, 0, sizeof(e));
@@ -324,29 +553,59 @@ int fa_gemm_tc_launch(const float* A, const float* B, float* C, int M, int N, in
     e.residual = ep->residual; e.ldr = ep->ldr; e.accumulate = ep->accumulate; e.alpha = ep->alpha;
     e.preact = ep->preact; e.ldpre = ep->ldpre;
   }
-  // MN-major tiles are gathered in 32-wide slabs, so BN is a multiple of 32 there
-  int bn = N >= 128 ? 128 : (N > 96 ? 128 : (N > 64 ? 96 : (N > 32 ? 64 : 32)));
-  const int64_t tiles = (int64_t)((M + BM - 1) / BM) * ((N + bn - 1) / bn);
-  int splits = 1, k_chunk = K;
-  const bool plain = !e.bias && e.act == ACT_NONE && !e.aux && !e.rowscale && !e.residual && !e.preact;
-  if (plain && e.accumulate && tiles < 2 * kNumSMs && K >= 4096) {
-    splits = (int)((3 * kNumSMs + tiles - 1) / tiles);
-    int maxs = K / 1024; if (maxs < 1) maxs = 1;
-    if (splits > maxs) splits = maxs;
-    k_chunk = ((K + splits - 1) / splits + BK - 1) / BK * BK;
-    splits = (K + k_chunk - 1) / k_chunk;
-    if (splits > 1) e.atomic = 1;
+  e.vec = (N % 4 == 0) && al16(C) && (ldc % 4 == 0) && (!e.bias || al16(e.bias)) &&
+          (!e.aux || (al16(e.aux) && e.ldaux % 4 == 0)) && (!e.residual || (al16(e.residual) && e.ldr % 4 == 0)) &&
+          (!e.preact || (al16(e.preact) && e.ldpre % 4 == 0));
+  const bool fwd_like = e.bias || e.act != ACT_NONE || e.rowscale || e.residual || e.preact;
+  const bool plain = !fwd_like && !e.aux;
+  int mode;
+  if (plain) mode = EPI_PLAIN;
+  else if (!e.aux && !e.accumulate) mode = EPI_FWD;
+  else if (!fwd_like) mode = EPI_BWD;
+  else mode = EPI_ANY;
+
+  // Tiling.  N tile = the narrowest of {32, 64, 96, 128} that covers N, else 128.  When that leaves SMs idle:
+  //  - plain epilogues split the reduction (fp32 atomics into C; a non-accumulating call zero-fills C first),
+  //    which also bounds the length of each truncating tensor-core accumulation;
+  //  - the others narrow the N tile (MN-major tiles are gathered in 32-wide slabs, so BN stays a multiple of 32).
+  TcGeom g;
+  memset(&g, 0, sizeof(g));
+  g.M = M; g.N = N; g.K = K; g.ldc = ldc;
+  g.a_mn = a_mn; g.b_mn = b_mn; g.x3 = single_pass ? 0 : 1;
+  g.tiles_m = (M + BM - 1) / BM;
+  int bn = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 96 ? 96 : 128));
+  int64_t tiles = (int64_t)g.tiles_m * ((N + bn - 1) / bn);
+  g.splits = 1;
+  g.k_chunk = K;
+  if (tiles < kNumSMs) {
+    if (plain && e.vec && K >= 1024) {
+      int splits = (int)((2 * kNumSMs + tiles - 1) / tiles);
+      int maxs = K / 256; if (maxs < 1) maxs = 1;
+      if (splits > maxs) splits = maxs;
+      g.k_chunk = ((K + splits - 1) / splits + BK - 1) / BK * BK;
+      g.splits = (K + g.k_chunk - 1) / g.k_chunk;
+      if (g.splits > 1) {
+        e.atomic = 1;
+        if (!e.accumulate) FA_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st));
+      }
+    } else {
+      while (bn > 32 && (bn == 96 || (int64_t)g.tiles_m * ((N + bn - 1) / bn) < kNumSMs)) bn = (bn == 96) ? 64 : bn >> 1;
+    }
   }
+  g.tiles_n = (N + bn - 1) / bn;
+
   CUtensorMap ta, tb;
   bool ok;
-  if (!a_mn) ok = make_map(&ta, A, M, K, lda, BK, BM);          // A [M,K]: box {32 k, 128 m}
-  else ok = make_map(&ta, A, K, M, lda, 32, BK);                // A stored [K,M]: box {32 m, 32 k}
+  if (!a_mn) ok = make_map(&ta, A, M, K, lda, BK, BM, false);          // A [M,K]: box {32 k, 128 m}
+  else ok = make_map(&ta, A, K, M, lda, 32, BK, true);                // A stored [K,M]: box {32 m, 32 k}
   if (!ok) { fa_set_error("fa_gemm(tcgen05): cuTensorMapEncodeTiled failed for A"); return FA_ERR_CUDA; }
-  if (!b_mn) ok = make_map(&tb, B, N, K, ldb, BK, bn);          // W [N,K]: box {32 k, bn n}
-  else ok = make_map(&tb, B, K, N, ldb, 32, BK);                // B stored [K,N]: box {32 n, 32 k}
+  if (!b_mn) ok = make_map(&tb, B, N, K, ldb, BK, bn, false);          // W [N,K]: box {32 k, bn n}
+  else ok = make_map(&tb, B, K, N, ldb, 32, BK, true);                // B stored [K,N]: box {32 n, 32 k}
   if (!ok) { fa_set_error("fa_gemm(tcgen05): cuTensorMapEncodeTiled failed for B"); return FA_ERR_CUDA; }
-  if (!a_mn && !b_mn) return dispatch_bn<false, false>(bn, ta, tb, C, M, N, K, ldc, splits, k_chunk, e, st);
-  if (!a_mn && b_mn) return dispatch_bn<false, true>(bn, ta, tb, C, M, N, K, ldc, splits, k_chunk, e, st);
-  if (a_mn && !b_mn) return dispatch_bn<true, false>(bn, ta, tb, C, M, N, K, ldc, splits, k_chunk, e, st);
-  return dispatch_bn<true, true>(bn, ta, tb, C, M, N, K, ldc, splits, k_chunk, e, st);
+  switch (mode) {
+    case EPI_PLAIN: return dispatch_bn<EPI_PLAIN>(bn, ta, tb, C, g, e, st);
+    case EPI_FWD: return dispatch_bn<EPI_FWD>(bn, ta, tb, C, g, e, st);
+    case EPI_BWD: return dispatch_bn<EPI_BWD>(bn, ta, tb, C, g, e, st);
+    default: return dispatch_bn<EPI_ANY>(bn, ta, tb, C, g, e, st);
+  }
 }

@@ -5,6 +5,7 @@ kernels on ``torch.cuda.current_stream()``.  PyTorch is the allocator and the st
 arithmetic happens in ``libfreqair.so``.  Nothing here can run without a CUDA device.
 """
 import ctypes
+import os
 
 import torch
 
@@ -13,6 +14,9 @@ from ._lib import FaGemmEpilogue
 
 ACT_NONE, ACT_GELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
 FLOP_COUNTER = [None]          # bench.py roofline leg: set to 0 to accumulate 2*M*N*K of every fa_gemm call
+# fa_gemm backend used when a call does not name one: 0 = auto (tcgen05 3xTF32 where eligible, else fp32 SIMT).
+# FREQAIR_GEMM_BACKEND=1 forces the fp32 SIMT kernel everywhere (A/B accuracy and speed comparisons).
+DEFAULT_GEMM_BACKEND = int(os.environ.get('FREQAIR_GEMM_BACKEND', '0'))
 K_GEMM, K_WIN_ATTN, K_JOINT_ATTN, K_BAND, K_LN, K_DWCONV, K_IM2COL, K_BN, K_OPTIM, K_DCN, K_ELEM = range(1, 12)
 
 
@@ -67,7 +71,7 @@ def _rows2d(t):
 
 def gemm(A, B, C, transA=False, transB=True, bias=None, act=ACT_NONE, act_param=0.0, aux=None, aux_act=ACT_NONE,
          aux_param=0.0, rowscale=None, rows_per_scale=1, residual=None, accumulate=False, alpha=1.0, preact=None,
-         backend=0):
+         backend=None):
     """C = epi(alpha * op(A) @ op(B)); see fa_gemm in include/freqair.h.  A, B, C, aux, residual, preact are 2-D
     row-major views (row stride may exceed the width).  transB=True means B is an nn.Linear weight [N, K]."""
     ar, ac, lda = _rows2d(A)
@@ -81,6 +85,8 @@ def gemm(A, B, C, transA=False, transB=True, bias=None, act=ACT_NONE, act_param=
         raise RuntimeError(f'freqair.gemm: C is {cr}x{cc}, expected {M}x{N}')
     if FLOP_COUNTER[0] is not None:
         FLOP_COUNTER[0] += 2 * M * N * K
+    if backend is None:
+        backend = DEFAULT_GEMM_BACKEND
     e = FaGemmEpilogue()
     e.bias = bias.data_ptr() if bias is not None else None
     e.act, e.act_param = act, act_param

@@ -45,8 +45,9 @@ enum { FA_ACT_NONE = 0, FA_ACT_GELU = 1, FA_ACT_LRELU = 2, FA_ACT_SIGMOID = 3 };
  * ref: every nn.Linear on the path - decoder_Uformer.py:121-122,294; encoder_Uformer.py:96-97,305;
  *      leff.py:98,114; encoder_Uformer.py:975 (448->65536 head); encoder_ViT.py:77,97; and the
  *      autograd backward of each (cuBLAS sgemm in the reference).
- * backend: 0 = auto (tcgen05 kind::tf32 when the shape is eligible, else fp32 SIMT),
- *          1 = force fp32 SIMT, 2 = force tcgen05 (error if not eligible). */
+ * backend: 0 = auto (tcgen05 error-compensated 3xTF32 - fp32-level accuracy - when the shape is eligible, else fp32
+ *          SIMT), 1 = force fp32 SIMT, 2 = force tcgen05 3xTF32 (error if not eligible), 3 = force tcgen05 single-pass
+ *          TF32 (operands truncated to 10 mantissa bits; measurement / comparison only). */
 typedef struct FaGemmEpilogue {
   const float* bias;
   int act; float act_param;

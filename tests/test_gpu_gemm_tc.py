@@ -1,0 +1,123 @@
+"""GPU: the TMA + tcgen05 contraction kernel against fp64 torch on the same seeded inputs.
+backend 2 = the product path, error-compensated 3xTF32: must match fp64 to fp32 round-off (2e-6 * sqrt(K) * scale).
+backend 3 = single-pass kind::tf32 (measurement only): the tensor core truncates both operands to 10 mantissa bits,
+products accumulate in fp32; raw fp32 inputs are allowed 6e-3 * sqrt(K) * rms(a) * rms(b).  Layout / descriptor / pipeline correctness is pinned EXACTLY: operands
+quantised to multiples of 1/64 in [-4, 4] are TF32-representable, every product is a multiple of 2^-12 and every
+partial sum stays below 2^12, so fp32 accumulation is exact in any order and the result must equal fp64 torch."""
+import importlib
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import PKG_NAME
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops():
+    return importlib.import_module(PKG_NAME + '.ops')
+
+
+def gen(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return torch.randn(*shape, generator=g) * scale
+
+
+def quant(t):
+    return ((t * 64).round() / 64).clamp(-4, 4)
+
+
+def tf32_close(C, ref, K, what, ascale=1.0, bscale=1.0):
+    C, ref = C.detach().double().cpu(), ref.double().cpu()
+    assert C.shape == ref.shape
+    err = (C - ref).abs().max().item()
+    tol = 6e-3 * math.sqrt(max(K, 1)) * ascale * bscale + 1e-6
+    assert err <= tol, f'{what}: max err {err:.3e} > {tol:.3e}'
+
+
+# shapes of the LeWin / LeFF / head path: ragged K (28, 56), ragged M and N, deep K, all four operand layouts
+SHAPES = [(128, 32, 32), (256, 56, 56), (4096, 224, 56), (1000, 112, 28), (2048, 448, 3584), (300, 96, 448),
+          (64, 16, 8), (129, 33 * 4, 200), (1024, 65536 // 16, 448), (512, 8, 72), (512, 27, 144), (516, 24, 72),
+          (40, 12, 520), (8, 8, 8)]
+
+
+@pytest.mark.parametrize('backend', [2, 3])
+@pytest.mark.parametrize('M,N,K', SHAPES)
+@pytest.mark.parametrize('tA,tB', [(False, True), (False, False), (True, False), (True, True)])
+def test_gemm_tc_plain(ops, M, N, K, tA, tB, backend):
+    if (tA and M % 4) or ((not tA) and K % 4) or (tB and K % 4) or ((not tB) and N % 4):    # lda / ldb pitch
+        pytest.skip('row pitch not 16-byte aligned: SIMT path covers it')
+    A = quant(gen(K, M) if tA else gen(M, K))
+    B = quant(gen(N, K, seed=1) if tB else gen(K, N, seed=1))
+    C = torch.full((M, N), float('nan'), device='cuda')
+    ops.gemm(A.cuda(), B.cuda(), C, transA=tA, transB=tB, backend=backend)
+    ref = (A.t() if tA else A).double() @ (B.t() if tB else B).double()
+    assert ref.abs().max().item() < 4096
+    err = (C.double().cpu() - ref).abs().max().item()
+    assert err == 0.0, f'tc gemm {M}x{N}x{K} tA={tA} tB={tB}: max err {err:.3e} on exactly representable data'
+
+
+@pytest.mark.parametrize('M,N,K,tA,tB', [(4096, 224, 56, False, True), (2048, 448, 3584, False, False),
+                                         (1024, 4096, 448, False, True), (448, 224, 8192, True, False)])
+def test_gemm_tc_fp32_inputs(ops, M, N, K, tA, tB):
+    A = gen(K, M) if tA else gen(M, K)
+    B = gen(N, K, seed=1) if tB else gen(K, N, seed=1)
+    ref = (A.t() if tA else A).double() @ (B.t() if tB else B).double()
+    C = torch.full((M, N), float('nan'), device='cuda')
+    ops.gemm(A.cuda(), B.cuda(), C, transA=tA, transB=tB, backend=3)
+    tf32_close(C, ref, K, f'tc gemm 1xTF32 {M}x{N}x{K} tA={tA} tB={tB}')
+    # product path: fp32-level accuracy, and no worse than the exact-fp32 SIMT kernel by more than 2x
+    C3 = torch.full((M, N), float('nan'), device='cuda')
+    ops.gemm(A.cuda(), B.cuda(), C3, transA=tA, transB=tB, backend=2)
+    C1 = torch.full((M, N), float('nan'), device='cuda')
+    ops.gemm(A.cuda(), B.cuda(), C1, transA=tA, transB=tB, backend=1)
+    e3 = (C3.double().cpu() - ref).abs().max().item()
+    e1 = (C1.double().cpu() - ref).abs().max().item()
+    assert e3 <= 3 * e1 + 1e-6, f'3xTF32 {M}x{N}x{K}: max err {e3:.3e} (fp32 SIMT {e1:.3e})'
+    print(f'3xTF32 err {e3:.3e}, fp32 SIMT err {e1:.3e}')
+
+
+def test_gemm_tc_epilogues(ops):
+    M, N, K = 320, 224, 56
+    A, W, b = gen(M, K), gen(N, K, seed=1), gen(N, seed=2)
+    R, aux = gen(M, N, seed=3), gen(M, N, seed=4)
+    rs = torch.tensor([0.0, 1.0 / 0.9, 1.0 / 0.9, 1.0, 0.5])
+    base = (A.double() @ W.double().t() + b.double()).float()
+    dA, dW, db = A.cuda(), W.cuda(), b.cuda()
+    C = torch.empty(M, N, device='cuda'); pre = torch.empty(M, N, device='cuda')
+    ops.gemm(dA, dW, C, bias=db, act=ops.ACT_GELU, preact=pre, backend=2)
+    tf32_close(pre, base, K, 'preact'); tf32_close(C, F.gelu(base), K, 'gelu')
+    ops.gemm(dA, dW, C, bias=db, act=ops.ACT_LRELU, act_param=0.1, backend=2)
+    tf32_close(C, F.leaky_relu(base, 0.1), K, 'lrelu')
+    ops.gemm(dA, dW, C, bias=db, rowscale=rs.cuda(), rows_per_scale=64, residual=R.cuda(), backend=2)
+    tf32_close(C, R + rs.repeat_interleave(64)[:, None] * base, K, 'residual+rowscale')
+    ag = aux.clone().requires_grad_(True)
+    F.gelu(ag).sum().backward()
+    ops.gemm(dA, dW, C, aux=aux.cuda(), aux_act=ops.ACT_GELU, backend=2)
+    tf32_close(C, (A @ W.t()) * ag.grad, K, 'dgelu')
+    big = torch.zeros(M, 2 * N, device='cuda'); big[:, N:] = R.cuda()
+    ops.gemm(dA, dW, big[:, N:], accumulate=True, alpha=0.5, backend=2)
+    tf32_close(big[:, N:], R + 0.5 * (A @ W.t()), K, 'accumulate strided')
+    assert big[:, :N].abs().max().item() == 0
+
+
+def test_gemm_tc_splitk_weight_grad(ops):
+    M, N, K = 40000, 56, 224          # dW[N,K] = dY^T[N,M] X[M,K], reduction over M (split-K + fp32 atomics)
+    dY, X = gen(M, N, scale=0.1), gen(M, K, seed=1)
+    G0 = gen(N, K, seed=2)
+    G = G0.cuda()
+    ops.gemm(dY.cuda(), X.cuda(), G, transA=True, transB=False, accumulate=True, backend=2)
+    tf32_close(G, G0 + (dY.double().t() @ X.double()).float(), M, 'split-k', ascale=0.1)
+
+
+def test_gemm_tc_matches_simt_on_tf32_exact_inputs(ops):
+    """Inputs already representable in TF32 (10-bit mantissa): both kernels must agree to fp32 round-off."""
+    M, N, K = 512, 128, 256
+    A, B = quant(gen(M, K)), quant(gen(N, K, seed=1))
+    C1 = torch.empty(M, N, device='cuda'); C2 = torch.empty(M, N, device='cuda')
+    ops.gemm(A.cuda(), B.cuda(), C1, backend=1)
+    ops.gemm(A.cuda(), B.cuda(), C2, backend=2)
+    assert (C1 - C2).abs().max().item() == 0.0

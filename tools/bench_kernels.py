@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""Micro-benchmark of the library's kernels on the shapes of the configs[1] train step (B=16, 128x128 crops).
+Prints one line per case: CUDA-event time (median of `reps`, L2 flushed between launches), TFLOP/s and GB/s of the
+algorithmic bytes.  Usage (GPU box):  python tools/bench_kernels.py gemm [--backend 0|1|2]
+"""
+import argparse
+import importlib
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+PKG = 'frequency-wised_all-in-one_image_restoration_model_b200'
+ops = importlib.import_module(PKG + '.ops')
+
+FLUSH = None
+
+
+def timeit(fn, reps=7, flush=True):
+    global FLUSH
+    if FLUSH is None:
+        FLUSH = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    for _ in range(2):
+        fn()
+    ts = []
+    for _ in range(reps):
+        if flush:
+            FLUSH.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def gemm_cases():
+    B = 16
+    cases = []
+    # decoder levels: (res, dim)
+    for res, dim in [(128, 56), (64, 112), (32, 224), (16, 448), (8, 896), (16, 896), (32, 448), (64, 224), (128, 112)]:
+        T = B * res * res
+        cases += [(f'dec{res}/{dim} q', T, dim, dim), (f'dec{res}/{dim} kv', T, 2 * dim, dim),
+                  (f'dec{res}/{dim} leff1', T, 4 * dim, dim), (f'dec{res}/{dim} leff2', T, dim, 4 * dim)]
+    for res, dim in [(128, 28), (64, 56), (32, 112), (16, 224), (8, 448)]:
+        T = 3 * B * res * res
+        cases += [(f'enc{res}/{dim} kv', T, 2 * dim, dim), (f'enc{res}/{dim} leff1', T, 4 * dim, dim)]
+    cases += [('head 448->65536', B * 64, 65536, 448)]
+    return cases
+
+
+def bench_gemm(backend, only=None, layouts='NT,NN,TN'):
+    print(f'{"case":24s} {"layout":3s} {"M":>8s} {"N":>6s} {"K":>6s} {"ms":>8s} {"TFLOP/s":>8s} {"GB/s":>8s}')
+    for name, M, N, K in gemm_cases():
+        if only and only not in name:
+            continue
+        X = torch.randn(M, K, device='cuda')
+        W = torch.randn(N, K, device='cuda') * 0.05
+        Y = torch.empty(M, N, device='cuda')
+        dX = torch.empty(M, K, device='cuda')
+        dW = torch.zeros(N, K, device='cuda')
+        for lay, fn, flops, byts in [
+            ('NT', lambda: ops.gemm(X, W, Y, backend=backend), 2 * M * N * K, 4 * (M * K + N * K + M * N)),
+            ('NN', lambda: ops.gemm(Y, W, dX, transB=False, backend=backend), 2 * M * N * K, 4 * (M * N + N * K + M * K)),
+            ('TN', lambda: ops.gemm(Y, X, dW, transA=True, transB=False, accumulate=True, backend=backend), 2 * M * N * K,
+             4 * (M * N + M * K + N * K)),
+        ]:
+            if lay not in layouts.split(','):
+                continue
+            try:
+                ms = timeit(fn)
+            except RuntimeError as e:
+                print(f'{name:24s} {lay:3s} {M:8d} {N:6d} {K:6d}   error: {str(e)[:80]}')
+                continue
+            print(f'{name:24s} {lay:3s} {M:8d} {N:6d} {K:6d} {ms:8.3f} {flops / ms / 1e9:8.1f} {byts / ms / 1e6:8.0f}', flush=True)
+        del X, W, Y, dX, dW
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('what', choices=['gemm'])
+    ap.add_argument('--backend', type=int, default=0)
+    ap.add_argument('--only', default=None)
+    ap.add_argument('--layouts', default='NT,NN,TN')
+    a = ap.parse_args()
+    if a.what == 'gemm':
+        bench_gemm(a.backend, a.only, a.layouts)
