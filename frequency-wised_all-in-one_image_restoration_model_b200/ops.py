@@ -38,8 +38,18 @@ def _f32(*ts):
             raise RuntimeError(f'freqair: expected a contiguous float32 tensor, got {t.dtype} strides {t.stride()}')
 
 
+PROFILE = None                 # tools/profile_step.py: list that receives (name, int-args signature, event0, event1)
+
+
 def _call(name, *args):
     lib = _lib.load()
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(getattr(lib, name)(*args), name)
+        e1.record()
+        PROFILE.append((name, tuple(a for a in args if isinstance(a, int) and not isinstance(a, bool) and abs(a) < (1 << 31)), e0, e1))
+        return
     _lib.check(getattr(lib, name)(*args), name)
 
 

@@ -50,13 +50,18 @@ class Segment:
 
 
 class BucketedAllReduce:
-    """Gradient mean over ranks in ~bucket_mb slices of the flat gradient buffers, launched from
-    post-accumulate-grad hooks on a side stream as soon as every parameter of a bucket has its gradient."""
+    """Gradient SUM over ranks in ~bucket_mb slices of the flat gradient buffers, launched from
+    post-accumulate-grad hooks on a side stream as soon as every parameter of a bucket has its gradient.
+    The 1/world_size of the mean rides the optimiser kernel (``fa_adam_step(grad_scale=...)``), so no extra pass
+    touches the 1.09 GB of gradients.  Device-agnostic on purpose: the bucket / hook logic is exercised on CPU
+    with the gloo backend at world_size 2 (tests/test_ddp_gloo.py); on CUDA the collectives run on a side stream."""
 
     def __init__(self, segments, bucket_mb=64, group=None):
         import torch.distributed as dist
         self.dist, self.group = dist, group
-        self.stream = torch.cuda.Stream()
+        self.on_cuda = segments[0].grad.is_cuda
+        self.stream = torch.cuda.Stream() if self.on_cuda else None
+        self.world = dist.get_world_size(group)
         self.buckets = []          # (tensor slice, n_params)
         self.pending = []
         self.handles = []
@@ -94,11 +99,15 @@ class BucketedAllReduce:
         if self.launched[b]:
             return
         self.launched[b] = True
+        if not self.on_cuda:
+            self.handles.append(self.dist.all_reduce(self.buckets[b][0], op=self.dist.ReduceOp.SUM, group=self.group,
+                                                     async_op=True))
+            return
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ev)
-            self.handles.append(self.dist.all_reduce(self.buckets[b][0], op=self.dist.ReduceOp.AVG, group=self.group,
+            self.handles.append(self.dist.all_reduce(self.buckets[b][0], op=self.dist.ReduceOp.SUM, group=self.group,
                                                      async_op=True))
 
     def finish(self):
@@ -107,7 +116,8 @@ class BucketedAllReduce:
                 self._launch(b)
         for h in self.handles:
             h.wait()
-        torch.cuda.current_stream().wait_stream(self.stream)
+        if self.on_cuda:
+            torch.cuda.current_stream().wait_stream(self.stream)
         self.reset()
 
 
@@ -146,7 +156,8 @@ class TrainStep:
         if self.ddp is not None:
             self.ddp.finish()
         self.t += 1
+        gscale = 1.0 / self.ddp.world if self.ddp is not None else 1.0       # mean over ranks, fused into Adam
         for s in self.segments:
-            ops.adam_step(s.flat, s.grad, s.m, s.v, self.lr, self.betas[0], self.betas[1], self.eps, self.t)
+            ops.adam_step(s.flat, s.grad, s.m, s.v, self.lr, self.betas[0], self.betas[1], self.eps, self.t, gscale)
         self.last = dict(loss=loss.detach(), l1=l1.detach(), ce=ce.detach())
         return self.last['loss']
