@@ -156,7 +156,11 @@ def main():
     ap.add_argument('--batch', type=int, default=BATCH, help='crops per GPU (the headline config uses 16)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-roofline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch the step kernel by kernel instead of replaying its CUDA graph')
     args = ap.parse_args()
+    if os.environ.get('FREQAIR_WATCHDOG'):                 # debugging aid: dump every thread's stack and exit if stuck
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ['FREQAIR_WATCHDOG']), exit=True)
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -193,6 +197,11 @@ def main():
     for _ in range(W):
         ts.step(*dev_in)
     barrier()
+    if not args.no_graph:
+        ts.capture(*dev_in)                                # whole step -> one CUDA graph; step() replays it from here on
+        for _ in range(2):
+            ts.step(*dev_in)
+        barrier()
     # ---------------------------------------------------------------- value: device-resident inputs
     sampler = ClockSampler(local)
     sampler.start()
@@ -230,6 +239,8 @@ def main():
     cpu_baseline = None
     if rank == 0 and not args.no_roofline:
         # dominant kernel class = the dense contractions (fa_gemm): time every launch with in-stream events
+        # (kernel-by-kernel launch of the same step: a graph replay cannot be bracketed per launch)
+        ts.graph = None
         ops.FLOP_COUNTER[0] = 0
         ops.prof_begin(ops.K_GEMM)
         ts.step(*dev_in)
@@ -260,6 +271,7 @@ def main():
                 'config': {'workload': 'configs[1]: Uformer encoder + Uformer decoder (all_3_bands, L=3, freq MSA) full '
                                        'train step incl. Adam, 128x128 crops, sigma=25 synthetic noise, random init',
                            'batch_per_gpu': B, 'global_batch': B * world, 'parallelism': f'dp{world}',
+                           'launch': 'eager' if args.no_graph else 'cuda_graph',
                            'l2': 'no explicit flush: one step streams >20 GB of activations + 4.5 GB of weights/optimizer '
                                  'state, far beyond the 126 MB L2'},
                 'clocks': clocks,

@@ -12,127 +12,138 @@ __device__ __forceinline__ float4 fma4(float4 a, float4 b, float4 c) {
 }
 
 // ------------------------------------------------------------------ depthwise 3x3 (LeFF)
-// weights in the reference layout [C][1][3][3]; staged transposed as wt[tap][C] so a channel quad is one float4.
-__global__ void __launch_bounds__(256) dwconv_fwd_kernel(const float* __restrict__ h1, const float* __restrict__ w,
-                                                         const float* __restrict__ bias, float* __restrict__ u2,
-                                                         float* __restrict__ h2, int B, int H, int W, int C) {
-  const int C4 = C >> 2;
-  const int64_t total = (int64_t)B * H * W * C4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C4) * 4;
-    int64_t p = i / C4;
-    const int x = (int)(p % W); p /= W;
-    const int y = (int)(p % H);
-    const int b = (int)(p / H);
-    float4 acc = bias ? ld4(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+// Sliding-window strips: a thread owns one channel quad (its 9 weight float4s live in registers for the whole
+// kernel) and walks a strip of DW_R rows x `seg` columns left to right, keeping a 3-column x (DW_R+2)-row window of
+// float4s in registers, so each step loads DW_R+2 values for DW_R outputs (1.6 loads per output instead of 9, and no
+// per-tap weight traffic).  Lanes of a warp are consecutive channel quads: every access is a contiguous 512-byte row.
+// weights in the reference layout [C][1][3][3].
+constexpr int DW_R = 4;
+struct StripGeom { int B, H, W, C, nys, nxs, seg; };
+
+__device__ __forceinline__ void strip_decode(int strip, const StripGeom& g, int& b, int& y0, int& x0) {
+  const int xs = strip % g.nxs; strip /= g.nxs;
+  const int ys = strip % g.nys;
+  b = strip / g.nys;
+  y0 = ys * DW_R;
+  x0 = xs * g.seg;
+}
+__device__ __forceinline__ void strip_loadcol(const float* __restrict__ base, int x, int y0, const StripGeom& g,
+                                              float4 (&col)[DW_R + 2]) {
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int yy = y + ky - 1;
-      if (yy < 0 || yy >= H) continue;
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int xx = x + kx - 1;
-        if (xx < 0 || xx >= W) continue;
-        const float4 v = ld4(h1 + (((int64_t)b * H + yy) * W + xx) * C + c);
-        const int t = ky * 3 + kx;
-        const float4 wv = make_float4(w[(c + 0) * 9 + t], w[(c + 1) * 9 + t], w[(c + 2) * 9 + t], w[(c + 3) * 9 + t]);
-        acc = fma4(v, wv, acc);
-      }
-    }
-    const int64_t o = (((int64_t)b * H + y) * W + x) * C + c;
-    st4(u2 + o, acc);
-    if (h2) st4(h2 + o, make_float4(gelu_f(acc.x), gelu_f(acc.y), gelu_f(acc.z), gelu_f(acc.w)));
+  for (int rr = 0; rr < DW_R + 2; ++rr) {
+    const int yy = y0 - 1 + rr;
+    col[rr] = (x >= 0 && x < g.W && yy >= 0 && yy < g.H) ? ld4(base + ((int64_t)yy * g.W + x) * g.C)
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
-// du1 = gelu'(u1) * sum_taps w[c][tap] * du2[p - delta(tap)]
-__global__ void __launch_bounds__(256) dwconv_bwd_data_kernel(const float* __restrict__ du2,
-                                                              const float* __restrict__ u1,
-                                                              const float* __restrict__ w, float* __restrict__ du1,
-                                                              int B, int H, int W, int C) {
-  const int C4 = C >> 2;
-  const int64_t total = (int64_t)B * H * W * C4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C4) * 4;
-    int64_t p = i / C4;
-    const int x = (int)(p % W); p /= W;
-    const int y = (int)(p % H);
-    const int b = (int)(p / H);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+// BWD = false: u2 = dwconv(h1) + b ; h2 = gelu(u2)
+// BWD = true : du1 = gelu'(u1) * dwconv^T(du2)   (the adjoint is the same stencil with the taps reversed)
+template <bool BWD>
+__global__ void __launch_bounds__(256) dwconv_strip_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, const float* __restrict__ u1,
+                                                           float* __restrict__ outA, float* __restrict__ outB,
+                                                           StripGeom g, int nstrips) {
+  const int c = (blockIdx.y * 32 + threadIdx.x) * 4;
+  if (c >= g.C) return;
+  float4 wv[9];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int yy = y - (ky - 1);              // output pixel that read us through tap (ky,kx)
-      if (yy < 0 || yy >= H) continue;
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int xx = x - (kx - 1);
-        if (xx < 0 || xx >= W) continue;
-        const float4 g = ld4(du2 + (((int64_t)b * H + yy) * W + xx) * C + c);
-        const int t = ky * 3 + kx;
-        const float4 wv = make_float4(w[(c + 0) * 9 + t], w[(c + 1) * 9 + t], w[(c + 2) * 9 + t], w[(c + 3) * 9 + t]);
-        acc = fma4(g, wv, acc);
-      }
-    }
-    const int64_t o = (((int64_t)b * H + y) * W + x) * C + c;
-    if (u1) {
-      const float4 u = ld4(u1 + o);
-      acc = make_float4(acc.x * gelu_grad_f(u.x), acc.y * gelu_grad_f(u.y), acc.z * gelu_grad_f(u.z),
-                        acc.w * gelu_grad_f(u.w));
-    }
-    st4(du1 + o, acc);
+  for (int t = 0; t < 9; ++t) {
+    const int ti = BWD ? 8 - t : t;
+    wv[t] = make_float4(w[(c + 0) * 9 + ti], w[(c + 1) * 9 + ti], w[(c + 2) * 9 + ti], w[(c + 3) * 9 + ti]);
   }
-}
-
-// dw[c][tap] += sum_p du2[p,c] * h1[p + delta(tap), c];  db[c] += sum_p du2[p,c]
-// block = 32 channel-quads x 8 pixel lanes, PIX pixels per block.
-constexpr int DW_PIX = 512;
-__global__ void __launch_bounds__(256) dwconv_bwd_weight_kernel(const float* __restrict__ du2,
-                                                                const float* __restrict__ h1, float* __restrict__ dw,
-                                                                float* __restrict__ db, int B, int H, int W, int C) {
-  __shared__ float red[8][32][41];
-  const int cq = threadIdx.x & 31, pl = threadIdx.x >> 5;
-  const int c = (blockIdx.y * 32 + cq) * 4;
-  const bool cok = c < C;
-  const int64_t T = (int64_t)B * H * W;
-  const int64_t p0 = (int64_t)blockIdx.x * DW_PIX;
-  float acc[9][4];
-  float accb[4] = {0.f, 0.f, 0.f, 0.f};
+  const float4 bv = (!BWD && bias) ? ld4(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int strip = blockIdx.x * blockDim.y + threadIdx.y; strip < nstrips; strip += gridDim.x * blockDim.y) {
+    int b, y0, x0;
+    strip_decode(strip, g, b, y0, x0);
+    const int64_t img = (int64_t)b * g.H * g.W * g.C + c;
+    const float* base = in + img;
+    float4 win[3][DW_R + 2];
+    strip_loadcol(base, x0 - 1, y0, g, win[1]);
+    strip_loadcol(base, x0, y0, g, win[2]);
+    const int x1 = min(g.W, x0 + g.seg);
+    for (int x = x0; x < x1; ++x) {
 #pragma unroll
-  for (int t = 0; t < 9; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
-  if (cok) {
-    for (int64_t p = p0 + pl; p < min(T, p0 + DW_PIX); p += 8) {
-      const int x = (int)(p % W);
-      const int y = (int)((p / W) % H);
-      const float4 g = ld4(du2 + p * C + c);
-      accb[0] += g.x; accb[1] += g.y; accb[2] += g.z; accb[3] += g.w;
+      for (int rr = 0; rr < DW_R + 2; ++rr) { win[0][rr] = win[1][rr]; win[1][rr] = win[2][rr]; }
+      strip_loadcol(base, x + 1, y0, g, win[2]);
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const int yy = y + ky - 1;
-        if (yy < 0 || yy >= H) continue;
+      for (int r = 0; r < DW_R; ++r) {
+        if (y0 + r >= g.H) break;
+        float4 acc = bv;
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int xx = x + kx - 1;
-          if (xx < 0 || xx >= W) continue;
-          const float4 v = ld4(h1 + (p + (int64_t)(ky - 1) * W + (kx - 1)) * C + c);
-          const int t = ky * 3 + kx;
-          acc[t][0] = fmaf(g.x, v.x, acc[t][0]); acc[t][1] = fmaf(g.y, v.y, acc[t][1]);
-          acc[t][2] = fmaf(g.z, v.z, acc[t][2]); acc[t][3] = fmaf(g.w, v.w, acc[t][3]);
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) acc = fma4(win[kx][r + ky], wv[ky * 3 + kx], acc);
+        const int64_t o = img + ((int64_t)(y0 + r) * g.W + x) * g.C;
+        if (!BWD) {
+          st4(outA + o, acc);
+          if (outB) st4(outB + o, make_float4(gelu_f(acc.x), gelu_f(acc.y), gelu_f(acc.z), gelu_f(acc.w)));
+        } else {
+          if (u1) {
+            const float4 u = ld4(u1 + o);
+            acc = make_float4(acc.x * gelu_grad_f(u.x), acc.y * gelu_grad_f(u.y), acc.z * gelu_grad_f(u.z),
+                              acc.w * gelu_grad_f(u.w));
+          }
+          st4(outA + o, acc);
         }
       }
     }
   }
+}
+
+// dw[c][tap] += sum_p du2[p,c] * h1[p + delta(tap), c];  db[c] += sum_p du2[p,c]
+// Same strips, window over h1; 36 + 4 accumulators per thread persist over all the strips a thread visits, then the
+// 8 strip lanes of a block are reduced in shared memory and flushed with one atomic per (channel, tap) per block.
+__global__ void __launch_bounds__(256) dwconv_wgrad_strip_kernel(const float* __restrict__ du2,
+                                                                 const float* __restrict__ h1, float* __restrict__ dw,
+                                                                 float* __restrict__ db, StripGeom g, int nstrips) {
+  __shared__ float red[8][32][41];
+  const int c = (blockIdx.y * 32 + threadIdx.x) * 4;
+  const bool cok = c < g.C;
+  float4 acc[9];
+  float4 accb = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int t = 0; t < 9; ++t)
+  for (int t = 0; t < 9; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (cok) {
+    for (int strip = blockIdx.x * blockDim.y + threadIdx.y; strip < nstrips; strip += gridDim.x * blockDim.y) {
+      int b, y0, x0;
+      strip_decode(strip, g, b, y0, x0);
+      const int64_t img = (int64_t)b * g.H * g.W * g.C + c;
+      const float* base = h1 + img;
+      float4 win[3][DW_R + 2];
+      strip_loadcol(base, x0 - 1, y0, g, win[1]);
+      strip_loadcol(base, x0, y0, g, win[2]);
+      const int x1 = min(g.W, x0 + g.seg);
+      for (int x = x0; x < x1; ++x) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) red[pl][cq][t * 4 + j] = acc[t][j];
+        for (int rr = 0; rr < DW_R + 2; ++rr) { win[0][rr] = win[1][rr]; win[1][rr] = win[2][rr]; }
+        strip_loadcol(base, x + 1, y0, g, win[2]);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) red[pl][cq][36 + j] = accb[j];
+        for (int r = 0; r < DW_R; ++r) {
+          if (y0 + r >= g.H) break;
+          const float4 gq = ld4(du2 + img + ((int64_t)(y0 + r) * g.W + x) * g.C);
+          accb.x += gq.x; accb.y += gq.y; accb.z += gq.z; accb.w += gq.w;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) acc[ky * 3 + kx] = fma4(gq, win[kx][r + ky], acc[ky * 3 + kx]);
+        }
+      }
+    }
+  }
+  const int pl = threadIdx.y, cq = threadIdx.x;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    red[pl][cq][t * 4 + 0] = acc[t].x; red[pl][cq][t * 4 + 1] = acc[t].y;
+    red[pl][cq][t * 4 + 2] = acc[t].z; red[pl][cq][t * 4 + 3] = acc[t].w;
+  }
+  red[pl][cq][36] = accb.x; red[pl][cq][37] = accb.y; red[pl][cq][38] = accb.z; red[pl][cq][39] = accb.w;
   __syncthreads();
-  // 32 quads x 40 values reduced over the 8 pixel lanes
-  for (int i = threadIdx.x; i < 32 * 40; i += 256) {
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  for (int i = tid; i < 32 * 40; i += 256) {
     const int q = i / 40, v = i % 40;
     const int cc = (blockIdx.y * 32 + q) * 4;
-    if (cc >= C) continue;
+    if (cc >= g.C) continue;
     float s = 0.f;
 #pragma unroll
     for (int l = 0; l < 8; ++l) s += red[l][q][v];
@@ -282,15 +293,31 @@ inline int ew_grid(int64_t total) {
 
 extern "C" {
 
+static StripGeom make_strips(int B, int H, int W, int C, int& nstrips, dim3& grid) {
+  StripGeom g;
+  g.B = B; g.H = H; g.W = W; g.C = C;
+  g.seg = W < 32 ? W : 32;
+  g.nys = (H + DW_R - 1) / DW_R;
+  g.nxs = (W + g.seg - 1) / g.seg;
+  nstrips = B * g.nys * g.nxs;
+  const int gy = (C / 4 + 31) / 32;
+  int gx = (nstrips + 7) / 8;
+  const int cap = (kNumSMs * 8 + gy - 1) / gy;          // ~8 resident blocks per SM in total
+  if (gx > cap) gx = cap;
+  grid = dim3((unsigned)(gx > 0 ? gx : 1), (unsigned)gy);
+  return g;
+}
+
 int fa_dwconv3x3_fwd(const float* h1, const float* w, const float* b, float* u2, float* h2, int B, int H, int W, int C,
                      fa_stream_t stream) {
   FA_REQUIRE(h1 && w && u2, "fa_dwconv3x3_fwd: null pointer");
   FA_REQUIRE(C % 4 == 0, "fa_dwconv3x3_fwd: C=%d must be a multiple of 4", C);
   cudaStream_t st = (cudaStream_t)stream;
   FaProfScope prof(FA_K_DWCONV, st);
-  const int64_t total = (int64_t)B * H * W * (C / 4);
-  if (total == 0) return FA_OK;
-  dwconv_fwd_kernel<<<ew_grid(total), 256, 0, st>>>(h1, w, b, u2, h2, B, H, W, C);
+  if ((int64_t)B * H * W * C == 0) return FA_OK;
+  int nstrips; dim3 grid;
+  const StripGeom g = make_strips(B, H, W, C, nstrips, grid);
+  dwconv_strip_kernel<false><<<grid, dim3(32, 8), 0, st>>>(h1, w, b, nullptr, u2, h2, g, nstrips);
   FA_LAUNCH_CHECK("fa_dwconv3x3_fwd");
   return FA_OK;
 }
@@ -301,16 +328,15 @@ int fa_dwconv3x3_bwd(const float* du2, const float* h1, const float* u1, const f
   FA_REQUIRE(C % 4 == 0, "fa_dwconv3x3_bwd: C=%d must be a multiple of 4", C);
   cudaStream_t st = (cudaStream_t)stream;
   FaProfScope prof(FA_K_DWCONV, st);
-  const int64_t total = (int64_t)B * H * W * (C / 4);
-  if (total == 0) return FA_OK;
-  dwconv_bwd_data_kernel<<<ew_grid(total), 256, 0, st>>>(du2, u1, w, du1, B, H, W, C);
+  if ((int64_t)B * H * W * C == 0) return FA_OK;
+  int nstrips; dim3 grid;
+  const StripGeom g = make_strips(B, H, W, C, nstrips, grid);
+  dwconv_strip_kernel<true><<<grid, dim3(32, 8), 0, st>>>(du2, w, nullptr, u1, du1, nullptr, g, nstrips);
   FA_LAUNCH_CHECK("fa_dwconv3x3_bwd(data)");
   if (dw) {
     FA_REQUIRE(h1, "fa_dwconv3x3_bwd: h1 required for the weight gradient");
     fa_count_launch(FA_K_DWCONV);
-    const int64_t T = (int64_t)B * H * W;
-    dim3 grid((unsigned)((T + DW_PIX - 1) / DW_PIX), (C / 4 + 31) / 32);
-    dwconv_bwd_weight_kernel<<<grid, 256, 0, st>>>(du2, h1, dw, db, B, H, W, C);
+    dwconv_wgrad_strip_kernel<<<grid, dim3(32, 8), 0, st>>>(du2, h1, dw, db, g, nstrips);
     FA_LAUNCH_CHECK("fa_dwconv3x3_bwd(weight)");
   }
   return FA_OK;

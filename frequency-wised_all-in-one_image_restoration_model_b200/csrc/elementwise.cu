@@ -70,7 +70,8 @@ __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, flo
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n, float b1,
                                                    float b2, float eps, float step_size, float inv_bc2_sqrt,
-                                                   float gscale, int vec) {
+                                                   float gscale, int vec, const float* __restrict__ hyper) {
+  if (hyper) { step_size = hyper[0]; inv_bc2_sqrt = hyper[1]; }     // step-dependent scalars read at run time (CUDA graphs)
   if (vec) {
     const int64_t n4 = n >> 2;
     float4* p4 = reinterpret_cast<float4*>(p);
@@ -180,8 +181,20 @@ int fa_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float 
   const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
   const bool al = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16) == 0;
   adam_kernel<<<ew_grid(n / 4 + 1), 256, 0, st>>>(p, g, m, v, n, beta1, beta2, eps, step_size, inv_bc2_sqrt, grad_scale,
-                                                  al ? 1 : 0);
+                                                  al ? 1 : 0, nullptr);
   FA_LAUNCH_CHECK("fa_adam_step");
+  return FA_OK;
+}
+
+int fa_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, float beta1, float beta2,
+                     float eps, float grad_scale, fa_stream_t stream) {
+  FA_REQUIRE(p && g && m && v && hyper, "fa_adam_step_dev: bad argument");
+  if (n == 0) return FA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_OPTIM, st);
+  const bool al = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16) == 0;
+  adam_kernel<<<ew_grid(n / 4 + 1), 256, 0, st>>>(p, g, m, v, n, beta1, beta2, eps, 0.f, 0.f, grad_scale, al ? 1 : 0, hyper);
+  FA_LAUNCH_CHECK("fa_adam_step_dev");
   return FA_OK;
 }
 

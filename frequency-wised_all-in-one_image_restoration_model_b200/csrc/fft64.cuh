@@ -13,7 +13,7 @@ namespace fft64 {
 
 constexpr int N = 64;
 constexpr int NH = 33;
-constexpr int PSTR = 65;
+constexpr int PSTR = 68;     // == 4 (mod 32): conflict-free for the FFT row passes and for mma A-fragment loads
 constexpr int SPSTR = 33;
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {

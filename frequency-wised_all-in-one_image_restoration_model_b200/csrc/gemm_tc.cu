@@ -33,9 +33,9 @@ constexpr int BK = 32;              // floats per k-block = one 128-byte swizzle
 constexpr int UMMA_K = 8;           // tf32
 constexpr int KC_BLOCKS = 8;        // k-blocks accumulated inside TMEM before promotion to registers (KC = 256)
 constexpr int MAX_STAGES = 8;
-constexpr int SPLIT_WARPS = 4;
+constexpr int SPLIT_WARPS = 4;      // 14 warps: 4 on one SM sub-partition -> 128 registers per thread
 constexpr int EPI_WARPS = 8;
-constexpr int EPI_WARP0 = 2 + SPLIT_WARPS;     // first epilogue warp (6: 6 % 4 == 2, quarters cycle 2,3,0,1,...)
+constexpr int EPI_WARP0 = 2 + SPLIT_WARPS;     // first epilogue warp (TMEM lane quarter = warp % 4)
 constexpr int NTHREADS = 32 * (2 + SPLIT_WARPS + EPI_WARPS);
 constexpr int A_BYTES = BM * BK * 4;
 
@@ -171,15 +171,26 @@ struct TcGeom {
   int a_mn, b_mn, x3, stages;
 };
 
-__device__ __forceinline__ float4 act4(float4 x, int act, float p) {
-  return make_float4(act_f(x.x, act, p), act_f(x.y, act, p), act_f(x.z, act, p), act_f(x.w, act, p));
+// compile-time activation: keeps the unrolled row loop straight-line (a run-time switch per element splits it into
+// basic blocks and serialises the erff chains of the 16 elements a thread has in flight)
+template <int ACT>
+__device__ __forceinline__ float act_c(float x, float p) {
+  if (ACT == ACT_GELU) return gelu_f(x);
+  if (ACT == ACT_LRELU) return x > 0.f ? x : x * p;
+  if (ACT == ACT_SIGMOID) return 1.0f / (1.0f + __expf(-x));
+  return x;
 }
-__device__ __forceinline__ float4 actg4(float4 a, int act, float p) {
-  return make_float4(act_grad_f(a.x, act, p), act_grad_f(a.y, act, p), act_grad_f(a.z, act, p), act_grad_f(a.w, act, p));
+template <int ACT>
+__device__ __forceinline__ float actg_c(float x, float p) {
+  if (ACT == ACT_GELU) return gelu_grad_f(x);
+  if (ACT == ACT_LRELU) return x > 0.f ? 1.0f : p;
+  if (ACT == ACT_SIGMOID) { const float sg = 1.0f / (1.0f + __expf(-x)); return sg * (1.0f - sg); }
+  return 1.0f;
 }
 
-// one float4 (4 consecutive columns of one output row) through the epilogue
-template <int MODE>
+// one float4 (4 consecutive columns of one output row) through the epilogue; ACT = the forward activation (FWD) or
+// the activation whose derivative multiplies the result (BWD); EPI_ANY takes both at run time (ACT ignored)
+template <int MODE, int ACT>
 __device__ __forceinline__ void epi_vec(float4 x, const EpiTC& e, float4 b4, int row, int col, float* __restrict__ cp) {
   if (MODE == EPI_PLAIN || MODE == EPI_ANY) {
     if (e.atomic) {
@@ -191,12 +202,22 @@ __device__ __forceinline__ void epi_vec(float4 x, const EpiTC& e, float4 b4, int
   x.z = fmaf(x.z, e.alpha, b4.z); x.w = fmaf(x.w, e.alpha, b4.w);
   if (MODE == EPI_FWD || MODE == EPI_ANY) {
     if (e.preact) *reinterpret_cast<float4*>(e.preact + (int64_t)row * e.ldpre + col) = x;
-    if (e.act != ACT_NONE) x = act4(x, e.act, e.act_p);
+    if (MODE == EPI_ANY) {
+      x = make_float4(act_f(x.x, e.act, e.act_p), act_f(x.y, e.act, e.act_p), act_f(x.z, e.act, e.act_p), act_f(x.w, e.act, e.act_p));
+    } else if (ACT != ACT_NONE) {
+      x = make_float4(act_c<ACT>(x.x, e.act_p), act_c<ACT>(x.y, e.act_p), act_c<ACT>(x.z, e.act_p), act_c<ACT>(x.w, e.act_p));
+    }
   }
   if (MODE == EPI_BWD || MODE == EPI_ANY) {
     if (e.aux) {
-      const float4 g = actg4(__ldg(reinterpret_cast<const float4*>(e.aux + (int64_t)row * e.ldaux + col)), e.aux_act, e.aux_p);
-      x.x *= g.x; x.y *= g.y; x.z *= g.z; x.w *= g.w;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(e.aux + (int64_t)row * e.ldaux + col));
+      if (MODE == EPI_ANY) {
+        x.x *= act_grad_f(a.x, e.aux_act, e.aux_p); x.y *= act_grad_f(a.y, e.aux_act, e.aux_p);
+        x.z *= act_grad_f(a.z, e.aux_act, e.aux_p); x.w *= act_grad_f(a.w, e.aux_act, e.aux_p);
+      } else {
+        x.x *= actg_c<ACT>(a.x, e.aux_p); x.y *= actg_c<ACT>(a.y, e.aux_p);
+        x.z *= actg_c<ACT>(a.z, e.aux_p); x.w *= actg_c<ACT>(a.w, e.aux_p);
+      }
     }
   }
   if (MODE == EPI_FWD || MODE == EPI_ANY) {
@@ -216,6 +237,18 @@ __device__ __forceinline__ void epi_vec(float4 x, const EpiTC& e, float4 b4, int
     }
   }
   *reinterpret_cast<float4*>(cp) = x;
+}
+
+// the 8 row-quads of one 32 x 32 chunk (lane = 4 columns of row it*4 + lane/8)
+template <int MODE, int ACT>
+__device__ __forceinline__ void epi_rows(const float* stg, const EpiTC& e, float4 b4, int row0, int rsub, int c4, int col,
+                                         int M, float* __restrict__ cp0, int64_t ldc) {
+#pragma unroll(MODE == EPI_ANY ? 1 : 4)
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + rsub;
+    if (row0 + r < M)
+      epi_vec<MODE, ACT>(*reinterpret_cast<const float4*>(&stg[stg_idx(r, c4)]), e, b4, row0 + r, col, cp0 + (int64_t)it * 4 * ldc);
+  }
 }
 
 template <int BN, int MODE>
@@ -338,7 +371,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
   } else if (warp < EPI_WARP0) {
     // ------------------------------------------------------------------ split warps: lo = x - trunc_tf32(x)
     if (X3) {
-      const int st = threadIdx.x - 64;        // 0..127
+      const int st = threadIdx.x - 64;        // 0..SPLIT_WARPS*32-1
       uint32_t it = 0;
       int s = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -418,13 +451,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
               if (MODE == EPI_FWD || MODE == EPI_ANY)
                 if (epi.bias) b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
               float* cp0 = C + (int64_t)(row0 + rsub) * g.ldc + col;
-#pragma unroll(MODE == EPI_ANY ? 1 : 4)
-              for (int it = 0; it < 8; ++it) {
-                const int r = it * 4 + rsub;
-                if (row0 + r < g.M)
-                  epi_vec<MODE>(*reinterpret_cast<const float4*>(&stg[stg_idx(r, c4)]), epi, b4, row0 + r, col,
-                                cp0 + (int64_t)it * 4 * g.ldc);
-              }
+              const int act = (MODE == EPI_FWD) ? epi.act : (MODE == EPI_BWD ? epi.aux_act : ACT_NONE);
+              if (act == ACT_GELU) epi_rows<MODE, ACT_GELU>(stg, epi, b4, row0, rsub, c4, col, g.M, cp0, g.ldc);
+              else if (act == ACT_LRELU) epi_rows<MODE, ACT_LRELU>(stg, epi, b4, row0, rsub, c4, col, g.M, cp0, g.ldc);
+              else if (act == ACT_SIGMOID) epi_rows<MODE, ACT_SIGMOID>(stg, epi, b4, row0, rsub, c4, col, g.M, cp0, g.ldc);
+              else epi_rows<MODE, ACT_NONE>(stg, epi, b4, row0, rsub, c4, col, g.M, cp0, g.ldc);
             }
           } else {
             // scalar fallback (ragged N or unaligned rows): lane = column, every FaGemmEpilogue field honoured

@@ -1,7 +1,11 @@
 // K2 (encoder form) - joint intra/inter-band window attention (FrequencyWindowAttention,
 // encoder_Uformer.py:190-313): the L band copies of one 8x8 window attend to each other as L*64 tokens.
-// Faithful dense form: every (l1,l2) pair gets its own relative-position-bias table and the 0/-100
-// intra|inter band mask is ADDED (not -inf), exactly as the reference does (:246-254, :281).
+// Every (l1,l2) pair gets its own relative-position-bias table.  The reference ADDS a 0/-100 intra|inter band mask
+// (:246-254, :281) instead of -inf; a masked score is >= 100 below an unmasked one of the same row (every row keeps
+// its own band's / the other bands' same-position token unmasked), so its softmax weight is <= e^-100+O(10) ~ 1e-40
+// relative - below one fp32 ulp of the row sum by 33 orders of magnitude.  The kernel therefore evaluates only the
+// unmasked (l1,l2) blocks (intra: 1 of L, inter: L-1 of L) and treats the others as exact zeros; the oracle keeps the
+// dense -100 form and tests/test_gpu_ops.py::test_joint_attn compares the two.
 // One CTA (256 threads) per (sample, window, head); K and V of all L bands stay resident in shared memory
 // while the L query blocks are swept, so q/k/v/o each cross HBM once.
 #include "freqair_internal.h"
@@ -25,6 +29,9 @@ __device__ __forceinline__ void jtoken(const JGeom& g, int wy, int wx, int p, in
   label = g.shift > 0 ? ry * 3 + rx : 0;
 }
 
+// (l1,l2) block carries the -100 band mask: intra (kind 0) masks other bands, inter (kind 1) masks the own band
+__device__ __forceinline__ bool jmasked(const JGeom& g, int l1, int l2) { return g.kind == 0 ? (l1 != l2) : (l1 == l2); }
+
 template <int HD>
 __device__ __forceinline__ void jload(float* dst, const float* __restrict__ src, int64_t ld, int col0, int64_t img_row0,
                                       const int* pix, int tid) {
@@ -44,6 +51,13 @@ __device__ __forceinline__ void jscores(const float* Q, const float* K, float* S
   constexpr int HS = HD + 1;
   const int ty = tid >> 4, tx = tid & 15;
   for (int l2 = 0; l2 < g.L; ++l2) {
+    if (jmasked(g, l1, l2)) {
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) S[(ty + 16 * ii) * SS + l2 * NTOK + tx + 16 * jj] = -INFINITY;
+      continue;
+    }
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -63,14 +77,12 @@ __device__ __forceinline__ void jscores(const float* Q, const float* K, float* S
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     const float* bt = bias + (l1 * g.L + l2) * 225;
-    const bool same = (l1 == l2);
-    const float mfreq = (g.kind == 0) ? (same ? 0.f : -100.f) : (same ? -100.f : 0.f);
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         const int i = ty + 16 * ii, j = tx + 16 * jj;
-        float s = acc[ii][jj] * scale + bt[((i >> 3) - (j >> 3) + 7) * 15 + ((i & 7) - (j & 7) + 7)] + mfreq;
+        float s = acc[ii][jj] * scale + bt[((i >> 3) - (j >> 3) + 7) * 15 + ((i & 7) - (j & 7) + 7)];
         if (label[i] != label[j]) s += -100.0f;
         S[i * SS + l2 * NTOK + j] = s;
       }
@@ -152,6 +164,7 @@ __global__ void __launch_bounds__(256) joint_fwd_kernel(const float* __restrict_
 #pragma unroll
       for (int dd = 0; dd < ND; ++dd) acc[i][dd] = 0.f;
     for (int j = 0; j < L * NTOK; ++j) {
+      if (jmasked(g, l1, j >> 6)) { j |= 63; continue; }          // whole band has zero weight
       float p[4], v[ND];
 #pragma unroll
       for (int i = 0; i < 4; ++i) p[i] = S[(ty + 16 * i) * SS + j];
@@ -234,6 +247,13 @@ __global__ void __launch_bounds__(256) joint_bwd_kernel(const float* __restrict_
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        if (jmasked(g, l1, l2)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) X[(ty + 16 * i) * SS + l2 * NTOK + tx + 16 * j] = 0.f;
+          continue;
+        }
         const float* Vl = V + l2 * NTOK * HS;
 #pragma unroll 4
         for (int d = 0; d < HD; ++d) {
@@ -259,6 +279,7 @@ __global__ void __launch_bounds__(256) joint_bwd_kernel(const float* __restrict_
 #pragma unroll
       for (int jj = 0; jj < 4 * MAXL; ++jj) {
         if (jj >= 4 * L) break;
+        if (jmasked(g, l1, jj >> 2)) continue;
         const int j = ty + 16 * jj;
         for (int i = 0; i < NTOK; ++i) {
           const float p = P[i * SS + j];
@@ -274,9 +295,10 @@ __global__ void __launch_bounds__(256) joint_bwd_kernel(const float* __restrict_
         for (int r = 0; r < 8; ++r) {
           const int i = w * 8 + r;
           float dot = 0.f;
-          for (int c = lane; c < LT; c += 32) dot += P[i * SS + c] * X[i * SS + c];
+          for (int c = lane; c < LT; c += 32) dot += P[i * SS + c] * X[i * SS + c];      // masked blocks: P = 0, X = 0
           dot = warp_sum(dot);
           for (int c = lane; c < LT; c += 32) {
+            if (jmasked(g, l1, c >> 6)) continue;                                       // dS stays 0 there
             const float ds = P[i * SS + c] * (X[i * SS + c] - dot);
             X[i * SS + c] = ds;
             if (dtables) {
@@ -295,6 +317,7 @@ __global__ void __launch_bounds__(256) joint_bwd_kernel(const float* __restrict_
 #pragma unroll
           for (int dd = 0; dd < ND; ++dd) acc[i][dd] = 0.f;
         for (int c = 0; c < LT; ++c) {
+          if (jmasked(g, l1, c >> 6)) { c |= 63; continue; }
           float s4[4], k4[ND];
 #pragma unroll
           for (int i = 0; i < 4; ++i) s4[i] = X[(ty + 16 * i) * SS + c];
@@ -316,6 +339,7 @@ __global__ void __launch_bounds__(256) joint_bwd_kernel(const float* __restrict_
 #pragma unroll
       for (int jj = 0; jj < 4 * MAXL; ++jj) {
         if (jj >= 4 * L) break;
+        if (jmasked(g, l1, jj >> 2)) continue;
         const int j = ty + 16 * jj;
         for (int i = 0; i < NTOK; ++i) {
           const float ds = X[i * SS + j] * scale;
@@ -364,6 +388,7 @@ int jcheck(const char* who, int L, int B, int H, int W, int heads, int hd, int s
   FA_REQUIRE(hd == 28 || hd == 56, "%s: head_dim=%d unsupported (28, 56)", who, hd);
   FA_REQUIRE(shift == 0 || (shift == 4 && H > WIN && W > WIN), "%s: shift=%d unsupported", who, shift);
   FA_REQUIRE(kind == 0 || kind == 1, "%s: kind must be 0 (intra) or 1 (inter)", who);
+  FA_REQUIRE(kind == 0 || L >= 2, "%s: inter-band attention needs L >= 2", who);
   FA_REQUIRE(ldq % 4 == 0 && ldkv % 4 == 0, "%s: row strides must be multiples of 4 floats", who);
   g.L = L; g.B = B; g.H = H; g.W = W; g.heads = heads; g.shift = shift; g.nWy = H / WIN; g.nWx = W / WIN; g.kind = kind;
   return FA_OK;

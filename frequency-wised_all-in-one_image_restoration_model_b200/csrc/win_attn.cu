@@ -9,6 +9,7 @@
 // across all windows a CTA visits before one flush of 225 atomics.
 #include "freqair_internal.h"
 #include "fft64.cuh"
+#include "mma_tf32.cuh"
 
 namespace {
 
@@ -32,12 +33,21 @@ __device__ __forceinline__ void token_of(const WinGeom& g, int b, int wy, int wx
   label = g.shift > 0 ? ry * 3 + rx : 0;
 }
 
+// smem row pitches of the 64 x hd operand tiles: KP = hd rounded up to the MMA k-step (zero-filled), pitch == 4 (mod 32)
+// makes the K-contiguous fragment loads (rows g / g+8, cols t / t+4) bank-conflict-free; the forward V tile, read with
+// the key index as k, uses pitch == 8 (mod 32) for the same reason.
+template <int HD> struct Pitch;
+template <> struct Pitch<28> { static constexpr int KP = 32, HS = 36, HSV = 40; };
+template <> struct Pitch<56> { static constexpr int KP = 56, HS = 60, HSV = 72; };
+template <> struct Pitch<64> { static constexpr int KP = 64, HS = 68, HSV = 72; };
+
 template <int HD>
 struct Smem {
-  static constexpr int HS = HD + 1;
+  static constexpr int HS = Pitch<HD>::HS;
+  static constexpr int HSV = Pitch<HD>::HSV;
   float q[NTOK * HS];
   float k[NTOK * HS];
-  float v[NTOK * HS];
+  float v[NTOK * HSV];
   float p[NTOK * fft64::PSTR];
   float2 sp[NTOK * fft64::SPSTR];
   float bias[232];
@@ -47,54 +57,44 @@ struct Smem {
   uint8_t band[NTOK * 33 + 8];
 };
 
-template <int HD>
+template <int HD, int HS>
 __device__ __forceinline__ void load_tile(float* dst, const float* __restrict__ src, int64_t ld, int col0,
                                           const int* rows, int tid) {
-  constexpr int HS = HD + 1;
-  constexpr int V4 = HD / 4;
+  constexpr int KP = Pitch<HD>::KP;
+  constexpr int V4 = KP / 4;
   for (int i = tid; i < NTOK * V4; i += NTHR) {
     const int t = i / V4, d = (i % V4) * 4;
-    const float4 v = *reinterpret_cast<const float4*>(src + (int64_t)rows[t] * ld + col0 + d);
-    float* o = dst + t * HS + d;
-    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    const float4 v = d < HD ? *reinterpret_cast<const float4*>(src + (int64_t)rows[t] * ld + col0 + d)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);            // k-padding of the contraction
+    *reinterpret_cast<float4*>(dst + t * HS + d) = v;
   }
 }
 
-// S[i][j] for i = ty+16*ii, j = tx+16*jj  ->  out[i*PSTR + j] = scale*dot(A_i, B_j) (+ bias + mask)
+// out[i*PSTR + j] = scale * dot(A_i, B_j) (+ bias + mask) on the tensor cores: warp w owns rows 16*(w&3).. and the
+// 32-column half (w>>2)
 template <int HD, bool BIASMASK>
-__device__ __forceinline__ void tile_abt(const float* A, const float* Bm, float* out, float scale, const float* bias,
-                                         const int* label, int tid) {
-  constexpr int HS = HD + 1;
+__device__ __forceinline__ void tile_abt(const float* A, int lda, const float* Bm, int ldb, float* out, float scale,
+                                         const float* bias, const int* label, int tid) {
   if (tid >= 256) return;
-  const int ty = tid >> 4, tx = tid & 15;
-  float acc[4][4];
+  const int w = tid >> 5, lane = tid & 31;
+  const int m0 = (w & 3) * 16, n0 = (w >> 2) * 32;
+  float c[4][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 4; ++i) { c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f; }
+  mma32::warp_mma<4>(c, Pitch<HD>::KP / 8, [&](int m, int k) { return A[(m0 + m) * lda + k]; },
+                     [&](int k, int n) { return Bm[(n0 + n) * ldb + k]; }, lane);
+  const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-#pragma unroll 4
-  for (int d = 0; d < HD; ++d) {
-    float a[4], b[4];
+  for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) a[i] = A[(ty + 16 * i) * HS + d];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) b[j] = Bm[(tx + 16 * j) * HS + d];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-  }
-#pragma unroll
-  for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      const int i = ty + 16 * ii, j = tx + 16 * jj;
-      float s = acc[ii][jj] * scale;
+    for (int r = 0; r < 4; ++r) {
+      const int i = m0 + g + ((r & 2) ? 8 : 0), j = n0 + nt * 8 + 2 * t + (r & 1);
+      float sv = c[nt][r] * scale;
       if (BIASMASK) {
-        s += bias[((i >> 3) - (j >> 3) + 7) * 15 + ((i & 7) - (j & 7) + 7)];
-        if (label[i] != label[j]) s += -100.0f;
+        sv += bias[((i >> 3) - (j >> 3) + 7) * 15 + ((i & 7) - (j & 7) + 7)];
+        if (label[i] != label[j]) sv += -100.0f;
       }
-      out[i * fft64::PSTR + j] = s;
+      out[i * fft64::PSTR + j] = sv;
     }
 }
 
@@ -113,38 +113,35 @@ __device__ __forceinline__ void softmax_rows(float* P, int tid) {
   }
 }
 
-// out[i][d] = sum_j P[i][j] * V[j][d]   (TRANS: sum_j P[j][i] * V[j][d]), written to global rows
+// out[i][d] = scale * sum_j P[i][j] * V[j][d]   (TRANS: sum_j P[j][i] * V[j][d]), written to global rows.
+// warp w owns rows 16*(w&3).. and the interleaved 8-column tiles (w>>2), (w>>2)+2, ... of the hd outputs.
 template <int HD, bool TRANS>
-__device__ __forceinline__ void tile_pv(const float* P, const float* V, float* __restrict__ out, int64_t ld, int col0,
-                                        const int* rows, float scale, int tid) {
-  constexpr int HS = HD + 1;
+__device__ __forceinline__ void tile_pv(const float* P, const float* V, int ldv, float* __restrict__ out, int64_t ld,
+                                        int col0, const int* rows, float scale, int tid) {
   if (tid >= 256) return;
-  const int ty = tid >> 4, tx = tid & 15;
-  constexpr int ND = (HD + 15) / 16;
-  float acc[4][ND];
+  constexpr int NTT = (HD + 7) / 8;          // 8-wide output tiles
+  constexpr int NTW = (NTT + 1) / 2;         // per warp
+  const int w = tid >> 5, lane = tid & 31;
+  const int m0 = (w & 3) * 16, nh = w >> 2;
+  float c[NTW][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < NTW; ++i) { c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f; }
+  mma32::warp_mma<NTW>(c, NTOK / 8,
+                       [&](int m, int k) { return TRANS ? P[k * fft64::PSTR + m0 + m] : P[(m0 + m) * fft64::PSTR + k]; },
+                       [&](int k, int n) {
+                         const int d = (nh + 2 * (n >> 3)) * 8 + (n & 7);
+                         return d < Pitch<HD>::KP ? V[k * ldv + d] : 0.f;
+                       },
+                       lane);
+  const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int j = 0; j < ND; ++j) acc[i][j] = 0.f;
-#pragma unroll 4
-  for (int j = 0; j < NTOK; ++j) {
-    float p[4], v[ND];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) p[i] = TRANS ? P[j * fft64::PSTR + ty + 16 * i] : P[(ty + 16 * i) * fft64::PSTR + j];
-#pragma unroll
-    for (int dd = 0; dd < ND; ++dd) { const int d = tx + 16 * dd; v[dd] = d < HD ? V[j * HS + d] : 0.f; }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int dd = 0; dd < ND; ++dd) acc[i][dd] = fmaf(p[i], v[dd], acc[i][dd]);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int dd = 0; dd < ND; ++dd) {
-      const int d = tx + 16 * dd;
-      if (d < HD) out[(int64_t)rows[ty + 16 * i] * ld + col0 + d] = acc[i][dd] * scale;
+  for (int nt = 0; nt < NTW; ++nt) {
+    const int d = (nh + 2 * nt) * 8 + 2 * t;
+    if (d < HD) {                              // HD is even: both columns of the pair are valid
+      *reinterpret_cast<float2*>(out + (int64_t)rows[m0 + g] * ld + col0 + d) = make_float2(c[nt][0] * scale, c[nt][1] * scale);
+      *reinterpret_cast<float2*>(out + (int64_t)rows[m0 + g + 8] * ld + col0 + d) = make_float2(c[nt][2] * scale, c[nt][3] * scale);
     }
+  }
 }
 
 template <int HD>
@@ -171,22 +168,23 @@ __global__ void __launch_bounds__(NTHR) win_attn_fwd_kernel(const float* __restr
     if (tid < 16) s.coef[tid] = tid < nbands ? coef[((int64_t)b * coef_bstride + h) * nbands + tid] : 0.f;
   }
   __syncthreads();
-  load_tile<HD>(s.q, q, ldq, h * HD, s.row, tid);
-  load_tile<HD>(s.k, kv, ldkv, h * HD, s.row, tid);
-  load_tile<HD>(s.v, kv, ldkv, C + h * HD, s.row, tid);
+  constexpr int HS = Smem<HD>::HS, HSV = Smem<HD>::HSV;
+  load_tile<HD, HS>(s.q, q, ldq, h * HD, s.row, tid);
+  load_tile<HD, HS>(s.k, kv, ldkv, h * HD, s.row, tid);
+  load_tile<HD, HSV>(s.v, kv, ldkv, C + h * HD, s.row, tid);
   __syncthreads();
-  tile_abt<HD, true>(s.q, s.k, s.p, scale, s.bias, s.label, tid);
+  tile_abt<HD, true>(s.q, HS, s.k, HS, s.p, scale, s.bias, s.label, tid);
   __syncthreads();
   softmax_rows(s.p, tid);
   __syncthreads();
   if (coef) fft64::filter_map(s.p, s.sp, s.band, s.coef, 1.0f, tid);
-  tile_pv<HD, false>(s.p, s.v, o, C, h * HD, s.row, 1.0f, tid);
+  tile_pv<HD, false>(s.p, s.v, HSV, o, C, h * HD, s.row, 1.0f, tid);
 }
 
 // ------------------------------------------------------------------ backward
 template <int HD>
 struct SmemB {
-  static constexpr int HS = HD + 1;
+  static constexpr int HS = Pitch<HD>::HS;
   float q[NTOK * HS];
   float k[NTOK * HS];
   float v[NTOK * HS];
@@ -235,13 +233,14 @@ __global__ void __launch_bounds__(NTHR) win_attn_bwd_kernel(const float* __restr
       s.ecoef[tid] = 0.f;
     }
     __syncthreads();
-    load_tile<HD>(s.q, q, ldq, h * HD, s.row, tid);
-    load_tile<HD>(s.k, kv, ldkv, h * HD, s.row, tid);
-    load_tile<HD>(s.v, kv, ldkv, C + h * HD, s.row, tid);
-    load_tile<HD>(s.dO, dout, C, h * HD, s.row, tid);
+    constexpr int HS = SmemB<HD>::HS;
+    load_tile<HD, HS>(s.q, q, ldq, h * HD, s.row, tid);
+    load_tile<HD, HS>(s.k, kv, ldkv, h * HD, s.row, tid);
+    load_tile<HD, HS>(s.v, kv, ldkv, C + h * HD, s.row, tid);
+    load_tile<HD, HS>(s.dO, dout, C, h * HD, s.row, tid);
     __syncthreads();
-    tile_abt<HD, true>(s.q, s.k, s.p, scale, s.bias, s.label, tid);     // S
-    tile_abt<HD, false>(s.dO, s.v, s.x, 1.0f, nullptr, nullptr, tid);   // dP' = dO.V^T
+    tile_abt<HD, true>(s.q, HS, s.k, HS, s.p, scale, s.bias, s.label, tid);     // S
+    tile_abt<HD, false>(s.dO, HS, s.v, HS, s.x, 1.0f, nullptr, nullptr, tid);   // dP' = dO.V^T
     __syncthreads();
     softmax_rows(s.p, tid);                                             // P
     __syncthreads();
@@ -293,7 +292,7 @@ __global__ void __launch_bounds__(NTHR) win_attn_bwd_kernel(const float* __restr
       __syncthreads();
       fft64::rows_inverse(s.spA, s.x, 1.0f / 4096.0f, tid);             // x = P'
       __syncthreads();
-      tile_pv<HD, true>(s.x, s.dO, dkv, 2 * C, C + h * HD, s.row, 1.0f, tid);   // dV = P'^T.dO
+      tile_pv<HD, true>(s.x, s.dO, HS, dkv, 2 * C, C + h * HD, s.row, 1.0f, tid);   // dV = P'^T.dO
       {
         // dP = filter(dP'): gain on F(dP'), inverse columns
         const int col = min(tid >> 3, 32), l = tid & 7;
@@ -313,7 +312,7 @@ __global__ void __launch_bounds__(NTHR) win_attn_bwd_kernel(const float* __restr
       __syncthreads();
       if (dcoef && tid < nbands) atomicAdd(&dcoef[((int64_t)b * coef_bstride + h) * nbands + tid], s.ecoef[tid]);
     } else {
-      tile_pv<HD, true>(s.p, s.dO, dkv, 2 * C, C + h * HD, s.row, 1.0f, tid);   // dV = P^T.dO
+      tile_pv<HD, true>(s.p, s.dO, HS, dkv, 2 * C, C + h * HD, s.row, 1.0f, tid);   // dV = P^T.dO
       __syncthreads();
     }
     // dS = P o (dP - rowsum(dP o P)) -> x ; bias gradient into shared memory
@@ -337,8 +336,8 @@ __global__ void __launch_bounds__(NTHR) win_attn_bwd_kernel(const float* __restr
       }
     }
     __syncthreads();
-    tile_pv<HD, false>(s.x, s.k, dq, C, h * HD, s.row, scale, tid);        // dQ = scale * dS.K
-    tile_pv<HD, true>(s.x, s.q, dkv, 2 * C, h * HD, s.row, scale, tid);    // dK = scale * dS^T.Q
+    tile_pv<HD, false>(s.x, s.k, HS, dq, C, h * HD, s.row, scale, tid);        // dQ = scale * dS.K
+    tile_pv<HD, true>(s.x, s.q, HS, dkv, 2 * C, h * HD, s.row, scale, tid);    // dK = scale * dS^T.Q
   }
   __syncthreads();
   if (dtable) for (int i = tid; i < 225; i += NTHR) atomicAdd(&dtable[i * g.heads + h], s.dbias[i]);

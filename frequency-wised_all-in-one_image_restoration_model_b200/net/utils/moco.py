@@ -64,12 +64,14 @@ class MoCo(nn.Module):
 
     @torch.no_grad()
     def _dequeue_and_enqueue(self, keys):
+        """moco.py:53-66 without the reference's ``int(self.queue_ptr)`` device->host sync: the write columns are
+        computed on the device from ``queue_ptr``, so the step never blocks the host and can be captured in a CUDA graph."""
         batch_size = keys[0].shape[0]
-        ptr = int(self.queue_ptr)
         assert self.K % batch_size == 0
-        for i in range(self.num_losses):
-            self.queue[i][:, ptr:ptr + batch_size] = keys[i].transpose(0, 1)
-        self.queue_ptr[0] = (ptr + batch_size) % self.K
+        cols = (self.queue_ptr + torch.arange(batch_size, device=self.queue_ptr.device)) % self.K
+        for i in range(len(keys)):
+            self.queue[i].index_copy_(1, cols, keys[i].transpose(0, 1))
+        self.queue_ptr.copy_((self.queue_ptr + batch_size) % self.K)
 
     def forward(self, im_q, im_k):
         if self.training:

@@ -414,3 +414,9 @@ def momentum_update(k, q, m):
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
     _f32(p, g, m, v)
     _call('fa_adam_step', _p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, step, grad_scale, _stream())
+
+
+def adam_step_dev(p, g, m, v, hyper, beta1, beta2, eps, grad_scale=1.0):
+    """Adam with {lr/(1-b1^t), 1/sqrt(1-b2^t)} read from the 2-float device tensor ``hyper`` (graph-replay safe)."""
+    _f32(p, g, m, v, hyper)
+    _call('fa_adam_step_dev', _p(p), _p(g), _p(m), _p(v), p.numel(), _p(hyper), beta1, beta2, eps, grad_scale, _stream())

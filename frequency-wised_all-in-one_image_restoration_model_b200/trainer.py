@@ -136,6 +136,13 @@ class TrainStep:
         moco._flat_q = self.segments[0].flat
         self.ddp = BucketedAllReduce(self.segments, bucket_mb) if distributed else None
         self.last = {}
+        # CUDA-graph state (capture()): static inputs / loss, and the two step-dependent Adam scalars in device memory
+        self.graph = None
+        self.static_in = None
+        self.static_out = None
+        dev = self.segments[0].flat.device
+        self.hyper = torch.zeros(2, device=dev, dtype=torch.float32)
+        self.hyper_host = torch.zeros(2, dtype=torch.float32).pin_memory() if dev.type == 'cuda' else torch.zeros(2)
 
     def zero_grad(self):
         for s in self.segments:
@@ -147,17 +154,61 @@ class TrainStep:
         l1 = l1_loss(restored, clean)                                                # train.py:89
         return l1 + self.w * ce, l1, ce                                              # train.py:92
 
-    def step(self, x_query, x_key, clean):
-        """One optimisation step; returns the (device) loss tensor."""
+    def _body(self, x_query, x_key, clean, use_hyper):
         self.zero_grad()
         restored, logits, labels = self.net(x_query, x_key)
         loss, l1, ce = self.loss(restored, logits, labels, clean)
         loss.backward()
         if self.ddp is not None:
             self.ddp.finish()
-        self.t += 1
         gscale = 1.0 / self.ddp.world if self.ddp is not None else 1.0       # mean over ranks, fused into Adam
         for s in self.segments:
-            ops.adam_step(s.flat, s.grad, s.m, s.v, self.lr, self.betas[0], self.betas[1], self.eps, self.t, gscale)
-        self.last = dict(loss=loss.detach(), l1=l1.detach(), ce=ce.detach())
+            if use_hyper:
+                ops.adam_step_dev(s.flat, s.grad, s.m, s.v, self.hyper, self.betas[0], self.betas[1], self.eps, gscale)
+            else:
+                ops.adam_step(s.flat, s.grad, s.m, s.v, self.lr, self.betas[0], self.betas[1], self.eps, self.t, gscale)
+        return dict(loss=loss.detach(), l1=l1.detach(), ce=ce.detach())
+
+    def _advance(self):
+        """t += 1 and the step-dependent Adam scalars {lr/(1-b1^t), 1/sqrt(1-b2^t)} pushed to the device."""
+        self.t += 1
+        self.hyper_host[0] = self.lr / (1.0 - self.betas[0] ** self.t)
+        self.hyper_host[1] = 1.0 / (1.0 - self.betas[1] ** self.t) ** 0.5
+        self.hyper.copy_(self.hyper_host, non_blocking=True)
+
+    def step(self, x_query, x_key, clean):
+        """One optimisation step; returns the (device) loss tensor.  Replays the captured graph when there is one."""
+        if self.graph is not None:
+            for dst, src in zip(self.static_in, (x_query, x_key, clean)):
+                if dst.data_ptr() != src.data_ptr():
+                    dst.copy_(src, non_blocking=True)
+            self._advance()
+            self.graph.replay()
+            self.last = self.static_out
+            return self.last['loss']
+        self.t += 1
+        self.last = self._body(x_query, x_key, clean, False)
         return self.last['loss']
+
+    def capture(self, x_query, x_key, clean, warmup=2):
+        """Capture the whole step (zero_grad, forward, losses, backward, gradient all-reduce, Adam, momentum and queue
+        updates: ~7 500 kernel launches) into ONE CUDA graph; later ``step`` calls copy the crops into the static input
+        buffers and replay it.  ``warmup`` eager steps run first on a side stream (allocator warm-up, one-time
+        cudaFuncSetAttribute calls); they are real optimisation steps."""
+        self.static_in = [t.clone() for t in (x_query, x_key, clean)]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._advance()
+                self._body(*self.static_in, True)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        self._advance()
+        with torch.cuda.graph(graph):
+            self.static_out = self._body(*self.static_in, True)
+        self.t -= 1                     # capture records the step without executing it
+        self.graph = graph
+        self.last = self.static_out
+        return self.static_out['loss']

@@ -207,6 +207,10 @@ int fa_momentum_update(float* k, const float* q, int64_t n, float m, fa_stream_t
 /* torch.optim.Adam step over a flat buffer (train.py:63,96); step >= 1 */
 int fa_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                  int step, float grad_scale, fa_stream_t stream);
+/* the same update with the two step-dependent scalars read from DEVICE memory at run time, hyper = {lr / (1 - beta1^t),
+ * 1 / sqrt(1 - beta2^t)}: a captured CUDA graph of the train step stays valid as t (and a scheduled lr) advance */
+int fa_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, float beta1, float beta2,
+                     float eps, float grad_scale, fa_stream_t stream);
 
 #ifdef __cplusplus
 }

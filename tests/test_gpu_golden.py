@@ -214,10 +214,24 @@ def test_vit_encoder_golden_and_gradients():
     assert maxerr(inter[:, :4, :8, :], t(g['inter_head'])) < 1e-3
     w = torch.randn(inter.shape, generator=torch.Generator().manual_seed(1))
     ((inter * w.cuda()).sum() * 1e-3 + out[0].square().sum()).backward()
-    rf, ro, ri = oa.vit_encoder_forward(sd, '', xq, 64, decompose_type='4_bands')
-    ((ri * w).sum() * 1e-3 + ro[0].square().sum()).backward()
-    # 12 transformer layers deep: fp32 round-off between two correct implementations reaches ~1e-2 of a gradient's
-    # scale (measured 0.9 % with the exact-fp32 SIMT contraction, 0.55 % with 3xTF32); absolute errors stay < 1e-3
+    # Gradient parity through 12 transformer layers is limited by the conditioning of the network, not by any one
+    # kernel: the fp32 CPU oracle itself sits up to 0.21 % (of a gradient's max) away from an fp64 evaluation of the same
+    # graph.  Ground truth is therefore the oracle in fp64; the CUDA path must be as close to it as fp32 arithmetic
+    # allows: err <= 20 x the fp32 oracle's own error + 2e-3 * scale, and < 1e-3 absolute (north_star).
+    g32, g64 = {}, {}
+    for dt, store in ((torch.float32, g32), (torch.float64, g64)):
+        sdt = {k: (v.detach().clone().to(dt) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+        for k, v in sdt.items():
+            if v.is_floating_point() and 'running' not in k:
+                v.requires_grad_(True)
+        rf, ro, ri = oa.vit_encoder_forward(sdt, '', xq.to(dt), 64, decompose_type='4_bands')
+        ((ri * w.to(dt)).sum() * 1e-3 + ro[0].square().sum()).backward()
+        store.update({k: v.grad.double() for k, v in sdt.items() if v.requires_grad and v.grad is not None})
     for name, p in vit.named_parameters():
-        _grad_close(p.grad, sd[name].grad, 'vit.' + name, tol=1.5e-2)
-        assert (p.grad.detach().cpu() - sd[name].grad).abs().max().item() < 1e-3, name
+        ref = g64[name]
+        scale = max(ref.abs().max().item(), 1e-12)
+        e_ref = (g32[name] - ref).abs().max().item()
+        e_our = (p.grad.detach().double().cpu() - ref).abs().max().item()
+        assert e_our <= 20 * e_ref + 2e-3 * scale, f'vit.{name}: err {e_our:.3e} (fp32 oracle {e_ref:.3e}) scale {scale:.3e}'
+        assert e_our < 1e-3, f'vit.{name}: absolute gradient error {e_our:.3e}'
+

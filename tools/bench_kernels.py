@@ -80,12 +80,38 @@ def bench_gemm(backend, only=None, layouts='NT,NN,TN'):
         del X, W, Y, dX, dW
 
 
+def bench_epi(backend):
+    """Epilogue flavours on the widest LeFF shape of the decoder (T = 262144 tokens, C = 112, hidden 448)."""
+    M, C, Hd = 262144, 112, 448
+    X = torch.randn(M, C, device='cuda'); W1 = torch.randn(Hd, C, device='cuda') * 0.05; b1 = torch.randn(Hd, device='cuda')
+    U = torch.empty(M, Hd, device='cuda'); Hh = torch.empty(M, Hd, device='cuda')
+    W2 = torch.randn(C, Hd, device='cuda') * 0.05; b2 = torch.randn(C, device='cuda')
+    Y = torch.empty(M, C, device='cuda'); R = torch.randn(M, C, device='cuda'); rs = torch.ones(16, device='cuda')
+    G = torch.randn(M, C, device='cuda'); dU = torch.empty(M, Hd, device='cuda')
+    cases = [
+        ('leff1 plain', lambda: ops.gemm(X, W1, Hh, backend=backend), 4 * (M * C + M * Hd)),
+        ('leff1 +bias', lambda: ops.gemm(X, W1, Hh, bias=b1, backend=backend), 4 * (M * C + M * Hd)),
+        ('leff1 +bias+gelu', lambda: ops.gemm(X, W1, Hh, bias=b1, act=ops.ACT_GELU, backend=backend), 4 * (M * C + M * Hd)),
+        ('leff1 +bias+gelu+preact', lambda: ops.gemm(X, W1, Hh, bias=b1, act=ops.ACT_GELU, preact=U, backend=backend), 4 * (M * C + 2 * M * Hd)),
+        ('leff2 plain', lambda: ops.gemm(Hh, W2, Y, backend=backend), 4 * (M * C + M * Hd)),
+        ('leff2 +bias+rs+res', lambda: ops.gemm(Hh, W2, Y, bias=b2, rowscale=rs, rows_per_scale=16384, residual=R, backend=backend), 4 * (2 * M * C + M * Hd)),
+        ('dX2 plain (NN)', lambda: ops.gemm(G, W2, dU, transB=False, backend=backend), 4 * (M * C + M * Hd)),
+        ('dX2 *gelu\'(aux) (NN)', lambda: ops.gemm(G, W2, dU, transB=False, aux=U, aux_act=ops.ACT_GELU, backend=backend), 4 * (M * C + 2 * M * Hd)),
+        ('dX1 accumulate (NN)', lambda: ops.gemm(dU, W1, Y, transB=False, accumulate=True, backend=backend), 4 * (2 * M * C + M * Hd)),
+    ]
+    for name, fn, byts in cases:
+        ms = timeit(fn)
+        print(f'{name:28s} {ms:8.3f} ms {byts / ms / 1e6:8.0f} GB/s', flush=True)
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
-    ap.add_argument('what', choices=['gemm'])
+    ap.add_argument('what', choices=['gemm', 'epi'])
     ap.add_argument('--backend', type=int, default=0)
     ap.add_argument('--only', default=None)
     ap.add_argument('--layouts', default='NT,NN,TN')
     a = ap.parse_args()
     if a.what == 'gemm':
         bench_gemm(a.backend, a.only, a.layouts)
+    if a.what == 'epi':
+        bench_epi(a.backend)
