@@ -215,6 +215,8 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = ops.launch_count()
+    if ts.graph is not None:                               # a replay re-launches every kernel recorded at capture
+        launches = ts.graph_launches * K
     clocks = sampler.summary()
     # ---------------------------------------------------------------- e2e: pinned host -> device every step, loss read back
     barrier()
@@ -237,9 +239,10 @@ def main():
 
     roofline = None
     cpu_baseline = None
-    if rank == 0 and not args.no_roofline:
+    if not args.no_roofline:
         # dominant kernel class = the dense contractions (fa_gemm): time every launch with in-stream events
-        # (kernel-by-kernel launch of the same step: a graph replay cannot be bracketed per launch)
+        # (kernel-by-kernel launch of the same step: a graph replay cannot be bracketed per launch).
+        # Every rank runs this step (it contains the gradient all-reduce); rank 0 reports.
         ts.graph = None
         ops.FLOP_COUNTER[0] = 0
         ops.prof_begin(ops.K_GEMM)
@@ -248,7 +251,7 @@ def main():
         gemm_ms, gemm_n = ops.prof_end()
         flops = ops.FLOP_COUNTER[0]
         ops.FLOP_COUNTER[0] = None
-        peak = measure_tf32_peak()
+        peak = measure_tf32_peak() if rank == 0 else 1.0
         ach = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
         roofline = {'bound': 'tensor', 'kernel': 'fa_gemm (all dense contractions of the step)', 'achieved': ach,
                     'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak if peak else None, 'traffic': None,

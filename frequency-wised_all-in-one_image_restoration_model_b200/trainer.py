@@ -138,6 +138,7 @@ class TrainStep:
         self.last = {}
         # CUDA-graph state (capture()): static inputs / loss, and the two step-dependent Adam scalars in device memory
         self.graph = None
+        self.graph_launches = 0
         self.static_in = None
         self.static_out = None
         dev = self.segments[0].flat.device
@@ -206,8 +207,10 @@ class TrainStep:
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         self._advance()
+        n0 = ops.launch_count()
         with torch.cuda.graph(graph):
             self.static_out = self._body(*self.static_in, True)
+        self.graph_launches = ops.launch_count() - n0        # libfreqair kernels recorded in the graph (per replay)
         self.t -= 1                     # capture records the step without executing it
         self.graph = graph
         self.last = self.static_out
