@@ -1,23 +1,29 @@
-// K2 (encoder form) - joint intra/inter-band window attention (FrequencyWindowAttention,
+// K2' (encoder form) - joint intra/inter-band window attention (FrequencyWindowAttention,
 // encoder_Uformer.py:190-313): the L band copies of one 8x8 window attend to each other as L*64 tokens.
 // Every (l1,l2) pair gets its own relative-position-bias table.  The reference ADDS a 0/-100 intra|inter band mask
 // (:246-254, :281) instead of -inf; a masked score is >= 100 below an unmasked one of the same row (every row keeps
 // its own band's / the other bands' same-position token unmasked), so its softmax weight is <= e^-100+O(10) ~ 1e-40
-// relative - below one fp32 ulp of the row sum by 33 orders of magnitude.  The kernel therefore evaluates only the
-// unmasked (l1,l2) blocks (intra: 1 of L, inter: L-1 of L) and treats the others as exact zeros; the oracle keeps the
-// dense -100 form and tests/test_gpu_ops.py::test_joint_attn compares the two.
-// One CTA (256 threads) per (sample, window, head); K and V of all L bands stay resident in shared memory
-// while the L query blocks are swept, so q/k/v/o each cross HBM once.
+// relative - below one fp32 ulp of the row sum by 33 orders of magnitude.  The kernels therefore evaluate only the
+// unmasked (l1,l2) blocks - intra: the query band's own 64 keys, inter: the 64*(L-1) keys of the other bands - and treat
+// the rest as exact zeros; the oracle keeps the dense -100 form and tests/test_gpu_ops.py::test_joint_attn compares.
+// One CTA (256 threads) per (query band, sample, window, head): the three contractions run on the tensor cores
+// (attn_tiles.cuh, 3xTF32), q/k/v/o cross HBM once, windows and the cyclic shift are index arithmetic.
+// Backward recomputes P, forms dS = P o (dP - rowsum(P o dP)) from the dP MMA fragments in registers (no second
+// 64 x 128 buffer), reduces the bias-table gradients in shared memory across the windows a CTA visits, and adds the
+// key-side gradients of a band with fp32 atomics only when two query bands contribute (inter, L = 3; two addends
+// commute, so the result stays deterministic).
 #include "freqair_internal.h"
+#include "attn_tiles.cuh"
 
 namespace {
 
-constexpr int WIN = 8;
-constexpr int NTOK = 64;
+using attn::WIN;
+using attn::NTOK;
 constexpr int MAXL = 3;
 
 struct JGeom { int L, B, H, W, heads, shift, nWy, nWx, kind; };
 
+// pixel (y*W + x) of window position p after the cyclic shift, and its SW-MSA region label
 __device__ __forceinline__ void jtoken(const JGeom& g, int wy, int wx, int p, int& pix, int& label) {
   const int sy = wy * WIN + (p >> 3), sx = wx * WIN + (p & 7);
   int y = sy + g.shift, x = sx + g.shift;
@@ -29,189 +35,118 @@ __device__ __forceinline__ void jtoken(const JGeom& g, int wy, int wx, int p, in
   label = g.shift > 0 ? ry * 3 + rx : 0;
 }
 
-// (l1,l2) block carries the -100 band mask: intra (kind 0) masks other bands, inter (kind 1) masks the own band
-__device__ __forceinline__ bool jmasked(const JGeom& g, int l1, int l2) { return g.kind == 0 ? (l1 != l2) : (l1 == l2); }
-
-template <int HD>
-__device__ __forceinline__ void jload(float* dst, const float* __restrict__ src, int64_t ld, int col0, int64_t img_row0,
-                                      const int* pix, int tid) {
-  constexpr int HS = HD + 1, V4 = HD / 4;
-  for (int i = tid; i < NTOK * V4; i += 256) {
-    const int t = i / V4, d = (i % V4) * 4;
-    const float4 v = *reinterpret_cast<const float4*>(src + (img_row0 + pix[t]) * ld + col0 + d);
-    float* o = dst + t * HS + d;
-    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-  }
+// key bands of query band l1: intra -> {l1}; inter -> every other band in increasing order
+template <int NKB>
+__device__ __forceinline__ void key_bands(const JGeom& g, int l1, int (&kb)[NKB]) {
+#pragma unroll
+  for (int n = 0; n < NKB; ++n) kb[n] = l1;
+  if (g.kind == 0) return;
+  int n = 0;
+  for (int l2 = 0; l2 < g.L; ++l2)
+    if (l2 != l1 && n < NKB) kb[n++] = l2;
 }
 
-// S block [64][L*64] for query band l1: scale*q.k + table[l1*L+l2][rel] + band mask + shift mask
-template <int HD>
-__device__ __forceinline__ void jscores(const float* Q, const float* K, float* S, int SS, const float* bias,
-                                        const int* label, const JGeom& g, int l1, float scale, int tid) {
-  constexpr int HS = HD + 1;
-  const int ty = tid >> 4, tx = tid & 15;
-  for (int l2 = 0; l2 < g.L; ++l2) {
-    if (jmasked(g, l1, l2)) {
-#pragma unroll
-      for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) S[(ty + 16 * ii) * SS + l2 * NTOK + tx + 16 * jj] = -INFINITY;
-      continue;
-    }
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    const float* Kl = K + l2 * NTOK * HS;
-#pragma unroll 4
-    for (int d = 0; d < HD; ++d) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = Q[(ty + 16 * i) * HS + d];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Kl[(tx + 16 * j) * HS + d];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-    const float* bt = bias + (l1 * g.L + l2) * 225;
-#pragma unroll
-    for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int i = ty + 16 * ii, j = tx + 16 * jj;
-        float s = acc[ii][jj] * scale + bt[((i >> 3) - (j >> 3) + 7) * 15 + ((i & 7) - (j & 7) + 7)];
-        if (label[i] != label[j]) s += -100.0f;
-        S[i * SS + l2 * NTOK + j] = s;
-      }
-  }
-}
+template <int HD, int NKB>
+struct JSmemF {
+  static constexpr int HS = attn::Pitch<HD>::HS, HSV = attn::Pitch<HD>::HSV, PS = NKB * NTOK + 4;
+  float q[NTOK * HS];
+  float k[NKB * NTOK * HS];
+  float v[NKB * NTOK * HSV];
+  float p[NTOK * PS];
+  float bias[NKB][232];
+  int rowq[NTOK];
+  int rowk[NKB][NTOK];
+  int label[NTOK];
+};
 
-__device__ __forceinline__ void jsoftmax(float* S, int SS, int ncol, int tid) {
-  const int w = tid >> 5, lane = tid & 31;
-  for (int r = 0; r < 8; ++r) {
-    float* row = S + (w * 8 + r) * SS;
-    float v[2 * MAXL];
-    float m = -INFINITY;
-#pragma unroll
-    for (int c = 0; c < 2 * MAXL; ++c) {
-      v[c] = (lane + 32 * c < ncol) ? row[lane + 32 * c] : -INFINITY;
-      m = fmaxf(m, v[c]);
-    }
-    m = warp_max(m);
-    float sum = 0.f;
-#pragma unroll
-    for (int c = 0; c < 2 * MAXL; ++c) {
-      v[c] = (lane + 32 * c < ncol) ? expf(v[c] - m) : 0.f;
-      sum += v[c];
-    }
-    const float inv = 1.0f / warp_sum(sum);
-#pragma unroll
-    for (int c = 0; c < 2 * MAXL; ++c)
-      if (lane + 32 * c < ncol) row[lane + 32 * c] = v[c] * inv;
-  }
-}
-
-template <int HD>
+template <int HD, int NKB>
 __global__ void __launch_bounds__(256) joint_fwd_kernel(const float* __restrict__ q, int64_t ldq,
                                                         const float* __restrict__ kv, int64_t ldkv,
                                                         float* __restrict__ o, JGeom g, float scale,
                                                         const float* __restrict__ tables) {
-  constexpr int HS = HD + 1;
-  extern __shared__ __align__(16) float sm[];
-  const int L = g.L, SS = L * NTOK + 1;
-  float* K = sm;                         // [L*64][HS]
-  float* V = K + L * NTOK * HS;
-  float* Q = V + L * NTOK * HS;          // [64][HS]
-  float* S = Q + NTOK * HS;              // [64][SS]
-  float* bias = S + NTOK * SS;           // [L*L][225]
-  int* pix = reinterpret_cast<int*>(bias + L * L * 225);
-  int* label = pix + NTOK;
+  using S = JSmemF<HD, NKB>;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  S& s = *reinterpret_cast<S*>(smraw);
   const int tid = threadIdx.x;
   const int C = g.heads * HD;
+  const int l1 = blockIdx.y;
   int id = blockIdx.x;
   const int h = id % g.heads; id /= g.heads;
   const int wx = id % g.nWx; id /= g.nWx;
   const int wy = id % g.nWy;
   const int b = id / g.nWy;
-  const int64_t HW = (int64_t)g.H * g.W;
+  const int HW = g.H * g.W;
+  int kb[NKB];
+  key_bands<NKB>(g, l1, kb);
 
-  if (tid < NTOK) jtoken(g, wy, wx, tid, pix[tid], label[tid]);
-  for (int i = tid; i < L * L * 225; i += 256) bias[i] = tables[(int64_t)i * g.heads + h];
+  if (tid < NTOK) {
+    int pix, label;
+    jtoken(g, wy, wx, tid, pix, label);
+    s.label[tid] = label;
+    s.rowq[tid] = (l1 * g.B + b) * HW + pix;
+#pragma unroll
+    for (int n = 0; n < NKB; ++n) s.rowk[n][tid] = (kb[n] * g.B + b) * HW + pix;
+  }
+#pragma unroll
+  for (int n = 0; n < NKB; ++n)
+    for (int i = tid; i < 225; i += 256) s.bias[n][i] = tables[((int64_t)(l1 * g.L + kb[n]) * 225 + i) * g.heads + h];
   __syncthreads();
-  for (int l = 0; l < L; ++l) {
-    const int64_t r0 = ((int64_t)l * g.B + b) * HW;
-    jload<HD>(K + l * NTOK * HS, kv, ldkv, h * HD, r0, pix, tid);
-    jload<HD>(V + l * NTOK * HS, kv, ldkv, C + h * HD, r0, pix, tid);
+  attn::load_tile<HD, S::HS, 256>(s.q, q, ldq, h * HD, s.rowq, tid);
+#pragma unroll
+  for (int n = 0; n < NKB; ++n) {
+    attn::load_tile<HD, S::HS, 256>(s.k + n * NTOK * S::HS, kv, ldkv, h * HD, s.rowk[n], tid);
+    attn::load_tile<HD, S::HSV, 256>(s.v + n * NTOK * S::HSV, kv, ldkv, C + h * HD, s.rowk[n], tid);
   }
-  for (int l1 = 0; l1 < L; ++l1) {
-    const int64_t r0 = ((int64_t)l1 * g.B + b) * HW;
-    __syncthreads();
-    jload<HD>(Q, q, ldq, h * HD, r0, pix, tid);
-    __syncthreads();
-    jscores<HD>(Q, K, S, SS, bias, label, g, l1, scale, tid);
-    __syncthreads();
-    jsoftmax(S, SS, L * NTOK, tid);
-    __syncthreads();
-    // O = P.V
-    const int ty = tid >> 4, tx = tid & 15;
-    constexpr int ND = (HD + 15) / 16;
-    float acc[4][ND];
+  __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int dd = 0; dd < ND; ++dd) acc[i][dd] = 0.f;
-    for (int j = 0; j < L * NTOK; ++j) {
-      if (jmasked(g, l1, j >> 6)) { j |= 63; continue; }          // whole band has zero weight
-      float p[4], v[ND];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) p[i] = S[(ty + 16 * i) * SS + j];
-#pragma unroll
-      for (int dd = 0; dd < ND; ++dd) { const int d = tx + 16 * dd; v[dd] = d < HD ? V[j * HS + d] : 0.f; }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int dd = 0; dd < ND; ++dd) acc[i][dd] = fmaf(p[i], v[dd], acc[i][dd]);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int dd = 0; dd < ND; ++dd) {
-        const int d = tx + 16 * dd;
-        if (d < HD) o[(r0 + pix[ty + 16 * i]) * C + h * HD + d] = acc[i][dd];
-      }
-  }
+  for (int n = 0; n < NKB; ++n)
+    attn::tile_abt<HD, true>(s.q, S::HS, s.k + n * NTOK * S::HS, S::HS, s.p + n * NTOK, S::PS, scale, s.bias[n], s.label, tid);
+  __syncthreads();
+  attn::softmax_rows<NKB * NTOK>(s.p, S::PS, tid);
+  __syncthreads();
+  attn::tile_pv<HD, false, NKB * NTOK, false>(s.p, S::PS, s.v, S::HSV, o, C, h * HD, s.rowq, 1.0f, tid);
 }
 
-template <int HD>
+template <int HD, int NKB>
+struct JSmemB {
+  static constexpr int HS = attn::Pitch<HD>::HS, PS = NKB * NTOK + 4;
+  float q[NTOK * HS];
+  float dO[NTOK * HS];
+  float k[NKB * NTOK * HS];
+  float v[NKB * NTOK * HS];
+  float p[NTOK * PS];            // S -> P -> dS
+  float red[2][NTOK];
+  float bias[NKB][232];
+  float dbias[NKB][232];
+  int rowq[NTOK];
+  int rowk[NKB][NTOK];
+  int label[NTOK];
+};
+
+template <int HD, int NKB, bool ATOMIC>
 __global__ void __launch_bounds__(256) joint_bwd_kernel(const float* __restrict__ q, int64_t ldq,
                                                         const float* __restrict__ kv, int64_t ldkv,
                                                         const float* __restrict__ dout, float* __restrict__ dq,
                                                         float* __restrict__ dkv, JGeom g, float scale,
                                                         const float* __restrict__ tables, float* __restrict__ dtables,
                                                         int total_items) {
-  constexpr int HS = HD + 1;
-  constexpr int ND = (HD + 15) / 16;
-  extern __shared__ __align__(16) float sm[];
-  const int L = g.L, SS = L * NTOK + 1, LT = L * NTOK;
-  float* K = sm;
-  float* V = K + LT * HS;
-  float* Q = V + LT * HS;
-  float* dO = Q + NTOK * HS;
-  float* P = dO + NTOK * HS;             // [64][SS]
-  float* X = P + NTOK * SS;              // dP -> dS
-  float* bias = X + NTOK * SS;
-  float* dbias = bias + L * L * 225;
-  int* pix = reinterpret_cast<int*>(dbias + L * L * 225);
-  int* label = pix + NTOK;
+  using S = JSmemB<HD, NKB>;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  S& s = *reinterpret_cast<S*>(smraw);
   const int tid = threadIdx.x;
-  const int ty = tid >> 4, tx = tid & 15;
   const int C = g.heads * HD;
+  const int l1 = blockIdx.y;
+  // gridDim.x is a multiple of heads, so every item this CTA visits has the same head (and the same query band)
   const int h = blockIdx.x % g.heads;
-  const int64_t HW = (int64_t)g.H * g.W;
-  for (int i = tid; i < L * L * 225; i += 256) { bias[i] = tables[(int64_t)i * g.heads + h]; dbias[i] = 0.f; }
+  const int HW = g.H * g.W;
+  int kb[NKB];
+  key_bands<NKB>(g, l1, kb);
+#pragma unroll
+  for (int n = 0; n < NKB; ++n)
+    for (int i = tid; i < 232; i += 256) {
+      s.bias[n][i] = i < 225 ? tables[((int64_t)(l1 * g.L + kb[n]) * 225 + i) * g.heads + h] : 0.f;
+      s.dbias[n][i] = 0.f;
+    }
 
   for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
     int id = item / g.heads;
@@ -219,165 +154,88 @@ __global__ void __launch_bounds__(256) joint_bwd_kernel(const float* __restrict_
     const int wy = id % g.nWy;
     const int b = id / g.nWy;
     __syncthreads();
-    if (tid < NTOK) jtoken(g, wy, wx, tid, pix[tid], label[tid]);
+    if (tid < NTOK) {
+      int pix, label;
+      jtoken(g, wy, wx, tid, pix, label);
+      s.label[tid] = label;
+      s.rowq[tid] = (l1 * g.B + b) * HW + pix;
+#pragma unroll
+      for (int n = 0; n < NKB; ++n) s.rowk[n][tid] = (kb[n] * g.B + b) * HW + pix;
+    }
     __syncthreads();
-    for (int l = 0; l < L; ++l) {
-      const int64_t r0 = ((int64_t)l * g.B + b) * HW;
-      jload<HD>(K + l * NTOK * HS, kv, ldkv, h * HD, r0, pix, tid);
-      jload<HD>(V + l * NTOK * HS, kv, ldkv, C + h * HD, r0, pix, tid);
+    attn::load_tile<HD, S::HS, 256>(s.q, q, ldq, h * HD, s.rowq, tid);
+    attn::load_tile<HD, S::HS, 256>(s.dO, dout, C, h * HD, s.rowq, tid);
+#pragma unroll
+    for (int n = 0; n < NKB; ++n) {
+      attn::load_tile<HD, S::HS, 256>(s.k + n * NTOK * S::HS, kv, ldkv, h * HD, s.rowk[n], tid);
+      attn::load_tile<HD, S::HS, 256>(s.v + n * NTOK * S::HS, kv, ldkv, C + h * HD, s.rowk[n], tid);
     }
-    // per-thread accumulators of dK / dV: token j = ty + 16*jj (jj < 4L), feature d = tx + 16*dd
-    float aK[4 * MAXL][ND], aV[4 * MAXL][ND];
+    __syncthreads();
 #pragma unroll
-    for (int jj = 0; jj < 4 * MAXL; ++jj)
+    for (int n = 0; n < NKB; ++n)
+      attn::tile_abt<HD, true>(s.q, S::HS, s.k + n * NTOK * S::HS, S::HS, s.p + n * NTOK, S::PS, scale, s.bias[n], s.label, tid);
+    __syncthreads();
+    attn::softmax_rows<NKB * NTOK>(s.p, S::PS, tid);
+    __syncthreads();
+    // dV[kb] = P[:, kb]^T . dO
 #pragma unroll
-      for (int dd = 0; dd < ND; ++dd) { aK[jj][dd] = 0.f; aV[jj][dd] = 0.f; }
-
-    for (int l1 = 0; l1 < L; ++l1) {
-      const int64_t r0 = ((int64_t)l1 * g.B + b) * HW;
-      __syncthreads();
-      jload<HD>(Q, q, ldq, h * HD, r0, pix, tid);
-      jload<HD>(dO, dout, C, h * HD, r0, pix, tid);
-      __syncthreads();
-      jscores<HD>(Q, K, P, SS, bias, label, g, l1, scale, tid);
-      // dP[i][c] = dO_i . V_c
-      for (int l2 = 0; l2 < L; ++l2) {
-        float acc[4][4];
+    for (int n = 0; n < NKB; ++n)
+      attn::tile_pv<HD, true, NTOK, ATOMIC>(s.p + n * NTOK, S::PS, s.dO, S::HS, dkv, 2 * C, C + h * HD, s.rowk[n], 1.0f, tid);
+    // dP = dO . V^T as MMA fragments (warp w: rows 16*(w&3).., column half w>>2 of every key band)
+    const int w = tid >> 5, lane = tid & 31;
+    const int m0 = (w & 3) * 16, n0 = (w >> 2) * 32;
+    const int gq = lane >> 2, tq = lane & 3;
+    float dp[NKB][4][4];
+    float part0 = 0.f, part1 = 0.f;                 // sum_j P*dP over this thread's columns, rows m0+gq and m0+gq+8
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+    for (int n = 0; n < NKB; ++n) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-        if (jmasked(g, l1, l2)) {
+      for (int i = 0; i < 4; ++i) { dp[n][i][0] = dp[n][i][1] = dp[n][i][2] = dp[n][i][3] = 0.f; }
+      const float* Vn = s.v + n * NTOK * S::HS;
+      mma32::warp_mma<4>(dp[n], attn::Pitch<HD>::KP / 8, [&](int m, int k) { return s.dO[(m0 + m) * S::HS + k]; },
+                         [&](int k, int nn) { return Vn[(n0 + nn) * S::HS + k]; }, lane);
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+      for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) X[(ty + 16 * i) * SS + l2 * NTOK + tx + 16 * j] = 0.f;
-          continue;
+        for (int r = 0; r < 4; ++r) {
+          const int i = m0 + gq + ((r & 2) ? 8 : 0), j = n * NTOK + n0 + nt * 8 + 2 * tq + (r & 1);
+          const float pv = s.p[i * S::PS + j] * dp[n][nt][r];
+          if (r & 2) part1 += pv; else part0 += pv;
         }
-        const float* Vl = V + l2 * NTOK * HS;
-#pragma unroll 4
-        for (int d = 0; d < HD; ++d) {
-          float a[4], bb[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) a[i] = dO[(ty + 16 * i) * HS + d];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) bb[j] = Vl[(tx + 16 * j) * HS + d];
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) X[(ty + 16 * i) * SS + l2 * NTOK + tx + 16 * j] = acc[i][j];
-      }
-      __syncthreads();
-      jsoftmax(P, SS, LT, tid);
-      __syncthreads();
-      // dV += P^T.dO (uses P), then dS = P o (dP - rowsum(dP o P)) in X
-#pragma unroll
-      for (int jj = 0; jj < 4 * MAXL; ++jj) {
-        if (jj >= 4 * L) break;
-        if (jmasked(g, l1, jj >> 2)) continue;
-        const int j = ty + 16 * jj;
-        for (int i = 0; i < NTOK; ++i) {
-          const float p = P[i * SS + j];
-#pragma unroll
-          for (int dd = 0; dd < ND; ++dd) {
-            const int d = tx + 16 * dd;
-            if (d < HD) aV[jj][dd] = fmaf(p, dO[i * HS + d], aV[jj][dd]);
-          }
-        }
-      }
-      {
-        const int w = tid >> 5, lane = tid & 31;
-        for (int r = 0; r < 8; ++r) {
-          const int i = w * 8 + r;
-          float dot = 0.f;
-          for (int c = lane; c < LT; c += 32) dot += P[i * SS + c] * X[i * SS + c];      // masked blocks: P = 0, X = 0
-          dot = warp_sum(dot);
-          for (int c = lane; c < LT; c += 32) {
-            if (jmasked(g, l1, c >> 6)) continue;                                       // dS stays 0 there
-            const float ds = P[i * SS + c] * (X[i * SS + c] - dot);
-            X[i * SS + c] = ds;
-            if (dtables) {
-              const int l2 = c >> 6, j = c & 63;
-              atomicAdd(&dbias[(l1 * L + l2) * 225 + ((i >> 3) - (j >> 3) + 7) * 15 + ((i & 7) - (j & 7) + 7)], ds);
-            }
-          }
-        }
-      }
-      __syncthreads();
-      // dQ = scale * dS.K  -> global ; dK += scale * dS^T.Q
-      {
-        float acc[4][ND];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int dd = 0; dd < ND; ++dd) acc[i][dd] = 0.f;
-        for (int c = 0; c < LT; ++c) {
-          if (jmasked(g, l1, c >> 6)) { c |= 63; continue; }
-          float s4[4], k4[ND];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) s4[i] = X[(ty + 16 * i) * SS + c];
-#pragma unroll
-          for (int dd = 0; dd < ND; ++dd) { const int d = tx + 16 * dd; k4[dd] = d < HD ? K[c * HS + d] : 0.f; }
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int dd = 0; dd < ND; ++dd) acc[i][dd] = fmaf(s4[i], k4[dd], acc[i][dd]);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int dd = 0; dd < ND; ++dd) {
-            const int d = tx + 16 * dd;
-            if (d < HD) dq[(r0 + pix[ty + 16 * i]) * C + h * HD + d] = acc[i][dd] * scale;
-          }
-      }
-#pragma unroll
-      for (int jj = 0; jj < 4 * MAXL; ++jj) {
-        if (jj >= 4 * L) break;
-        if (jmasked(g, l1, jj >> 2)) continue;
-        const int j = ty + 16 * jj;
-        for (int i = 0; i < NTOK; ++i) {
-          const float ds = X[i * SS + j] * scale;
-#pragma unroll
-          for (int dd = 0; dd < ND; ++dd) {
-            const int d = tx + 16 * dd;
-            if (d < HD) aK[jj][dd] = fmaf(ds, Q[i * HS + d], aK[jj][dd]);
-          }
-        }
-      }
     }
+    part0 += __shfl_xor_sync(0xffffffffu, part0, 1); part0 += __shfl_xor_sync(0xffffffffu, part0, 2);
+    part1 += __shfl_xor_sync(0xffffffffu, part1, 1); part1 += __shfl_xor_sync(0xffffffffu, part1, 2);
+    if (tq == 0) { s.red[w >> 2][m0 + gq] = part0; s.red[w >> 2][m0 + gq + 8] = part1; }
+    __syncthreads();                                // row sums complete; dV reads of P complete
+    {
+      const float D0 = s.red[0][m0 + gq] + s.red[1][m0 + gq], D1 = s.red[0][m0 + gq + 8] + s.red[1][m0 + gq + 8];
 #pragma unroll
-    for (int jj = 0; jj < 4 * MAXL; ++jj) {
-      if (jj >= 4 * L) break;
-      const int j = ty + 16 * jj;
-      const int l = j >> 6, t = j & 63;
-      const int64_t row = ((int64_t)l * g.B + b) * HW + pix[t];
+      for (int n = 0; n < NKB; ++n)
 #pragma unroll
-      for (int dd = 0; dd < ND; ++dd) {
-        const int d = tx + 16 * dd;
-        if (d < HD) {
-          dkv[row * 2 * C + h * HD + d] = aK[jj][dd];
-          dkv[row * 2 * C + C + h * HD + d] = aV[jj][dd];
-        }
-      }
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int i = m0 + gq + ((r & 2) ? 8 : 0), jl = n0 + nt * 8 + 2 * tq + (r & 1);
+            float* pp = &s.p[i * S::PS + n * NTOK + jl];
+            const float ds = *pp * (dp[n][nt][r] - ((r & 2) ? D1 : D0));
+            *pp = ds;
+            if (dtables) atomicAdd(&s.dbias[n][((i >> 3) - (jl >> 3) + 7) * 15 + ((i & 7) - (jl & 7) + 7)], ds);
+          }
     }
+    __syncthreads();
+    // dQ = scale * dS . K ;  dK[kb] = scale * dS[:, kb]^T . Q
+    attn::tile_pv<HD, false, NKB * NTOK, false>(s.p, S::PS, s.k, S::HS, dq, C, h * HD, s.rowq, scale, tid);
+#pragma unroll
+    for (int n = 0; n < NKB; ++n)
+      attn::tile_pv<HD, true, NTOK, ATOMIC>(s.p + n * NTOK, S::PS, s.q, S::HS, dkv, 2 * C, h * HD, s.rowk[n], scale, tid);
   }
   __syncthreads();
-  if (dtables) for (int i = tid; i < L * L * 225; i += 256) atomicAdd(&dtables[(int64_t)i * g.heads + h], dbias[i]);
-}
-
-size_t fwd_smem(int L, int HD) {
-  const int HS = HD + 1, SS = L * NTOK + 1;
-  return sizeof(float) * ((size_t)2 * L * NTOK * HS + NTOK * HS + NTOK * SS + L * L * 225) + sizeof(int) * 2 * NTOK;
-}
-size_t bwd_smem(int L, int HD) {
-  const int HS = HD + 1, SS = L * NTOK + 1;
-  return sizeof(float) * ((size_t)2 * L * NTOK * HS + 2 * NTOK * HS + 2 * NTOK * SS + 2 * L * L * 225) + sizeof(int) * 2 * NTOK;
+  if (dtables) {
+#pragma unroll
+    for (int n = 0; n < NKB; ++n)
+      for (int i = tid; i < 225; i += 256)
+        atomicAdd(&dtables[((int64_t)(l1 * g.L + kb[n]) * 225 + i) * g.heads + h], s.dbias[n][i]);
+  }
 }
 
 int jcheck(const char* who, int L, int B, int H, int W, int heads, int hd, int shift, int kind, int64_t ldq, int64_t ldkv,
@@ -390,7 +248,41 @@ int jcheck(const char* who, int L, int B, int H, int W, int heads, int hd, int s
   FA_REQUIRE(kind == 0 || kind == 1, "%s: kind must be 0 (intra) or 1 (inter)", who);
   FA_REQUIRE(kind == 0 || L >= 2, "%s: inter-band attention needs L >= 2", who);
   FA_REQUIRE(ldq % 4 == 0 && ldkv % 4 == 0, "%s: row strides must be multiples of 4 floats", who);
+  FA_REQUIRE((int64_t)L * B * H * W < (1ll << 31) / 64, "%s: too many tokens", who);
   g.L = L; g.B = B; g.H = H; g.W = W; g.heads = heads; g.shift = shift; g.nWy = H / WIN; g.nWx = W / WIN; g.kind = kind;
+  return FA_OK;
+}
+
+template <int HD, int NKB>
+int launch_jfwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, float* o, const JGeom& g, float scale,
+                const float* tables, cudaStream_t st) {
+  const size_t smem = sizeof(JSmemF<HD, NKB>);
+  static bool done = false;
+  if (!done) {
+    FA_CUDA(cudaFuncSetAttribute(joint_fwd_kernel<HD, NKB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    done = true;
+  }
+  dim3 grid((unsigned)(g.B * g.nWy * g.nWx * g.heads), (unsigned)g.L);
+  joint_fwd_kernel<HD, NKB><<<grid, 256, smem, st>>>(q, ldq, kv, ldkv, o, g, scale, tables);
+  FA_LAUNCH_CHECK("fa_joint_attn_fwd");
+  return FA_OK;
+}
+
+template <int HD, int NKB, bool ATOMIC>
+int launch_jbwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, const float* dout, float* dq, float* dkv,
+                const JGeom& g, float scale, const float* tables, float* dtables, cudaStream_t st) {
+  const size_t smem = sizeof(JSmemB<HD, NKB>);
+  static bool done = false;
+  if (!done) {
+    FA_CUDA(cudaFuncSetAttribute(joint_bwd_kernel<HD, NKB, ATOMIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    done = true;
+  }
+  const int items = g.B * g.nWy * g.nWx * g.heads;
+  int gx = ((4 * kNumSMs / g.L + g.heads - 1) / g.heads) * g.heads;      // ~4 CTAs per SM in total, multiple of heads
+  if (gx > items) gx = items;                                           // items is a multiple of heads
+  dim3 grid((unsigned)gx, (unsigned)g.L);
+  joint_bwd_kernel<HD, NKB, ATOMIC><<<grid, 256, smem, st>>>(q, ldq, kv, ldkv, dout, dq, dkv, g, scale, tables, dtables, items);
+  FA_LAUNCH_CHECK("fa_joint_attn_bwd");
   return FA_OK;
 }
 
@@ -401,48 +293,40 @@ extern "C" {
 int fa_joint_attn_fwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, float* o, int L, int B, int H, int W,
                       int heads, int hd, int shift, float scale, const float* tables, int kind, fa_stream_t stream) {
   FA_REQUIRE(q && kv && o && tables, "fa_joint_attn_fwd: null pointer");
+  FA_REQUIRE(((uintptr_t)q | (uintptr_t)kv | (uintptr_t)o) % 16 == 0, "fa_joint_attn_fwd: pointers must be 16-byte aligned");
   JGeom g;
   int rc = jcheck("fa_joint_attn_fwd", L, B, H, W, heads, hd, shift, kind, ldq, ldkv, g);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   FaProfScope prof(FA_K_JOINT_ATTN, st);
-  const size_t smem = fwd_smem(L, hd);
-  const int items = B * g.nWy * g.nWx * heads;
-  if (hd == 28) {
-    FA_CUDA(cudaFuncSetAttribute(joint_fwd_kernel<28>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    joint_fwd_kernel<28><<<items, 256, smem, st>>>(q, ldq, kv, ldkv, o, g, scale, tables);
-  } else {
-    FA_CUDA(cudaFuncSetAttribute(joint_fwd_kernel<56>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    joint_fwd_kernel<56><<<items, 256, smem, st>>>(q, ldq, kv, ldkv, o, g, scale, tables);
-  }
-  FA_LAUNCH_CHECK("fa_joint_attn_fwd");
-  return FA_OK;
+  const int nkb = (kind == 0) ? 1 : L - 1;
+  if (hd == 28) return nkb == 1 ? launch_jfwd<28, 1>(q, ldq, kv, ldkv, o, g, scale, tables, st)
+                                : launch_jfwd<28, 2>(q, ldq, kv, ldkv, o, g, scale, tables, st);
+  return nkb == 1 ? launch_jfwd<56, 1>(q, ldq, kv, ldkv, o, g, scale, tables, st)
+                  : launch_jfwd<56, 2>(q, ldq, kv, ldkv, o, g, scale, tables, st);
 }
 
 int fa_joint_attn_bwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, const float* dout, float* dq,
                       float* dkv, int L, int B, int H, int W, int heads, int hd, int shift, float scale,
                       const float* tables, float* dtables, int kind, fa_stream_t stream) {
   FA_REQUIRE(q && kv && dout && dq && dkv && tables, "fa_joint_attn_bwd: null pointer");
+  FA_REQUIRE(((uintptr_t)q | (uintptr_t)kv | (uintptr_t)dout | (uintptr_t)dq | (uintptr_t)dkv) % 16 == 0,
+             "fa_joint_attn_bwd: pointers must be 16-byte aligned");
   JGeom g;
   int rc = jcheck("fa_joint_attn_bwd", L, B, H, W, heads, hd, shift, kind, ldq, ldkv, g);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   FaProfScope prof(FA_K_JOINT_ATTN, st);
-  const size_t smem = bwd_smem(L, hd);
-  FA_REQUIRE(smem <= 227 * 1024, "fa_joint_attn_bwd: L=%d hd=%d needs %zu B of shared memory", L, hd, smem);
-  const int items = B * g.nWy * g.nWx * heads;
-  int grid = (2 * kNumSMs / heads) * heads;
-  if (grid < heads) grid = heads;
-  if (grid > items) grid = items;
-  if (hd == 28) {
-    FA_CUDA(cudaFuncSetAttribute(joint_bwd_kernel<28>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    joint_bwd_kernel<28><<<grid, 256, smem, st>>>(q, ldq, kv, ldkv, dout, dq, dkv, g, scale, tables, dtables, items);
-  } else {
-    FA_CUDA(cudaFuncSetAttribute(joint_bwd_kernel<56>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    joint_bwd_kernel<56><<<grid, 256, smem, st>>>(q, ldq, kv, ldkv, dout, dq, dkv, g, scale, tables, dtables, items);
+  const int nkb = (kind == 0) ? 1 : L - 1;
+  const int C = heads * hd;
+  if (nkb == 2) {
+    // two query bands add into every key band's gradient: zero-fill, then fp32 atomics
+    FA_CUDA(cudaMemsetAsync(dkv, 0, (size_t)L * B * H * W * 2 * C * sizeof(float), st));
+    if (hd == 28) return launch_jbwd<28, 2, true>(q, ldq, kv, ldkv, dout, dq, dkv, g, scale, tables, dtables, st);
+    return launch_jbwd<56, 2, true>(q, ldq, kv, ldkv, dout, dq, dkv, g, scale, tables, dtables, st);
   }
-  FA_LAUNCH_CHECK("fa_joint_attn_bwd");
-  return FA_OK;
+  if (hd == 28) return launch_jbwd<28, 1, false>(q, ldq, kv, ldkv, dout, dq, dkv, g, scale, tables, dtables, st);
+  return launch_jbwd<56, 1, false>(q, ldq, kv, ldkv, dout, dq, dkv, g, scale, tables, dtables, st);
 }
 
 }  // extern "C"

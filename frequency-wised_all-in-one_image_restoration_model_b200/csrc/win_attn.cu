@@ -9,13 +9,14 @@
 // across all windows a CTA visits before one flush of 225 atomics.
 #include "freqair_internal.h"
 #include "fft64.cuh"
-#include "mma_tf32.cuh"
+#include "attn_tiles.cuh"
 
 namespace {
 
 constexpr int NTHR = 288;
-constexpr int WIN = 8;
-constexpr int NTOK = 64;
+using attn::WIN;
+using attn::NTOK;
+using attn::Pitch;
 
 struct WinGeom {
   int B, H, W, heads, shift, nWy, nWx;
@@ -33,14 +34,6 @@ __device__ __forceinline__ void token_of(const WinGeom& g, int b, int wy, int wx
   label = g.shift > 0 ? ry * 3 + rx : 0;
 }
 
-// smem row pitches of the 64 x hd operand tiles: KP = hd rounded up to the MMA k-step (zero-filled), pitch == 4 (mod 32)
-// makes the K-contiguous fragment loads (rows g / g+8, cols t / t+4) bank-conflict-free; the forward V tile, read with
-// the key index as k, uses pitch == 8 (mod 32) for the same reason.
-template <int HD> struct Pitch;
-template <> struct Pitch<28> { static constexpr int KP = 32, HS = 36, HSV = 40; };
-template <> struct Pitch<56> { static constexpr int KP = 56, HS = 60, HSV = 72; };
-template <> struct Pitch<64> { static constexpr int KP = 64, HS = 68, HSV = 72; };
-
 template <int HD>
 struct Smem {
   static constexpr int HS = Pitch<HD>::HS;
@@ -57,91 +50,22 @@ struct Smem {
   uint8_t band[NTOK * 33 + 8];
 };
 
+// thin adaptors onto the shared tensor-core tile routines (64 keys, map pitch fft64::PSTR)
 template <int HD, int HS>
 __device__ __forceinline__ void load_tile(float* dst, const float* __restrict__ src, int64_t ld, int col0,
                                           const int* rows, int tid) {
-  constexpr int KP = Pitch<HD>::KP;
-  constexpr int V4 = KP / 4;
-  for (int i = tid; i < NTOK * V4; i += NTHR) {
-    const int t = i / V4, d = (i % V4) * 4;
-    const float4 v = d < HD ? *reinterpret_cast<const float4*>(src + (int64_t)rows[t] * ld + col0 + d)
-                            : make_float4(0.f, 0.f, 0.f, 0.f);            // k-padding of the contraction
-    *reinterpret_cast<float4*>(dst + t * HS + d) = v;
-  }
+  attn::load_tile<HD, HS, NTHR>(dst, src, ld, col0, rows, tid);
 }
-
-// out[i*PSTR + j] = scale * dot(A_i, B_j) (+ bias + mask) on the tensor cores: warp w owns rows 16*(w&3).. and the
-// 32-column half (w>>2)
 template <int HD, bool BIASMASK>
 __device__ __forceinline__ void tile_abt(const float* A, int lda, const float* Bm, int ldb, float* out, float scale,
                                          const float* bias, const int* label, int tid) {
-  if (tid >= 256) return;
-  const int w = tid >> 5, lane = tid & 31;
-  const int m0 = (w & 3) * 16, n0 = (w >> 2) * 32;
-  float c[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f; }
-  mma32::warp_mma<4>(c, Pitch<HD>::KP / 8, [&](int m, int k) { return A[(m0 + m) * lda + k]; },
-                     [&](int k, int n) { return Bm[(n0 + n) * ldb + k]; }, lane);
-  const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int i = m0 + g + ((r & 2) ? 8 : 0), j = n0 + nt * 8 + 2 * t + (r & 1);
-      float sv = c[nt][r] * scale;
-      if (BIASMASK) {
-        sv += bias[((i >> 3) - (j >> 3) + 7) * 15 + ((i & 7) - (j & 7) + 7)];
-        if (label[i] != label[j]) sv += -100.0f;
-      }
-      out[i * fft64::PSTR + j] = sv;
-    }
+  attn::tile_abt<HD, BIASMASK>(A, lda, Bm, ldb, out, fft64::PSTR, scale, bias, label, tid);
 }
-
-__device__ __forceinline__ void softmax_rows(float* P, int tid) {
-  if (tid >= 256) return;
-  const int w = tid >> 5, lane = tid & 31;
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    float* row = P + (w * 8 + r) * fft64::PSTR;
-    const float a = row[lane], b = row[lane + 32];
-    const float m = warp_max(fmaxf(a, b));
-    const float ea = expf(a - m), eb = expf(b - m);
-    const float inv = 1.0f / warp_sum(ea + eb);
-    row[lane] = ea * inv;
-    row[lane + 32] = eb * inv;
-  }
-}
-
-// out[i][d] = scale * sum_j P[i][j] * V[j][d]   (TRANS: sum_j P[j][i] * V[j][d]), written to global rows.
-// warp w owns rows 16*(w&3).. and the interleaved 8-column tiles (w>>2), (w>>2)+2, ... of the hd outputs.
+__device__ __forceinline__ void softmax_rows(float* P, int tid) { attn::softmax_rows<64>(P, fft64::PSTR, tid); }
 template <int HD, bool TRANS>
 __device__ __forceinline__ void tile_pv(const float* P, const float* V, int ldv, float* __restrict__ out, int64_t ld,
                                         int col0, const int* rows, float scale, int tid) {
-  if (tid >= 256) return;
-  constexpr int NTT = (HD + 7) / 8;          // 8-wide output tiles
-  constexpr int NTW = (NTT + 1) / 2;         // per warp
-  const int w = tid >> 5, lane = tid & 31;
-  const int m0 = (w & 3) * 16, nh = w >> 2;
-  float c[NTW][4];
-#pragma unroll
-  for (int i = 0; i < NTW; ++i) { c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f; }
-  mma32::warp_mma<NTW>(c, NTOK / 8,
-                       [&](int m, int k) { return TRANS ? P[k * fft64::PSTR + m0 + m] : P[(m0 + m) * fft64::PSTR + k]; },
-                       [&](int k, int n) {
-                         const int d = (nh + 2 * (n >> 3)) * 8 + (n & 7);
-                         return d < Pitch<HD>::KP ? V[k * ldv + d] : 0.f;
-                       },
-                       lane);
-  const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int nt = 0; nt < NTW; ++nt) {
-    const int d = (nh + 2 * nt) * 8 + 2 * t;
-    if (d < HD) {                              // HD is even: both columns of the pair are valid
-      *reinterpret_cast<float2*>(out + (int64_t)rows[m0 + g] * ld + col0 + d) = make_float2(c[nt][0] * scale, c[nt][1] * scale);
-      *reinterpret_cast<float2*>(out + (int64_t)rows[m0 + g + 8] * ld + col0 + d) = make_float2(c[nt][2] * scale, c[nt][3] * scale);
-    }
-  }
+  attn::tile_pv<HD, TRANS, 64, false>(P, fft64::PSTR, V, ldv, out, ld, col0, rows, scale, tid);
 }
 
 template <int HD>
