@@ -132,6 +132,22 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// explicit shared-space accesses: the 1024-byte alignment of the dynamic smem base goes through an integer cast, after
+// which the compiler only knows a generic pointer and would emit LD.E / ST.E (generic path, long-scoreboard latency)
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+
 __device__ __forceinline__ float lo1(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __device__ __forceinline__ float4 lo4(float4 v) { return make_float4(lo1(v.x), lo1(v.y), lo1(v.z), lo1(v.w)); }
 
@@ -241,13 +257,13 @@ __device__ __forceinline__ void epi_vec(float4 x, const EpiTC& e, float4 b4, int
 
 // the 8 row-quads of one 32 x 32 chunk (lane = 4 columns of row it*4 + lane/8)
 template <int MODE, int ACT>
-__device__ __forceinline__ void epi_rows(const float* stg, const EpiTC& e, float4 b4, int row0, int rsub, int c4, int col,
+__device__ __forceinline__ void epi_rows(uint32_t stg_s, const EpiTC& e, float4 b4, int row0, int rsub, int c4, int col,
                                          int M, float* __restrict__ cp0, int64_t ldc) {
 #pragma unroll(MODE == EPI_ANY ? 1 : 4)
   for (int it = 0; it < 8; ++it) {
     const int r = it * 4 + rsub;
     if (row0 + r < M)
-      epi_vec<MODE, ACT>(*reinterpret_cast<const float4*>(&stg[stg_idx(r, c4)]), e, b4, row0 + r, col, cp0 + (int64_t)it * 4 * ldc);
+      epi_vec<MODE, ACT>(lds128(stg_s + 4 * stg_idx(r, c4)), e, b4, row0 + r, col, cp0 + (int64_t)it * 4 * ldc);
   }
 }
 
@@ -380,14 +396,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
         const int nkb = (min(g.K, kbeg + g.k_chunk) - kbeg + BK - 1) / BK;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           mbar_wait(&full[s], (it / STAGES) & 1);
-          const float4* a = reinterpret_cast<const float4*>(sA + s * A_BYTES);
-          float4* al = reinterpret_cast<float4*>(sAlo + s * A_BYTES);
+          // all loads first, then all stores: a load-convert-store chain per element would serialise ~32 shared-memory
+          // round trips per stage (measured: the split stage, not the tensor pipe, then paces the whole kernel)
+          constexpr int NA = A_BYTES / 16 / (SPLIT_WARPS * 32), NB = B_BYTES / 16 / (SPLIT_WARPS * 32);
+          const uint32_t a = smem_u32(sA + s * A_BYTES) + st * 16, b = smem_u32(sB + s * B_BYTES) + st * 16;
+          const uint32_t al = smem_u32(sAlo + s * A_BYTES) + st * 16, bl = smem_u32(sBlo + s * B_BYTES) + st * 16;
+          float4 ra[NA], rb[NB];
 #pragma unroll
-          for (int i = 0; i < A_BYTES / 16 / (SPLIT_WARPS * 32); ++i) al[st + i * SPLIT_WARPS * 32] = lo4(a[st + i * SPLIT_WARPS * 32]);
-          const float4* b = reinterpret_cast<const float4*>(sB + s * B_BYTES);
-          float4* bl = reinterpret_cast<float4*>(sBlo + s * B_BYTES);
+          for (int i = 0; i < NA; ++i) ra[i] = lds128(a + i * SPLIT_WARPS * 512);
 #pragma unroll
-          for (int i = 0; i < B_BYTES / 16 / (SPLIT_WARPS * 32); ++i) bl[st + i * SPLIT_WARPS * 32] = lo4(b[st + i * SPLIT_WARPS * 32]);
+          for (int i = 0; i < NB; ++i) rb[i] = lds128(b + i * SPLIT_WARPS * 512);
+#pragma unroll
+          for (int i = 0; i < NA; ++i) sts128(al + i * SPLIT_WARPS * 512, lo4(ra[i]));
+#pragma unroll
+          for (int i = 0; i < NB; ++i) sts128(bl + i * SPLIT_WARPS * 512, lo4(rb[i]));
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to UMMA
           mbar_arrive(&ready[s]);
           if (++s == STAGES) s = 0;
@@ -400,6 +422,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     const int q = warp & 3;
     const int half = ew >> 2;                 // which interleaved set of 32-column chunks: half, half+2
     float* stg = stg_all + ew * (32 * 32);
+    const uint32_t stg_s = smem_u32(stg);
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;        // vector path: a warp instruction covers 4 rows x 32 columns
     uint32_t lu = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -441,8 +464,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
           // transpose through smem: thread = row writes its 32 columns (8 x float4, conflict-free by the XOR swizzle)
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj)
-            *reinterpret_cast<float4*>(&stg[stg_idx(lane, 4 * jj)]) =
-                make_float4(v[ci][4 * jj], v[ci][4 * jj + 1], v[ci][4 * jj + 2], v[ci][4 * jj + 3]);
+            sts128(stg_s + 4 * stg_idx(lane, 4 * jj), make_float4(v[ci][4 * jj], v[ci][4 * jj + 1], v[ci][4 * jj + 2], v[ci][4 * jj + 3]));
           __syncwarp();
           if (epi.vec) {
             const int col = n0 + c * 32 + c4;
@@ -452,10 +474,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
                 if (epi.bias) b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
               float* cp0 = C + (int64_t)(row0 + rsub) * g.ldc + col;
               const int act = (MODE == EPI_FWD) ? epi.act : (MODE == EPI_BWD ? epi.aux_act : ACT_NONE);
-              if (act == ACT_GELU) epi_rows<MODE, ACT_GELU>(stg, epi, b4, row0, rsub, c4, col, g.M, cp0, g.ldc);
-              else if (act == ACT_LRELU) epi_rows<MODE, ACT_LRELU>(stg, epi, b4, row0, rsub, c4, col, g.M, cp0, g.ldc);
-              else if (act == ACT_SIGMOID) epi_rows<MODE, ACT_SIGMOID>(stg, epi, b4, row0, rsub, c4, col, g.M, cp0, g.ldc);
-              else epi_rows<MODE, ACT_NONE>(stg, epi, b4, row0, rsub, c4, col, g.M, cp0, g.ldc);
+              if (act == ACT_GELU) epi_rows<MODE, ACT_GELU>(stg_s, epi, b4, row0, rsub, c4, col, g.M, cp0, g.ldc);
+              else if (act == ACT_LRELU) epi_rows<MODE, ACT_LRELU>(stg_s, epi, b4, row0, rsub, c4, col, g.M, cp0, g.ldc);
+              else if (act == ACT_SIGMOID) epi_rows<MODE, ACT_SIGMOID>(stg_s, epi, b4, row0, rsub, c4, col, g.M, cp0, g.ldc);
+              else epi_rows<MODE, ACT_NONE>(stg_s, epi, b4, row0, rsub, c4, col, g.M, cp0, g.ldc);
             }
           } else {
             // scalar fallback (ragged N or unaligned rows): lane = column, every FaGemmEpilogue field honoured
@@ -466,7 +488,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll 1
             for (int r = 0; r < nrows; ++r) {
               const int row = row0 + r;
-              float x = stg[stg_idx(r, lane)] * epi.alpha;
+              float x = lds32(stg_s + 4 * stg_idx(r, lane)) * epi.alpha;
               if (!colok) continue;
               float* cp = C + (int64_t)row * g.ldc + col;
               if (epi.atomic) { atomicAdd(cp, x); continue; }

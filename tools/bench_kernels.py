@@ -104,9 +104,38 @@ def bench_epi(backend):
         print(f'{name:28s} {ms:8.3f} ms {byts / ms / 1e6:8.0f} GB/s', flush=True)
 
 
+def bench_misc():
+    """Bandwidth kernels at the shapes of the step: algorithmic GB/s against the 6.5 TB/s HBM roof."""
+    print(f'{"kernel":44s} {"ms":>8s} {"GB/s":>8s}')
+
+    def rep(name, fn, byts):
+        ms = timeit(fn)
+        print(f'{name:44s} {ms:8.3f} {byts / ms / 1e6:8.0f}', flush=True)
+    for rows, C in [(262144, 56), (262144, 112), (786432, 28), (65536, 224), (16384, 448), (4096, 896), (1024, 896)]:
+        x = torch.randn(rows, C, device='cuda'); g = torch.randn(C, device='cuda'); b = torch.randn(C, device='cuda')
+        y = torch.empty_like(x); dy = torch.randn_like(x); dres = torch.randn_like(x); dx = torch.empty_like(x)
+        dg = torch.zeros(C, device='cuda'); db = torch.zeros(C, device='cuda')
+        _, mean, rstd = ops.layernorm_fwd(x, g, b, y)
+        rep(f'layernorm_fwd {rows}x{C}', lambda: ops.layernorm_fwd(x, g, b, y), 8 * rows * C)
+        rep(f'layernorm_bwd {rows}x{C}', lambda: ops.layernorm_bwd(dy, x, mean, rstd, g, dres, dg, db, dx), 16 * rows * C)
+        out = torch.zeros(C, device='cuda')
+        rep(f'colsum {rows}x{C}', lambda: ops.colsum(x, out), 4 * rows * C)
+        rs = torch.ones(16, device='cuda')
+        rep(f'scale_rows {rows}x{C}', lambda: ops.scale_rows(x, rs, rows // 16), 8 * rows * C)
+        del x, y, dy, dres, dx
+    for B, H, C in [(16, 128, 224), (16, 128, 448), (48, 128, 112), (16, 64, 896), (16, 32, 1792), (16, 16, 3584), (16, 8, 3584)]:
+        h1 = torch.randn(B * H * H, C, device='cuda'); w = torch.randn(C, 1, 3, 3, device='cuda'); bb = torch.randn(C, device='cuda')
+        n = B * H * H * C
+        rep(f'dwconv_fwd B{B} {H}x{H} C{C}', lambda: ops.dwconv_fwd(h1, w, bb, B, H, H, C), 12 * n)
+        du2 = torch.randn_like(h1); u1 = torch.randn_like(h1)
+        dw = torch.zeros_like(w); dbb = torch.zeros(C, device='cuda')
+        rep(f'dwconv_bwd B{B} {H}x{H} C{C}', lambda: ops.dwconv_bwd(du2, h1, u1, w, dw, dbb, B, H, H, C), 16 * n)
+        del h1, du2, u1
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
-    ap.add_argument('what', choices=['gemm', 'epi'])
+    ap.add_argument('what', choices=['gemm', 'epi', 'misc'])
     ap.add_argument('--backend', type=int, default=0)
     ap.add_argument('--only', default=None)
     ap.add_argument('--layouts', default='NT,NN,TN')
@@ -115,3 +144,5 @@ if __name__ == '__main__':
         bench_gemm(a.backend, a.only, a.layouts)
     if a.what == 'epi':
         bench_epi(a.backend)
+    if a.what == 'misc':
+        bench_misc()

@@ -21,6 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--batch', type=int, default=16)
     ap.add_argument('--top', type=int, default=60)
+    ap.add_argument('--gemm', action='store_true')
     a = ap.parse_args()
     ops = importlib.import_module(PKG + '.ops')
     synth = importlib.import_module(PKG + '.synth')
@@ -52,6 +53,15 @@ def main():
     print(f'sum of library-call times: {tot:.2f} ms')
     for n, (ms, c) in sorted(by_name.items(), key=lambda kv: -kv[1][0]):
         print(f'{ms:9.3f} ms {100 * ms / tot:5.1f}% {c:5d}  {n}')
+    if a.gemm:
+        print('--- every fa_gemm signature: ms, calls, TFLOP/s, GB/s (M N K lda ldb ldc tA tB)')
+        for (n, sig), (ms, c) in sorted(by_sig.items(), key=lambda kv: -kv[1][0]):
+            if n != 'fa_gemm':
+                continue
+            M, N, K = sig[0], sig[1], sig[2]
+            fl = 2.0 * M * N * K * c
+            by = 4.0 * (M * K + N * K + M * N) * c
+            print(f'{ms:9.3f} ms {c:4d}  {fl / ms / 1e9:7.1f} TF/s {by / ms / 1e6:7.0f} GB/s  {sig}')
     print('--- by signature (gemm: M N K lda ldb ldc tA tB)')
     for (n, sig), (ms, c) in sorted(by_sig.items(), key=lambda kv: -kv[1][0])[:a.top]:
         print(f'{ms:9.3f} ms {100 * ms / tot:5.1f}% {c:4d}  {n} {sig}')
