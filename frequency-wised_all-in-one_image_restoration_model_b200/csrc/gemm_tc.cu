@@ -24,6 +24,7 @@
 // the instruction cache (a fully generic, fully unrolled epilogue measured ~40 % "no instruction" stalls).
 // Every mbarrier wait is bounded: a protocol bug traps instead of hanging the GPU.
 #include <cuda.h>
+#include <stdlib.h>
 #include "freqair_internal.h"
 
 namespace {
@@ -38,6 +39,8 @@ constexpr int EPI_WARPS = 8;
 constexpr int EPI_WARP0 = 2 + SPLIT_WARPS;     // first epilogue warp (TMEM lane quarter = warp % 4)
 constexpr int NTHREADS = 32 * (2 + SPLIT_WARPS + EPI_WARPS);
 constexpr int A_BYTES = BM * BK * 4;
+constexpr int TMEM_A_COL0 = 256;    // a_tmem: ring of {A, A_lo} k-blocks (2 x 32 columns per stage) behind the two accumulators
+constexpr int MAX_TMEM_A_STAGES = 4;
 
 // epilogue flavours
 enum { EPI_PLAIN = 0,   // alpha, accumulate, split-K atomics                         (dX, dW)
@@ -119,6 +122,29 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 registers per thread -> 32 lanes x 32 columns of TMEM (thread = lane = A-tile row); completion via tc_wait_st()
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]),
+        "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]),
+        "f"(v[18]), "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]),
+        "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem: lane = row, column = k] . B[smem descriptor]
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
   asm volatile(
@@ -185,6 +211,7 @@ struct TcGeom {
   int64_t ldc;
   int k_chunk, splits, tiles_m, tiles_n;
   int a_mn, b_mn, x3, stages;
+  int a_tmem;    // x3 only: A and A_lo are staged in TMEM by the split warps (MMA reads only B from shared memory)
 };
 
 // compile-time activation: keeps the unrolled row loop straight-line (a run-time switch per element splits it into
@@ -277,11 +304,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int STAGES = g.stages;
-  const bool X3 = g.x3 != 0, A_MN = g.a_mn != 0, B_MN = g.b_mn != 0;
+  const bool X3 = g.x3 != 0, A_MN = g.a_mn != 0, B_MN = g.b_mn != 0, A_TMEM = g.a_tmem != 0;
   unsigned char* sA = smem;
   unsigned char* sB = sA + STAGES * A_BYTES;
-  unsigned char* sAlo = sB + STAGES * B_BYTES;                                // x3 only
-  unsigned char* sBlo = sAlo + (X3 ? STAGES * A_BYTES : 0);
+  unsigned char* sAlo = sB + STAGES * B_BYTES;                                // x3 only (absent with a_tmem)
+  unsigned char* sBlo = sAlo + ((X3 && !A_TMEM) ? STAGES * A_BYTES : 0);
   float* stg_all = reinterpret_cast<float*>(sBlo + (X3 ? STAGES * B_BYTES : 0));   // [EPI_WARPS][32][32]
   uint64_t* full = reinterpret_cast<uint64_t*>(stg_all + EPI_WARPS * 32 * 32);
   uint64_t* empty = full + MAX_STAGES;
@@ -302,8 +329,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
+  const uint32_t tmem_cols = A_TMEM ? 512u : (uint32_t)TMEM_COLS;
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -345,8 +373,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     if (lane == 0) {
       // ---------------------------------------------------------------- MMA issuer
       // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32, a=b=tf32, majors, N>>3, M>>4
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (((A_MN && !A_TMEM) ? 1u : 0u) << 15) |
+                             ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t astep = A_MN ? 1024u : 32u, bstep = B_MN ? 1024u : 32u;
       uint32_t it = 0, lu = 0;           // lu = accumulation units issued (a unit = up to KC_BLOCKS k-blocks of one tile)
       int s = 0;
@@ -369,7 +397,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t ad = make_desc(a0 + k * astep, A_MN), bd = make_desc(b0 + k * bstep, B_MN);
               const uint32_t acc0 = (kb > kb0 || k > 0) ? 1u : 0u;
-              if (X3) {
+              if (A_TMEM) {
+                const uint32_t at = tmem_base + TMEM_A_COL0 + s * 64 + k * UMMA_K;         // hi at +0, lo at +32
+                tc_mma_tf32_ts(d_tmem, at + 32, bd, idesc, acc0);                           // small terms first
+                tc_mma_tf32_ts(d_tmem, at, make_desc(bl0 + k * bstep, B_MN), idesc, 1u);
+                tc_mma_tf32_ts(d_tmem, at, bd, idesc, 1u);
+              } else if (X3) {
                 tc_mma_tf32(d_tmem, make_desc(al0 + k * astep, A_MN), bd, idesc, acc0);     // small terms first
                 tc_mma_tf32(d_tmem, ad, make_desc(bl0 + k * bstep, B_MN), idesc, 1u);
                 tc_mma_tf32(d_tmem, ad, bd, idesc, 1u);
@@ -396,20 +429,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
         const int nkb = (min(g.K, kbeg + g.k_chunk) - kbeg + BK - 1) / BK;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           mbar_wait(&full[s], (it / STAGES) & 1);
-          // all loads first, then all stores: a load-convert-store chain per element would serialise ~32 shared-memory
-          // round trips per stage (measured: the split stage, not the tensor pipe, then paces the whole kernel)
-          constexpr int NA = A_BYTES / 16 / (SPLIT_WARPS * 32), NB = B_BYTES / 16 / (SPLIT_WARPS * 32);
-          const uint32_t a = smem_u32(sA + s * A_BYTES) + st * 16, b = smem_u32(sB + s * B_BYTES) + st * 16;
-          const uint32_t al = smem_u32(sAlo + s * A_BYTES) + st * 16, bl = smem_u32(sBlo + s * B_BYTES) + st * 16;
-          float4 ra[NA], rb[NB];
+          constexpr int NB = B_BYTES / 16 / (SPLIT_WARPS * 32);
+          const uint32_t b = smem_u32(sB + s * B_BYTES) + st * 16, bl = smem_u32(sBlo + s * B_BYTES) + st * 16;
+          float4 rb[NB];
+          if (A_TMEM) {
+            // thread = A-tile row (= TMEM lane): gather the row's 32 k-values from the swizzled tile TMA wrote, store
+            // them and their lo parts into this stage's TMEM columns; the MMA then reads A without touching smem
+            const int q4 = warp & 3, r = q4 * 32 + lane;
+            const uint32_t a0 = smem_u32(sA + s * A_BYTES);
+            float av[32];
+            if (!A_MN) {
+              const uint32_t base = a0 + r * 128;
 #pragma unroll
-          for (int i = 0; i < NA; ++i) ra[i] = lds128(a + i * SPLIT_WARPS * 512);
+              for (int c = 0; c < 8; ++c) {
+                const float4 v = lds128(base + (((c ^ r) & 7) << 4));
+                av[4 * c] = v.x; av[4 * c + 1] = v.y; av[4 * c + 2] = v.z; av[4 * c + 3] = v.w;
+              }
+            } else {
+              const uint32_t base = a0 + (r >> 5) * 4096 + (r & 7) * 4;
+              const int cm = (r & 31) >> 3;
 #pragma unroll
-          for (int i = 0; i < NB; ++i) rb[i] = lds128(b + i * SPLIT_WARPS * 512);
+              for (int k = 0; k < 32; ++k) av[k] = lds32(base + k * 128 + (((cm ^ k) & 3) << 5));
+            }
 #pragma unroll
-          for (int i = 0; i < NA; ++i) sts128(al + i * SPLIT_WARPS * 512, lo4(ra[i]));
+            for (int i = 0; i < NB; ++i) rb[i] = lds128(b + i * SPLIT_WARPS * 512);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + TMEM_A_COL0 + s * 64;
+            tc_st32(taddr, av);
 #pragma unroll
-          for (int i = 0; i < NB; ++i) sts128(bl + i * SPLIT_WARPS * 512, lo4(rb[i]));
+            for (int k = 0; k < 32; ++k) av[k] = lo1(av[k]);
+            tc_st32(taddr + 32, av);
+#pragma unroll
+            for (int i = 0; i < NB; ++i) sts128(bl + i * SPLIT_WARPS * 512, lo4(rb[i]));
+            tc_wait_st();
+            tc_fence_before();
+          } else {
+            // all loads first, then all stores: a load-convert-store chain per element would serialise ~32 shared-memory
+            // round trips per stage (measured: the split stage, not the tensor pipe, then paces the whole kernel)
+            constexpr int NA = A_BYTES / 16 / (SPLIT_WARPS * 32);
+            const uint32_t a = smem_u32(sA + s * A_BYTES) + st * 16, al = smem_u32(sAlo + s * A_BYTES) + st * 16;
+            float4 ra[NA];
+#pragma unroll
+            for (int i = 0; i < NA; ++i) ra[i] = lds128(a + i * SPLIT_WARPS * 512);
+#pragma unroll
+            for (int i = 0; i < NB; ++i) rb[i] = lds128(b + i * SPLIT_WARPS * 512);
+#pragma unroll
+            for (int i = 0; i < NA; ++i) sts128(al + i * SPLIT_WARPS * 512, lo4(ra[i]));
+#pragma unroll
+            for (int i = 0; i < NB; ++i) sts128(bl + i * SPLIT_WARPS * 512, lo4(rb[i]));
+          }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to UMMA
           mbar_arrive(&ready[s]);
           if (++s == STAGES) s = 0;
@@ -511,7 +578,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
   }
 }
 
@@ -552,11 +619,12 @@ bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int
 template <int BN, int MODE>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, float* C, TcGeom g, const EpiTC& e, cudaStream_t st) {
   // one persistent CTA per SM; the operand ring takes what the 227 KB leave after the 32 KB epilogue transpose tiles
-  const int stage_bytes = (A_BYTES + BN * BK * 4) * (g.x3 ? 2 : 1);
+  const int stage_bytes = g.a_tmem ? (A_BYTES + 2 * BN * BK * 4) : (A_BYTES + BN * BK * 4) * (g.x3 ? 2 : 1);
   const int tail_bytes = EPI_WARPS * 32 * 32 * 4 + (3 * MAX_STAGES + 4) * 8 + 16;
   const int budget = 227 * 1024 - 1024 - tail_bytes;
   int stages = budget / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (g.a_tmem && stages > MAX_TMEM_A_STAGES) stages = MAX_TMEM_A_STAGES;
   g.stages = stages;
   const size_t smem = 1024 + (size_t)stages * stage_bytes + tail_bytes;
   auto kern = gemm_tc_kernel<BN, MODE>;
@@ -625,6 +693,8 @@ int fa_gemm_tc_launch(const float* A, const float* B, float* C, int M, int N, in
   memset(&g, 0, sizeof(g));
   g.M = M; g.N = N; g.K = K; g.ldc = ldc;
   g.a_mn = a_mn; g.b_mn = b_mn; g.x3 = single_pass ? 0 : 1;
+  static const bool atmem_env = [] { const char* e = getenv("FREQAIR_GEMM_ATMEM"); return !(e && e[0] == '0'); }();
+  g.a_tmem = (g.x3 && atmem_env) ? 1 : 0;
   g.tiles_m = (M + BM - 1) / BM;
   int bn = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 96 ? 96 : 128));
   int64_t tiles = (int64_t)g.tiles_m * ((N + bn - 1) / bn);
