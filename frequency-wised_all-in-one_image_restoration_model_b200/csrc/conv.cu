@@ -152,6 +152,167 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_strip_kernel(const float* __
   }
 }
 
+// ------------------------------------------------------------------ 3x3 conv to a few output channels (OutputProj)
+// tokens [B,H*W,C] -> NCHW image [B,CO,H*W] (+ bias + residual image), CO <= 4, C <= 128 (decoder_Uformer.py:476-499,
+// :1171).  A 1008-wide patch matrix for 3 output channels is 1 GB of pure traffic per direction at B=16; here a warp
+// owns a pixel, lane = channel quad with its 9 x CO weight float4s in registers, and the three dot products are warp
+// reductions: the feature map is read once (through L1 for the 9 taps) and nothing is materialised.
+// wk layout: [CO][(ky,kx,ci)] - the GEMM weight matrix of convs.conv_weight_matrix.
+template <int CO>
+__global__ void __launch_bounds__(256) conv3x3_out_fwd_kernel(const float* __restrict__ t, const float* __restrict__ wk,
+                                                              const float* __restrict__ bias,
+                                                              const float* __restrict__ ximg, float* __restrict__ out,
+                                                              int B, int H, int W, int C) {
+  const int lane = threadIdx.x & 31;
+  const int c = lane * 4;
+  const bool cok = c < C;
+  float4 w[CO][9];
+#pragma unroll
+  for (int co = 0; co < CO; ++co)
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) w[co][tp] = cok ? ld4(wk + ((int64_t)co * 9 + tp) * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int HW = H * W;
+  const int64_t total = (int64_t)B * HW;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t p = warp; p < total; p += nwarps) {
+    const int b = (int)(p / HW), pix = (int)(p % HW), y = pix / W, x = pix % W;
+    float acc[CO];
+#pragma unroll
+    for (int co = 0; co < CO; ++co) acc[co] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x + kx - 1;
+        if (xx < 0 || xx >= W || !cok) continue;
+        const float4 v = ld4(t + (((int64_t)b * H + yy) * W + xx) * C + c);
+#pragma unroll
+        for (int co = 0; co < CO; ++co) {
+          const float4 ww = w[co][ky * 3 + kx];
+          acc[co] = fmaf(v.x, ww.x, fmaf(v.y, ww.y, fmaf(v.z, ww.z, fmaf(v.w, ww.w, acc[co]))));
+        }
+      }
+    }
+#pragma unroll
+    for (int co = 0; co < CO; ++co) {
+      const float sum = warp_sum(acc[co]);
+      if (lane == co) {
+        const int64_t o = ((int64_t)b * CO + co) * HW + pix;
+        out[o] = sum + (bias ? bias[co] : 0.f) + (ximg ? ximg[o] : 0.f);
+      }
+    }
+  }
+}
+
+// dt[p][ci] = sum_tap sum_co dout[p - delta(tap)][co] * w[co][tap][ci]
+template <int CO>
+__global__ void __launch_bounds__(256) conv3x3_out_bwd_data_kernel(const float* __restrict__ dout,
+                                                                   const float* __restrict__ wk, float* __restrict__ dt,
+                                                                   int B, int H, int W, int C) {
+  const int lane = threadIdx.x & 31;
+  const int c = lane * 4;
+  const bool cok = c < C;
+  float4 w[CO][9];
+#pragma unroll
+  for (int co = 0; co < CO; ++co)
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) w[co][tp] = cok ? ld4(wk + ((int64_t)co * 9 + tp) * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int HW = H * W;
+  const int64_t total = (int64_t)B * HW;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t p = warp; p < total; p += nwarps) {
+    const int b = (int)(p / HW), pix = (int)(p % HW), y = pix / W, x = pix % W;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y - (ky - 1);
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x - (kx - 1);
+        if (xx < 0 || xx >= W) continue;
+#pragma unroll
+        for (int co = 0; co < CO; ++co) {
+          const float g = __ldg(dout + ((int64_t)b * CO + co) * HW + yy * W + xx);       // warp-uniform address
+          const float4 ww = w[co][ky * 3 + kx];
+          acc = fma4(make_float4(g, g, g, g), ww, acc);
+        }
+      }
+    }
+    if (cok) st4(dt + p * C + c, acc);
+  }
+}
+
+// dW[co][tap][ci] += sum_p dout[p][co] * t[p + delta(tap)][ci];  db[co] += sum_p dout[p][co]
+template <int CO>
+__global__ void __launch_bounds__(256) conv3x3_out_bwd_weight_kernel(const float* __restrict__ t,
+                                                                     const float* __restrict__ dout,
+                                                                     float* __restrict__ dW, float* __restrict__ db,
+                                                                     int B, int H, int W, int C) {
+  __shared__ float red[32][CO * 9 * 4 + 1];
+  __shared__ float redb[CO];
+  const int lane = threadIdx.x & 31;
+  const int c = lane * 4;
+  const bool cok = c < C;
+  for (int i = threadIdx.x; i < 32 * (CO * 9 * 4 + 1); i += blockDim.x) (&red[0][0])[i] = 0.f;
+  if (threadIdx.x < CO) redb[threadIdx.x] = 0.f;
+  __syncthreads();
+  float4 acc[CO][9];
+  float accb[CO];
+#pragma unroll
+  for (int co = 0; co < CO; ++co) {
+    accb[co] = 0.f;
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) acc[co][tp] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int HW = H * W;
+  const int64_t total = (int64_t)B * HW;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t p = warp; p < total; p += nwarps) {
+    const int b = (int)(p / HW), pix = (int)(p % HW), y = pix / W, x = pix % W;
+    float g[CO];
+#pragma unroll
+    for (int co = 0; co < CO; ++co) { g[co] = __ldg(dout + ((int64_t)b * CO + co) * HW + pix); accb[co] += g[co]; }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x + kx - 1;
+        if (xx < 0 || xx >= W || !cok) continue;
+        const float4 v = ld4(t + (((int64_t)b * H + yy) * W + xx) * C + c);
+#pragma unroll
+        for (int co = 0; co < CO; ++co) acc[co][ky * 3 + kx] = fma4(make_float4(g[co], g[co], g[co], g[co]), v, acc[co][ky * 3 + kx]);
+      }
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < CO; ++co)
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) {
+      float* r = &red[lane][(co * 9 + tp) * 4];
+      atomicAdd(r + 0, acc[co][tp].x); atomicAdd(r + 1, acc[co][tp].y);
+      atomicAdd(r + 2, acc[co][tp].z); atomicAdd(r + 3, acc[co][tp].w);
+    }
+  if (lane == 0) {
+#pragma unroll
+    for (int co = 0; co < CO; ++co) atomicAdd(&redb[co], accb[co]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * CO * 9 * 4; i += blockDim.x) {
+    const int l = i / (CO * 9 * 4), v = i % (CO * 9 * 4);
+    const int cc = l * 4 + (v & 3), ct = v >> 2;              // ct = co*9 + tap
+    if (cc < C) atomicAdd(&dW[(int64_t)ct * C + cc], red[l][v]);
+  }
+  if (db && threadIdx.x < CO) atomicAdd(&db[threadIdx.x], redb[threadIdx.x]);
+}
+
 // ------------------------------------------------------------------ im2col / col2im
 template <bool NCHW>
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int B, int H,
@@ -291,6 +452,20 @@ inline int ew_grid(int64_t total) {
 
 }  // namespace
 
+template <int CO>
+static int conv_out_launch(int what, const float* t, const float* wk, const float* bias, const float* ximg, float* out,
+                           const float* dout, float* dt, float* dW, float* db, int B, int H, int W, int C,
+                           cudaStream_t st) {
+  const int64_t pixels = (int64_t)B * H * W;
+  int64_t blocks = (pixels + 63) / 64;                       // >= 8 pixels per warp
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  const int grid = (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+  if (what == 0) conv3x3_out_fwd_kernel<CO><<<grid, 256, 0, st>>>(t, wk, bias, ximg, out, B, H, W, C);
+  else if (what == 1) conv3x3_out_bwd_data_kernel<CO><<<grid, 256, 0, st>>>(dout, wk, dt, B, H, W, C);
+  else conv3x3_out_bwd_weight_kernel<CO><<<grid < 2 * kNumSMs ? grid : 2 * kNumSMs, 256, 0, st>>>(t, dout, dW, db, B, H, W, C);
+  return FA_OK;
+}
+
 extern "C" {
 
 static StripGeom make_strips(int B, int H, int W, int C, int& nstrips, dim3& grid) {
@@ -338,6 +513,45 @@ int fa_dwconv3x3_bwd(const float* du2, const float* h1, const float* u1, const f
     fa_count_launch(FA_K_DWCONV);
     dwconv_wgrad_strip_kernel<<<grid, dim3(32, 8), 0, st>>>(du2, h1, dw, db, g, nstrips);
     FA_LAUNCH_CHECK("fa_dwconv3x3_bwd(weight)");
+  }
+  return FA_OK;
+}
+
+int fa_conv3x3_out_fwd(const float* t, const float* wk, const float* bias, const float* ximg, float* out, int B, int H,
+                       int W, int C, int Co, fa_stream_t stream) {
+  FA_REQUIRE(t && wk && out, "fa_conv3x3_out_fwd: null pointer");
+  FA_REQUIRE(C % 4 == 0 && C <= 128 && Co >= 1 && Co <= 4, "fa_conv3x3_out_fwd: C=%d (mult of 4, <=128), Co=%d (1..4)", C, Co);
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_IM2COL, st);
+  if ((int64_t)B * H * W == 0) return FA_OK;
+  switch (Co) {
+    case 1: conv_out_launch<1>(0, t, wk, bias, ximg, out, nullptr, nullptr, nullptr, nullptr, B, H, W, C, st); break;
+    case 2: conv_out_launch<2>(0, t, wk, bias, ximg, out, nullptr, nullptr, nullptr, nullptr, B, H, W, C, st); break;
+    case 3: conv_out_launch<3>(0, t, wk, bias, ximg, out, nullptr, nullptr, nullptr, nullptr, B, H, W, C, st); break;
+    default: conv_out_launch<4>(0, t, wk, bias, ximg, out, nullptr, nullptr, nullptr, nullptr, B, H, W, C, st); break;
+  }
+  FA_LAUNCH_CHECK("fa_conv3x3_out_fwd");
+  return FA_OK;
+}
+
+int fa_conv3x3_out_bwd(const float* t, const float* wk, const float* dout, float* dt, float* dW, float* db, int B, int H,
+                       int W, int C, int Co, fa_stream_t stream) {
+  FA_REQUIRE(t && wk && dout, "fa_conv3x3_out_bwd: null pointer");
+  FA_REQUIRE(C % 4 == 0 && C <= 128 && Co >= 1 && Co <= 4, "fa_conv3x3_out_bwd: C=%d (mult of 4, <=128), Co=%d (1..4)", C, Co);
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_IM2COL, st);
+  if ((int64_t)B * H * W == 0) return FA_OK;
+  for (int what = 1; what <= 2; ++what) {
+    if (what == 1 && !dt) continue;
+    if (what == 2 && !dW) continue;
+    if (what == 2) fa_count_launch(FA_K_IM2COL);
+    switch (Co) {
+      case 1: conv_out_launch<1>(what, t, wk, nullptr, nullptr, nullptr, dout, dt, dW, db, B, H, W, C, st); break;
+      case 2: conv_out_launch<2>(what, t, wk, nullptr, nullptr, nullptr, dout, dt, dW, db, B, H, W, C, st); break;
+      case 3: conv_out_launch<3>(what, t, wk, nullptr, nullptr, nullptr, dout, dt, dW, db, B, H, W, C, st); break;
+      default: conv_out_launch<4>(what, t, wk, nullptr, nullptr, nullptr, dout, dt, dW, db, B, H, W, C, st); break;
+    }
+    FA_LAUNCH_CHECK("fa_conv3x3_out_bwd");
   }
   return FA_OK;
 }

@@ -219,24 +219,37 @@ class UpsampleCatFn(torch.autograd.Function):
 
 class OutputProjFn(torch.autograd.Function):
     """Conv2d 3x3 s1 p1 tokens -> NCHW image, plus the global residual x + y
-    (OutputProj decoder_Uformer.py:476-499 and :1171)."""
+    (OutputProj decoder_Uformer.py:476-499 and :1171).  Direct kernels: the 9*C-wide patch matrix of this layer would be
+    1 GB per direction at B=16 for three output channels."""
 
     @staticmethod
     def forward(ctx, t, wk, b, ximg, H, W):
         B, _, C = t.shape
-        col = ops.im2col(t.contiguous(), B, H, W, C, 3, 3, 1, 1)
         Co = wk.shape[0]
-        y = torch.empty(B * H * W, Co, device=t.device, dtype=torch.float32)
-        ops.gemm(col, wk, y, bias=b)
-        out = ops.tokens_to_nchw(y, ximg.contiguous().view(B, Co, H * W) if ximg is not None else None, B, H * W, Co)
+        tc, wkc = t.contiguous(), wk.contiguous()
+        if C % 4 == 0 and C <= 128 and Co <= 4:
+            out = ops.conv3x3_out_fwd(tc, wkc, b, ximg.contiguous() if ximg is not None else None, B, H, W, C, Co)
+            ctx.direct = True
+            ctx.save_for_backward(tc, wkc)
+        else:
+            col = ops.im2col(tc, B, H, W, C, 3, 3, 1, 1)
+            y = torch.empty(B * H * W, Co, device=t.device, dtype=torch.float32)
+            ops.gemm(col, wkc, y, bias=b)
+            out = ops.tokens_to_nchw(y, ximg.contiguous().view(B, Co, H * W) if ximg is not None else None, B, H * W, Co)
+            ctx.direct = False
+            ctx.save_for_backward(col, wkc)
         ctx.geom = (B, H, W, C, Co)
-        ctx.save_for_backward(col, wk)
         return out.view(B, Co, H, W)
 
     @staticmethod
     def backward(ctx, dout):
-        col, wk = ctx.saved_tensors
         B, H, W, C, Co = ctx.geom
+        dres = dout if ctx.needs_input_grad[3] else None
+        if ctx.direct:
+            tc, wk = ctx.saved_tensors
+            dt, dW, db = ops.conv3x3_out_bwd(tc, wk, dout.contiguous(), B, H, W, C, Co, want_dt=ctx.needs_input_grad[0])
+            return dt, dW, db, dres, None, None
+        col, wk = ctx.saved_tensors
         g = ops.nchw_to_tokens(dout.contiguous(), B, H * W, Co).view(-1, Co)
         dW, db = _z(wk), torch.empty(Co, device=g.device)
         ops.colsum(g, db)
@@ -244,7 +257,7 @@ class OutputProjFn(torch.autograd.Function):
         dcol = torch.empty_like(col)
         ops.gemm(g, wk, dcol, transB=False)
         dt = ops.col2im(dcol, B, H, W, C, 3, 3, 1, 1)
-        return dt, dW, db, (dout if ctx.needs_input_grad[3] else None), None, None
+        return dt, dW, db, dres, None, None
 
 
 def conv_weight_matrix(w):

@@ -304,6 +304,22 @@ def col2im(col, B, H, W, C, kh, kw, stride, pad):
     return dx
 
 
+def conv3x3_out_fwd(t, wk, bias, ximg, B, H, W, C, Co):
+    _f32(t, wk, bias, ximg)
+    out = torch.empty(B, Co, H * W, device=t.device, dtype=torch.float32)
+    _call('fa_conv3x3_out_fwd', _p(t), _p(wk), _p(bias), _p(ximg), _p(out), B, H, W, C, Co, _stream())
+    return out
+
+
+def conv3x3_out_bwd(t, wk, dout, B, H, W, C, Co, want_dt=True):
+    _f32(t, wk, dout)
+    dt = torch.empty(B, H * W, C, device=t.device, dtype=torch.float32) if want_dt else None
+    dW = torch.zeros(Co, 9 * C, device=t.device, dtype=torch.float32)
+    db = torch.zeros(Co, device=t.device, dtype=torch.float32)
+    _call('fa_conv3x3_out_bwd', _p(t), _p(wk), _p(dout), _p(dt), _p(dW), _p(db), B, H, W, C, Co, _stream())
+    return dt, dW, db
+
+
 def pixel_shuffle2_fwd(g, y, B, H, W, Co):
     _f32(g)
     _call('fa_pixel_shuffle2_fwd', _p(g), _p(y), y.stride(0), B, H, W, Co, _stream())

@@ -165,6 +165,14 @@ int fa_im2col(const float* x, float* col, int B, int H, int W, int C, int kh, in
               fa_stream_t stream);
 int fa_col2im(const float* col, float* dx, int B, int H, int W, int C, int kh, int kw, int stride, int pad,
               fa_stream_t stream);
+/* 3x3 s1 p1 conv from tokens [B,H*W,C] to a FEW output channels, written as an NCHW image [B,Co,H*W] with the bias and
+ * an optional residual image added: OutputProj + the network's global skip (decoder_Uformer.py:476-499, :1171).
+ * C % 4 == 0, C <= 128, Co <= 4.  wk = [Co][(ky,kx,ci)].  No patch matrix is built (it would be 9*C/Co times the output).
+ * bwd: dt [B,H*W,C] (may be NULL), dW [Co][(ky,kx,ci)] and db [Co] ACCUMULATE (caller zero-fills; either may be NULL). */
+int fa_conv3x3_out_fwd(const float* t, const float* wk, const float* bias, const float* ximg, float* out, int B, int H,
+                       int W, int C, int Co, fa_stream_t stream);
+int fa_conv3x3_out_bwd(const float* t, const float* wk, const float* dout, float* dt, float* dW, float* db, int B, int H,
+                       int W, int C, int Co, fa_stream_t stream);
 /* ConvTranspose2d k2 s2 scatter (decoder_Uformer.py:438): y[b][2y+ky][2x+kx][co] = g[(b,y,x)][(ky,kx,co)];
  * y has row stride ldy (writes the left half of the skip-concat buffer, :1162). bwd is the gather. */
 int fa_pixel_shuffle2_fwd(const float* g, float* y, int64_t ldy, int B, int H, int W, int Co, fa_stream_t stream);

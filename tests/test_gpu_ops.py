@@ -173,6 +173,26 @@ def test_im2col_col2im(ops, C, k, s, p):
     close(dx, dref, 1e-5, 'col2im')
 
 
+@pytest.mark.parametrize('C,Co,H,W', [(112, 3, 16, 24), (28, 3, 8, 8), (56, 1, 9, 7)])
+def test_conv3x3_out(ops, C, Co, H, W):
+    """OutputProj direct conv (tokens -> NCHW image + residual) and its backward vs F.conv2d."""
+    B = 2
+    t = gen(B, H * W, C).requires_grad_(True)
+    w = (gen(Co, C, 3, 3, seed=1) * 0.1).requires_grad_(True)
+    b = gen(Co, seed=2).requires_grad_(True)
+    ximg = gen(B, Co, H, W, seed=3)
+    dout = gen(B, Co, H, W, seed=4)
+    ref = F.conv2d(t.view(B, H, W, C).permute(0, 3, 1, 2), w, b, padding=1) + ximg
+    ref.backward(dout)
+    wk = w.detach().permute(0, 2, 3, 1).reshape(Co, -1).contiguous()
+    out = ops.conv3x3_out_fwd(dev(t.detach()), dev(wk), dev(b.detach()), dev(ximg), B, H, W, C, Co)
+    close(out.view(B, Co, H, W), ref, 1e-5, 'conv3x3_out fwd')
+    dt, dW, db = ops.conv3x3_out_bwd(dev(t.detach()), dev(wk), dev(dout), B, H, W, C, Co)
+    close(dt, t.grad, 1e-5, 'conv3x3_out dt')
+    close(dW.view(Co, 3, 3, C).permute(0, 3, 1, 2), w.grad, 2e-5, 'conv3x3_out dW')
+    close(db, b.grad, 2e-5, 'conv3x3_out db')
+
+
 def test_pixel_shuffle_and_layout(ops):
     B, H, W, Ci, Co = 2, 4, 4, 16, 8
     x = gen(B, H * W, Ci)
