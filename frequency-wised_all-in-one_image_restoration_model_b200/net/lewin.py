@@ -16,6 +16,51 @@ def _z(t):
     return torch.zeros_like(t)
 
 
+# Direct gradient sinks.  trainer.TrainStep makes every parameter's .grad a view of one flat, per-step-zeroed buffer; the
+# block-level backward then ACCUMULATES weight / bias / norm gradients straight into those views (GEMM epilogue
+# accumulate, atomics) and hands autograd ``None``, which removes ~2 000 AccumulateGrad add kernels and as many
+# zero-filled temporaries per step.  GRAD_READY(param) tells the bucketed all-reduce that a gradient is complete
+# (the post-accumulate hooks no longer fire for these parameters).  With DIRECT_GRAD off, or for a parameter without
+# a .grad buffer, gradients are returned to autograd as usual (what the parity tests exercise).
+DIRECT_GRAD = False
+GRAD_READY = None
+
+
+def _sink(p):
+    if DIRECT_GRAD and p is not None and p.requires_grad and p.grad is not None and p.grad.is_contiguous():
+        return p.grad
+    return None
+
+
+def _wbuf(p):
+    """(buffer to accumulate a weight-like gradient into, value to return to autograd)"""
+    sk = _sink(p)
+    if sk is not None:
+        return sk, None
+    z = torch.zeros_like(p)
+    return z, z
+
+
+def _bias_grad(g, p):
+    """Column sums of g into the bias gradient; returns the value for autograd (None when written in place)."""
+    if p is None:
+        return None
+    sk = _sink(p)
+    if sk is not None:
+        ops.colsum(g, sk, accumulate=True)
+        return None
+    db = torch.empty_like(p)
+    ops.colsum(g, db)
+    return db
+
+
+def _ready(*ps):
+    if GRAD_READY is not None:
+        for p in ps:
+            if p is not None and _sink(p) is not None:
+                GRAD_READY(p)
+
+
 def linear_grads(g, x, W, dW, db, want_dx=True, dx=None, accumulate_dx=False):
     """Backward of y = x W^T + b for 2-D row-major g [T,N], x [T,K], W [N,K]: fills dW (+=), db, returns dx."""
     if db is not None:
@@ -27,6 +72,20 @@ def linear_grads(g, x, W, dW, db, want_dx=True, dx=None, accumulate_dx=False):
         dx = torch.empty_like(x)
     ops.gemm(g, W, dx, transB=False, accumulate=accumulate_dx)
     return dx
+
+
+def linear_param_grads(g, x, W, b, want_dx=True, dx=None, accumulate_dx=False):
+    """linear_grads with the parameter gradients routed through the sinks: returns (dx, dW_ret, db_ret)."""
+    db_ret = _bias_grad(g, b)
+    dW, dW_ret = _wbuf(W)
+    ops.gemm(g, x, dW, transA=True, transB=False, accumulate=True)
+    _ready(W, b)
+    if not want_dx:
+        return None, dW_ret, db_ret
+    if dx is None:
+        dx = torch.empty_like(x)
+    ops.gemm(g, W, dx, transB=False, accumulate=accumulate_dx)
+    return dx, dW_ret, db_ret
 
 
 # ----------------------------------------------------------------------------- LeFF
@@ -44,18 +103,20 @@ def leff_fwd(xn2, w1, b1, wdw, bdw, w2, b2, B, H, W, residual, dp_scale, save):
     return out
 
 
-def leff_bwd(gs, sv, xn2, w1, wdw, w2, B, H, W):
-    """gs: gradient wrt the LeFF output (DropPath scale already applied). Returns dxn2 and param grads."""
-    dW2, db2 = _z(w2), torch.empty(w2.shape[0], device=gs.device)
-    ops.colsum(gs, db2)
+def leff_bwd(gs, sv, xn2, w1, b1, wdw, bdw, w2, b2, B, H, W):
+    """gs: gradient wrt the LeFF output (DropPath scale already applied). Returns dxn2 and the parameter gradients
+    (None where they were accumulated straight into the parameters' .grad buffers)."""
+    db2 = _bias_grad(gs, b2)
+    dW2, dW2r = _wbuf(w2)
     ops.gemm(gs, sv['h2'], dW2, transA=True, transB=False, accumulate=True)
     du2 = torch.empty_like(sv['u2'])
     ops.gemm(gs, w2, du2, transB=False, aux=sv['u2'], aux_act=ops.ACT_GELU)
-    dwdw, dbdw = _z(wdw), torch.zeros(wdw.shape[0], device=gs.device)
+    dwdw, dwdwr = _wbuf(wdw)
+    dbdw, dbdwr = _wbuf(bdw)
     du1 = ops.dwconv_bwd(du2, sv['h1'], sv['u1'], wdw, dwdw, dbdw, B, H, W, wdw.shape[0])
-    dW1, db1 = _z(w1), torch.empty(w1.shape[0], device=gs.device)
-    dxn2 = linear_grads(du1, xn2, w1, dW1, db1)
-    return dxn2, (dW1, db1, dwdw, dbdw, dW2, db2)
+    _ready(w2, b2, wdw, bdw)
+    dxn2, dW1r, db1r = linear_param_grads(du1, xn2, w1, b1)
+    return dxn2, (dW1r, db1r, dwdwr, dbdwr, dW2r, db2)
 
 
 class DecoderBlockFn(torch.autograd.Function):
@@ -84,6 +145,7 @@ class DecoderBlockFn(torch.autograd.Function):
         x2 = leff_fwd(xn2, w1, b1, wdw, bdw, w2, b2, B, H, W, x1, dp_m, sv)
         ctx.cfg = cfg
         ctx.has = (coef is not None, dp_a is not None, dp_m is not None)
+        ctx.params = (n1w, n1b, table, wq, bq, wkv, bkv, wp, bp, n2w, n2b, w1, b1, wdw, bdw, w2, b2)
         ctx.save_for_backward(x2d, mean1, rstd1, xn, qkv, o, x1, mean2, rstd2, xn2, sv['u1'], sv['h1'], sv['u2'],
                               sv['h2'], coef, dp_a, dp_m, n1w, table, wq, wkv, wp, n2w, w1, wdw, w2)
         return x2.view(B, H * W, C)
@@ -92,30 +154,36 @@ class DecoderBlockFn(torch.autograd.Function):
     def backward(ctx, dx2):
         (x2d, mean1, rstd1, xn, qkv, o, x1, mean2, rstd2, xn2, u1, h1, u2, h2, coef, dp_a, dp_m, n1w, table, wq, wkv,
          wp, n2w, w1, wdw, w2) = ctx.saved_tensors
+        (P_n1w, P_n1b, P_table, P_wq, P_bq, P_wkv, P_bkv, P_wp, P_bp, P_n2w, P_n2b, P_w1, P_b1, P_wdw, P_bdw, P_w2,
+         P_b2) = ctx.params
         B, H, W, heads, shift, bob, nbands = ctx.cfg
         T, C = x2d.shape
         hd = C // heads
         g = dx2.reshape(T, C).contiguous()
         gs = ops.scale_rows(g, dp_m, H * W)
-        dxn2, (dW1, db1, dwdw, dbdw, dW2, db2) = leff_bwd(gs, dict(u1=u1, h1=h1, u2=u2, h2=h2), xn2, w1, wdw, w2, B, H, W)
-        dn2w, dn2b = _z(n2w), _z(n2w)
+        dxn2, (dW1, db1, dwdw, dbdw, dW2, db2) = leff_bwd(gs, dict(u1=u1, h1=h1, u2=u2, h2=h2), xn2, P_w1, P_b1, P_wdw,
+                                                         P_bdw, P_w2, P_b2, B, H, W)
+        dn2w, dn2wr = _wbuf(P_n2w)
+        dn2b, dn2br = _wbuf(P_n2b)
         g1 = ops.layernorm_bwd(dxn2, x1, mean2, rstd2, n2w, g, dn2w, dn2b)
+        _ready(P_n2w, P_n2b)
         gs1 = ops.scale_rows(g1, dp_a, H * W)
-        dWp, dbp = _z(wp), torch.empty(C, device=g.device)
-        do = linear_grads(gs1, o, wp, dWp, dbp)
+        do, dWp, dbp = linear_param_grads(gs1, o, P_wp, P_bp)
         dq = torch.empty(T, C, device=g.device)
         dkv = torch.empty(T, 2 * C, device=g.device)
-        dtable = _z(table)
+        dtable, dtabler = _wbuf(P_table)
         dcoef = _z(coef) if coef is not None else None
         ops.win_attn_bwd(qkv[:, :C], qkv[:, C:], do, dq, dkv, B, H, W, heads, hd, shift, hd ** -0.5, table, dtable, coef,
                          heads, dcoef, bob, nbands)
-        dWq, dbq, dWkv, dbkv = _z(wq), torch.empty(C, device=g.device), _z(wkv), torch.empty(2 * C, device=g.device)
-        dxn = linear_grads(dq, xn, wq, dWq, dbq)
-        linear_grads(dkv, xn, wkv, dWkv, dbkv, dx=dxn, accumulate_dx=True)
-        dn1w, dn1b = _z(n1w), _z(n1w)
+        _ready(P_table)
+        dxn, dWq, dbq = linear_param_grads(dq, xn, P_wq, P_bq)
+        _, dWkv, dbkv = linear_param_grads(dkv, xn, P_wkv, P_bkv, dx=dxn, accumulate_dx=True)
+        dn1w, dn1wr = _wbuf(P_n1w)
+        dn1b, dn1br = _wbuf(P_n1b)
         dx = ops.layernorm_bwd(dxn, x2d, mean1, rstd1, n1w, g1, dn1w, dn1b)
-        return (None, dx.view(B, H * W, C), dcoef, None, None, dn1w, dn1b, dtable, dWq, dbq, dWkv, dbkv, dWp, dbp, dn2w,
-                dn2b, dW1, db1, dwdw, dbdw, dW2, db2)
+        _ready(P_n1w, P_n1b)
+        return (None, dx.view(B, H * W, C), dcoef, None, None, dn1wr, dn1br, dtabler, dWq, dbq, dWkv, dbkv, dWp, dbp,
+                dn2wr, dn2br, dW1, db1, dwdw, dbdw, dW2, db2)
 
 
 class EncoderBlockFn(torch.autograd.Function):
@@ -158,6 +226,8 @@ class EncoderBlockFn(torch.autograd.Function):
         sv = {}
         x2 = leff_fwd(xn2, w1, b1, wdw, bdw, w2, b2, LB, H, W, x1, dp_m, sv)
         ctx.cfg = cfg
+        ctx.params = (n1w, n1b, wqA, bqA, wkvA, bkvA, wpA, bpA, wqB, bqB, wkvB, bkvB, wpB, bpB, n2w, n2b, w1, b1, wdw,
+                      bdw, w2, b2)
         ctx.save_for_backward(x2d, mean1, rstd1, xn, qkvA, oA, yA, qkvB, oB, x1, mean2, rstd2, xn2, sv['u1'], sv['h1'],
                               sv['u2'], sv['h2'], dp_a, dp_m, n1w, tabA, wqA, wkvA, wpA, tabB, wqB, wkvB, wpB, n2w, w1,
                               wdw, w2)
@@ -167,6 +237,8 @@ class EncoderBlockFn(torch.autograd.Function):
     def backward(ctx, dx2):
         (x2d, mean1, rstd1, xn, qkvA, oA, yA, qkvB, oB, x1, mean2, rstd2, xn2, u1, h1, u2, h2, dp_a, dp_m, n1w, tabA,
          wqA, wkvA, wpA, tabB, wqB, wkvB, wpB, n2w, w1, wdw, w2) = ctx.saved_tensors
+        (P_n1w, P_n1b, P_wqA, P_bqA, P_wkvA, P_bkvA, P_wpA, P_bpA, P_wqB, P_bqB, P_wkvB, P_bkvB, P_wpB, P_bpB, P_n2w,
+         P_n2b, P_w1, P_b1, P_wdw, P_bdw, P_w2, P_b2) = ctx.params
         L, B, H, W, heads, shift, msa = ctx.cfg
         T, C = x2d.shape
         LB = T // (H * W)
@@ -175,41 +247,41 @@ class EncoderBlockFn(torch.autograd.Function):
         dev = x2d.device
         g = dx2.reshape(T, C).contiguous()
         gs = ops.scale_rows(g, dp_m, H * W)
-        dxn2, (dW1, db1, dwdw, dbdw, dW2, db2) = leff_bwd(gs, dict(u1=u1, h1=h1, u2=u2, h2=h2), xn2, w1, wdw, w2, LB, H, W)
-        dn2w, dn2b = _z(n2w), _z(n2w)
+        dxn2, (dW1, db1, dwdw, dbdw, dW2, db2) = leff_bwd(gs, dict(u1=u1, h1=h1, u2=u2, h2=h2), xn2, P_w1, P_b1, P_wdw,
+                                                         P_bdw, P_w2, P_b2, LB, H, W)
+        dn2w, dn2wr = _wbuf(P_n2w)
+        dn2b, dn2br = _wbuf(P_n2b)
         g1 = ops.layernorm_bwd(dxn2, x1, mean2, rstd2, n2w, g, dn2w, dn2b)
+        _ready(P_n2w, P_n2b)
         gs1 = ops.scale_rows(g1, dp_a, H * W)
         dq = torch.empty(T, C, device=dev)
         dkv = torch.empty(T, 2 * C, device=dev)
         gB = [None] * 7
         if msa == 'origin':
-            dWpA, dbpA = _z(wpA), torch.empty(C, device=dev)
-            doA = linear_grads(gs1, oA, wpA, dWpA, dbpA)
+            doA, dWpA, dbpA = linear_param_grads(gs1, oA, P_wpA, P_bpA)
             dtabA = _z(tabA)
             ops.win_attn_bwd(qkvA[:, :C], qkvA[:, C:], doA, dq, dkv, LB, H, W, heads, hd, shift, scale, tabA, dtabA, None,
                              heads, None, None, 0)
         else:
-            dWpB, dbpB = _z(wpB), torch.empty(C, device=dev)
-            doB = linear_grads(gs1, oB, wpB, dWpB, dbpB)
+            doB, dWpB, dbpB = linear_param_grads(gs1, oB, P_wpB, P_bpB)
             dtabB = _z(tabB)
             ops.joint_attn_bwd(qkvB[:, :C], qkvB[:, C:], doB, dq, dkv, L, B, H, W, heads, hd, shift, scale, tabB, dtabB, 1)
-            dWqB, dbqB, dWkvB, dbkvB = _z(wqB), torch.empty(C, device=dev), _z(wkvB), torch.empty(2 * C, device=dev)
-            dyA = linear_grads(dq, yA, wqB, dWqB, dbqB)
-            linear_grads(dkv, yA, wkvB, dWkvB, dbkvB, dx=dyA, accumulate_dx=True)
+            dyA, dWqB, dbqB = linear_param_grads(dq, yA, P_wqB, P_bqB)
+            _, dWkvB, dbkvB = linear_param_grads(dkv, yA, P_wkvB, P_bkvB, dx=dyA, accumulate_dx=True)
             gB = [dtabB, dWqB, dbqB, dWkvB, dbkvB, dWpB, dbpB]
-            dWpA, dbpA = _z(wpA), torch.empty(C, device=dev)
-            doA = linear_grads(dyA, oA, wpA, dWpA, dbpA)
+            doA, dWpA, dbpA = linear_param_grads(dyA, oA, P_wpA, P_bpA)
             dtabA = _z(tabA)
             dq = torch.empty(T, C, device=dev)
             dkv = torch.empty(T, 2 * C, device=dev)
             ops.joint_attn_bwd(qkvA[:, :C], qkvA[:, C:], doA, dq, dkv, L, B, H, W, heads, hd, shift, scale, tabA, dtabA, 0)
-        dWqA, dbqA, dWkvA, dbkvA = _z(wqA), torch.empty(C, device=dev), _z(wkvA), torch.empty(2 * C, device=dev)
-        dxn = linear_grads(dq, xn, wqA, dWqA, dbqA)
-        linear_grads(dkv, xn, wkvA, dWkvA, dbkvA, dx=dxn, accumulate_dx=True)
-        dn1w, dn1b = _z(n1w), _z(n1w)
+        dxn, dWqA, dbqA = linear_param_grads(dq, xn, P_wqA, P_bqA)
+        _, dWkvA, dbkvA = linear_param_grads(dkv, xn, P_wkvA, P_bkvA, dx=dxn, accumulate_dx=True)
+        dn1w, dn1wr = _wbuf(P_n1w)
+        dn1b, dn1br = _wbuf(P_n1b)
         dx = ops.layernorm_bwd(dxn, x2d, mean1, rstd1, n1w, g1, dn1w, dn1b)
-        return (None, dx.view(LB, H * W, C), None, None, dn1w, dn1b, dtabA, dWqA, dbqA, dWkvA, dbkvA, dWpA, dbpA, *gB,
-                dn2w, dn2b, dW1, db1, dwdw, dbdw, dW2, db2)
+        _ready(P_n1w, P_n1b)
+        return (None, dx.view(LB, H * W, C), None, None, dn1wr, dn1br, dtabA, dWqA, dbqA, dWkvA, dbkvA, dWpA, dbpA, *gB,
+                dn2wr, dn2br, dW1, db1, dwdw, dbdw, dW2, db2)
 
 
 # ----------------------------------------------------------------------------- dense layers as autograd nodes
@@ -226,6 +298,7 @@ class LinearFn(torch.autograd.Function):
         ctx.act = (act, act_param)
         ctx.has_bias = b is not None
         ctx.has_res = residual is not None
+        ctx.params = (W, b)
         ctx.save_for_backward(x2, W, pre if pre is not None else (y if act != ops.ACT_NONE else None))
         ctx.xshape = x.shape
         return y.view(*x.shape[:-1], W.shape[0])
@@ -239,9 +312,8 @@ class LinearFn(torch.autograd.Function):
         if act != ops.ACT_NONE:
             # LeakyReLU: sign(out) == sign(pre-activation), so the saved output serves as aux
             g = ops.act_bwd(g, pre, act, ap)
-        dW = _z(W)
-        db = torch.empty(W.shape[0], device=g.device) if ctx.has_bias else None
-        dx = linear_grads(g, x2, W, dW, db, want_dx=ctx.needs_input_grad[0])
+        P_W, P_b = ctx.params
+        dx, dW, db = linear_param_grads(g, x2, P_W, P_b, want_dx=ctx.needs_input_grad[0])
         return (dx.view(ctx.xshape) if dx is not None else None), dW, db, None, None, dres
 
 
@@ -255,14 +327,18 @@ class LayerNormFn(torch.autograd.Function):
         xc = x.contiguous()
         y, mean, rstd = ops.layernorm_fwd(xc, w, b)
         ctx.save_for_backward(xc, mean, rstd, w)
+        ctx.params = (w, b)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, mean, rstd, w = ctx.saved_tensors
-        dw, db = _z(w), _z(w)
+        P_w, P_b = ctx.params
+        dw, dwr = _wbuf(P_w)
+        db, dbr = _wbuf(P_b)
         dx = ops.layernorm_bwd(dy.contiguous(), x, mean, rstd, w, None, dw, db)
-        return dx, dw, db
+        _ready(P_w, P_b)
+        return dx, dwr, dbr
 
 
 def layer_norm(x, w, b):

@@ -11,6 +11,7 @@ import torch.nn.functional as F
 
 from . import ops
 from .losses import l1_loss
+from .net import lewin
 
 
 def _offsets(params):
@@ -63,6 +64,8 @@ class BucketedAllReduce:
         self.stream = torch.cuda.Stream() if self.on_cuda else None
         self.world = dist.get_world_size(group)
         self.buckets = []          # (tensor slice, n_params)
+        self.bucket_of = {}        # id(param) -> bucket index
+        self.seen = set()
         self.pending = []
         self.handles = []
         per = int(bucket_mb * (1 << 20) // 4)
@@ -81,9 +84,23 @@ class BucketedAllReduce:
                 self.buckets.append((seg.grad[bounds[i]:bounds[i + 1]], counts[i]))
             for p, b in zip(seg.params, owners):
                 p.register_post_accumulate_grad_hook(self._make_hook(b))
+                self.bucket_of[id(p)] = b
         self.reset()
 
+    def param_ready(self, p):
+        """A block-level backward accumulated this parameter's gradient straight into the flat buffer (no
+        AccumulateGrad, so no hook): same bookkeeping as the hook, once per parameter per step."""
+        k = id(p)
+        b = self.bucket_of.get(k)
+        if b is None or k in self.seen:
+            return
+        self.seen.add(k)
+        self.pending[b] -= 1
+        if self.pending[b] == 0:
+            self._launch(b)
+
     def reset(self):
+        self.seen = set()
         self.pending = [c for _, c in self.buckets]
         self.handles = []
         self.launched = [False] * len(self.buckets)
@@ -135,6 +152,9 @@ class TrainStep:
         self.segments = [Segment(enc_params, fq), Segment(dec_params)]
         moco._flat_q = self.segments[0].flat
         self.ddp = BucketedAllReduce(self.segments, bucket_mb) if distributed else None
+        # parameters now own .grad views of per-step-zeroed flat buffers: let the block backwards accumulate into them
+        lewin.DIRECT_GRAD = True
+        lewin.GRAD_READY = self.ddp.param_ready if self.ddp is not None else None
         self.last = {}
         # CUDA-graph state (capture()): static inputs / loss, and the two step-dependent Adam scalars in device memory
         self.graph = None

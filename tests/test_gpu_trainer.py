@@ -1,0 +1,88 @@
+"""GPU: the fused train step (trainer.TrainStep) - direct gradient sinks vs gradients routed through autograd,
+CUDA-graph replay vs kernel-by-kernel launch, and Adam vs torch.optim.Adam on the same gradients."""
+import importlib
+import types
+
+import pytest
+import torch
+
+from conftest import PKG_NAME
+
+pytestmark = pytest.mark.gpu
+
+
+def make_opt(batch):
+    return types.SimpleNamespace(encoder_type='Uformer', decoder_type='Uformer', encoder_dim=256, L=3,
+                                 encoder_msa_type='freq', encoder_embed_dim=28, embed_dim=56,
+                                 degradation_embedding_method=['all_3_bands'], frequency_decompose_type='none',
+                                 learnable_modulator=False, debug_mode=False, batch_size=batch, out_channels=3,
+                                 batch_wise_decompose=False)
+
+
+def build(batch=2):
+    model = importlib.import_module(PKG_NAME + '.net.model')
+    trainer = importlib.import_module(PKG_NAME + '.trainer')
+    synth = importlib.import_module(PKG_NAME + '.synth')
+    torch.manual_seed(0)
+    net = model.AirNet(make_opt(batch)).cuda().train()
+    for m in net.modules():                      # DropPath off: the two runs must see identical graphs
+        if hasattr(m, 'drop_path_prob'):
+            m.drop_path_prob = 0.0
+    ts = trainer.TrainStep(net, lr=2e-4, contrast_loss_weight=0.6)
+    x = [t.cuda() for t in synth.noisy_batch(batch, 25)]
+    return net, ts, x
+
+
+def test_direct_grad_equals_autograd_grad():
+    lewin = importlib.import_module(PKG_NAME + '.net.lewin')
+    net, ts, x = build()
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    grads = {}
+    for direct in (True, False):
+        net.load_state_dict(sd0)
+        lewin.DIRECT_GRAD = direct
+        ts.zero_grad()
+        restored, logits, labels = net(*x[:2])
+        loss, _, _ = ts.loss(restored, logits, labels, x[2])
+        loss.backward()
+        grads[direct] = [s.grad.clone() for s in ts.segments]
+    lewin.DIRECT_GRAD = True
+    for a, b in zip(grads[True], grads[False]):
+        scale = b.abs().max().item()
+        assert (a - b).abs().max().item() <= 2e-5 * scale + 1e-8
+        assert a.abs().sum().item() > 0
+
+
+def test_graph_replay_matches_eager_and_adam_matches_torch():
+    net, ts, x = build()
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    # eager: three steps
+    eager_losses = [ts.step(*x).item() for _ in range(3)]
+    flat_eager = [s.flat.clone() for s in ts.segments]
+    # torch.optim.Adam on the same gradients (first step only: afterwards the parameters differ by round-off)
+    net.load_state_dict(sd0)
+    net2_params = [p for s in ts.segments for p in s.params]
+    ref = [p.detach().clone() for p in net2_params]
+    ts.t = 0
+    for s in ts.segments:
+        s.m.zero_(); s.v.zero_()
+    ts.step(*x)
+    gr = [p.grad.detach().clone() for p in net2_params]
+    ref_p = [r.clone().requires_grad_(True) for r in ref]
+    opt = torch.optim.Adam(ref_p, lr=2e-4)
+    for r, g in zip(ref_p, gr):
+        r.grad = g
+    opt.step()
+    worst = max((p.detach() - r.detach()).abs().max().item() for p, r in zip(net2_params, ref_p))
+    assert worst < 1e-6, worst
+    # graph: restore the initial state, capture, replay three steps
+    net.load_state_dict(sd0)
+    ts.t = 0
+    for s in ts.segments:
+        s.m.zero_(); s.v.zero_()
+    net.E.E.queue_ptr.zero_()
+    ts.capture(*x, warmup=0)
+    graph_losses = [ts.step(*x).item() for _ in range(3)]
+    assert ts.graph_launches > 1000
+    for a, b in zip(eager_losses, graph_losses):
+        assert abs(a - b) <= 2e-4 * max(abs(a), 1.0), (eager_losses, graph_losses)
