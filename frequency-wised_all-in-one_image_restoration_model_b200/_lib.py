@@ -18,7 +18,8 @@ class FaGemmEpilogue(ctypes.Structure):
                 ('aux', ctypes.c_void_p), ('ldaux', ctypes.c_int64), ('aux_act', ctypes.c_int),
                 ('aux_param', ctypes.c_float), ('rowscale', ctypes.c_void_p), ('rows_per_scale', ctypes.c_int),
                 ('residual', ctypes.c_void_p), ('ldr', ctypes.c_int64), ('accumulate', ctypes.c_int),
-                ('alpha', ctypes.c_float), ('preact', ctypes.c_void_p), ('ldpre', ctypes.c_int64)]
+                ('alpha', ctypes.c_float), ('preact', ctypes.c_void_p), ('ldpre', ctypes.c_int64),
+                ('a_rowsum', ctypes.c_void_p)]
 
 
 _SCALARS = {'int': ctypes.c_int, 'int64_t': ctypes.c_int64, 'float': ctypes.c_float, 'double': ctypes.c_double,

@@ -92,6 +92,15 @@ int fa_gemm(const float* A, const float* B, float* C, int M, int N, int K, int64
       return FA_ERR_UNSUPPORTED;
     }
   }
+  FaGemmEpilogue e2;
+  if (epi && epi->a_rowsum) {
+    // the SIMT kernel has no fused row-sum: take it in a separate pass over A, then contract without it
+    int rc = fa_a_rowsum(A, epi->a_rowsum, M, K, lda, transA, stream);
+    if (rc) return rc;
+    e2 = *epi;
+    e2.a_rowsum = nullptr;
+    epi = &e2;
+  }
   return fa_gemm_simt_launch(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, epi, st);
 }
 

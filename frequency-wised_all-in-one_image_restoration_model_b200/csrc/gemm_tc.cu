@@ -204,6 +204,7 @@ struct EpiTC {
   int accumulate; float alpha; int atomic;
   float* preact; int64_t ldpre;
   int vec;     // every epilogue array is 16-byte aligned with a row pitch that is a multiple of 4 floats, and N % 4 == 0
+  float* a_rowsum;   // a_tmem only: a_rowsum[m] += sum_k op(A)[m,k], accumulated by the split warps (thread = A row)
 };
 
 struct TcGeom {
@@ -421,6 +422,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     // ------------------------------------------------------------------ split warps: lo = x - trunc_tf32(x)
     if (X3) {
       const int st = threadIdx.x - 64;        // 0..SPLIT_WARPS*32-1
+      float rsum = 0.f;                       // a_rowsum: this thread's A row, summed over the k-blocks of the tile
       uint32_t it = 0;
       int s = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -454,6 +456,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
             for (int i = 0; i < NB; ++i) rb[i] = lds128(b + i * SPLIT_WARPS * 512);
             const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + TMEM_A_COL0 + s * 64;
+            if (epi.a_rowsum) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) rsum += av[k];
+            }
             tc_st32(taddr, av);
 #pragma unroll
             for (int k = 0; k < 32; ++k) av[k] = lo1(av[k]);
@@ -480,6 +486,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to UMMA
           mbar_arrive(&ready[s]);
           if (++s == STAGES) s = 0;
+        }
+        if (A_TMEM && epi.a_rowsum) {
+          const int rest = t / g.splits;
+          const int row = (rest / g.tiles_n) * BM + (warp & 3) * 32 + lane;
+          if (rest % g.tiles_n == 0 && row < g.M) atomicAdd(epi.a_rowsum + row, rsum);     // each A tile counted once
+          rsum = 0.f;
         }
       }
     }
@@ -673,6 +685,7 @@ int fa_gemm_tc_launch(const float* A, const float* B, float* C, int M, int N, in
     e.rowscale = ep->rowscale; e.rows_per_scale = ep->rows_per_scale > 0 ? ep->rows_per_scale : 1;
     e.residual = ep->residual; e.ldr = ep->ldr; e.accumulate = ep->accumulate; e.alpha = ep->alpha;
     e.preact = ep->preact; e.ldpre = ep->ldpre;
+    e.a_rowsum = ep->a_rowsum;
   }
   e.vec = (N % 4 == 0) && al16(C) && (ldc % 4 == 0) && (!e.bias || al16(e.bias)) &&
           (!e.aux || (al16(e.aux) && e.ldaux % 4 == 0)) && (!e.residual || (al16(e.residual) && e.ldr % 4 == 0)) &&
@@ -695,6 +708,7 @@ int fa_gemm_tc_launch(const float* A, const float* B, float* C, int M, int N, in
   g.a_mn = a_mn; g.b_mn = b_mn; g.x3 = single_pass ? 0 : 1;
   static const bool atmem_env = [] { const char* e = getenv("FREQAIR_GEMM_ATMEM"); return !(e && e[0] == '0'); }();
   g.a_tmem = (g.x3 && atmem_env) ? 1 : 0;
+  if (e.a_rowsum && !g.a_tmem) return FA_ERR_UNSUPPORTED;      // fused row sums ride the TMEM staging of A
   g.tiles_m = (M + BM - 1) / BM;
   int bn = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 96 ? 96 : 128));
   int64_t tiles = (int64_t)g.tiles_m * ((N + bn - 1) / bn);

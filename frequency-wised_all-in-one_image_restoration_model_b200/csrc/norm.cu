@@ -142,6 +142,20 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X
   }
 }
 
+// out[m] += sum_k X[m*ld + k]  (one warp per row)
+__global__ void __launch_bounds__(256) rowsum_kernel(const float* __restrict__ X, float* __restrict__ out, int M, int K,
+                                                     int64_t ld) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t m = warp; m < M; m += nwarps) {
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) s += X[m * ld + k];
+    s = warp_sum(s);
+    if (lane == 0) out[m] += s;
+  }
+}
+
 // ---------------------------------------------------------------- BatchNorm on [B,C,S]
 __device__ __forceinline__ float block_sum(float v, float* sh) {
   v = warp_sum(v);
@@ -426,6 +440,16 @@ int fa_colsum(const float* X, float* out, int M, int N, int64_t ld, const float*
   return FA_OK;
 }
 
+int fa_a_rowsum_impl(const float* A, float* out, int M, int K, int64_t lda, int transA, fa_stream_t stream) {
+  if (transA) return fa_colsum(A, out, K, M, lda, nullptr, 1, 1, stream);     // stored [K, M]: column sums
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M <= 0 || K <= 0) return FA_OK;
+  const int grid = ln_grid(M);
+  rowsum_kernel<<<grid, 256, 0, st>>>(A, out, M, K, lda);
+  FA_LAUNCH_CHECK("fa_gemm(a_rowsum)");
+  return FA_OK;
+}
+
 int fa_bn_stats(const float* x, double* sums, int B, int C, int64_t S, fa_stream_t stream) {
   FA_REQUIRE(x && sums && B > 0 && C > 0 && S > 0, "fa_bn_stats: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -543,3 +567,7 @@ int fa_token_mean_bwd(const float* dy, float* dx, int B, int HW, int C, fa_strea
 }
 
 }  // extern "C"
+
+int fa_a_rowsum(const float* A, float* out, int M, int K, int64_t lda, int transA, fa_stream_t stream) {
+  return fa_a_rowsum_impl(A, out, M, K, lda, transA, stream);
+}

@@ -42,7 +42,9 @@ struct Smem {
   float k[NTOK * HS];
   float v[NTOK * HSV];
   float p[NTOK * fft64::PSTR];
-  float2 sp[NTOK * fft64::SPSTR];
+  // the half spectrum of the filter phase reuses the q|k tiles (dead once the scores exist): 85 KB -> 68 KB, 3 CTAs per SM
+  static_assert(2 * NTOK * HS * sizeof(float) >= NTOK * fft64::SPSTR * sizeof(float2), "q|k tiles too small for the spectrum");
+  __device__ __forceinline__ float2* sp() { return reinterpret_cast<float2*>(q); }
   float bias[232];
   float coef[16];
   int row[NTOK];
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(NTHR) win_attn_fwd_kernel(const float* __restr
   __syncthreads();
   softmax_rows(s.p, tid);
   __syncthreads();
-  if (coef) fft64::filter_map(s.p, s.sp, s.band, s.coef, 1.0f, tid);
+  if (coef) fft64::filter_map(s.p, s.sp(), s.band, s.coef, 1.0f, tid);
   tile_pv<HD, false>(s.p, s.v, HSV, o, C, h * HD, s.row, 1.0f, tid);
 }
 
@@ -109,14 +111,20 @@ __global__ void __launch_bounds__(NTHR) win_attn_fwd_kernel(const float* __restr
 template <int HD>
 struct SmemB {
   static constexpr int HS = Pitch<HD>::HS;
+  // The two half-spectrum buffers of the filter phase live on top of the q|k|v tiles when those are large enough (hd 56,
+  // 64): q, k, v are dead between the score / dP' contractions and the final dQ / dK ones, and q, k are simply gathered
+  // again (L2 hits) afterwards.  That takes the CTA from 135 KB to 101 KB of shared memory, i.e. from 1 to 2 CTAs per SM
+  // - the kernel is a chain of short phases separated by block barriers, so the second CTA roughly doubles throughput.
+  static constexpr bool ALIAS = 3 * NTOK * HS * sizeof(float) >= 2 * NTOK * fft64::SPSTR * sizeof(float2);
   float q[NTOK * HS];
   float k[NTOK * HS];
   float v[NTOK * HS];
   float dO[NTOK * HS];
   float p[NTOK * fft64::PSTR];       // P (softmax), kept for dS
   float x[NTOK * fft64::PSTR];       // dP' -> P' -> dP -> dS
-  float2 spA[NTOK * fft64::SPSTR];
-  float2 spB[NTOK * fft64::SPSTR];
+  float2 sp_own[ALIAS ? 1 : 2 * NTOK * fft64::SPSTR];
+  __device__ __forceinline__ float2* spA() { return ALIAS ? reinterpret_cast<float2*>(q) : sp_own; }
+  __device__ __forceinline__ float2* spB() { return spA() + NTOK * fft64::SPSTR; }
   float bias[232];
   float dbias[232];
   float coef[16];
@@ -170,25 +178,25 @@ __global__ void __launch_bounds__(NTHR) win_attn_bwd_kernel(const float* __restr
     __syncthreads();
     if (coef) {
       // F(dP') -> spB
-      fft64::rows_forward(s.x, s.spB, tid);
+      fft64::rows_forward(s.x, s.spB(), tid);
       __syncthreads();
       {
         const int col = min(tid >> 3, 32), l = tid & 7;
         float2 a[8];
-        fft64::col_load(s.spB, a, col, l);
+        fft64::col_load(s.spB(), a, col, l);
         fft64::fft64_group<-1>(a, l);
         __syncwarp();
-        if ((tid >> 3) <= 32) fft64::col_store(s.spB, a, col, l);
+        if ((tid >> 3) <= 32) fft64::col_store(s.spB(), a, col, l);
       }
-      fft64::rows_forward(s.p, s.spA, tid);
+      fft64::rows_forward(s.p, s.spA(), tid);
       __syncthreads();
       {
         // F(P): band energies against F(dP'), then gain and inverse columns -> spA
         const int col = min(tid >> 3, 32), l = tid & 7;
         const bool live = (tid >> 3) <= 32;
         float2 a[8], bb[8];
-        fft64::col_load(s.spA, a, col, l);
-        fft64::col_load(s.spB, bb, col, l);
+        fft64::col_load(s.spA(), a, col, l);
+        fft64::col_load(s.spB(), bb, col, l);
         fft64::fft64_group<-1>(a, l);
         const float wgt = (col == 0 || col == 32) ? 1.0f : 2.0f;
         float e[8];
@@ -205,7 +213,7 @@ __global__ void __launch_bounds__(NTHR) win_attn_bwd_kernel(const float* __restr
         }
         fft64::fft64_group<1>(a, l);
         __syncwarp();
-        if (live) fft64::col_store(s.spA, a, col, l);
+        if (live) fft64::col_store(s.spA(), a, col, l);
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
           float v = live ? e[t] : 0.f;
@@ -214,14 +222,14 @@ __global__ void __launch_bounds__(NTHR) win_attn_bwd_kernel(const float* __restr
         }
       }
       __syncthreads();
-      fft64::rows_inverse(s.spA, s.x, 1.0f / 4096.0f, tid);             // x = P'
+      fft64::rows_inverse(s.spA(), s.x, 1.0f / 4096.0f, tid);             // x = P'
       __syncthreads();
       tile_pv<HD, true>(s.x, s.dO, HS, dkv, 2 * C, C + h * HD, s.row, 1.0f, tid);   // dV = P'^T.dO
       {
         // dP = filter(dP'): gain on F(dP'), inverse columns
         const int col = min(tid >> 3, 32), l = tid & 7;
         float2 a[8];
-        fft64::col_load(s.spB, a, col, l);
+        fft64::col_load(s.spB(), a, col, l);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float gn = 1.0f + s.coef[s.band[(l + 8 * j) * 33 + col]];
@@ -229,11 +237,15 @@ __global__ void __launch_bounds__(NTHR) win_attn_bwd_kernel(const float* __restr
         }
         fft64::fft64_group<1>(a, l);
         __syncwarp();
-        if ((tid >> 3) <= 32) fft64::col_store(s.spB, a, col, l);
+        if ((tid >> 3) <= 32) fft64::col_store(s.spB(), a, col, l);
       }
       __syncthreads();                                                  // dV reads of x done, spB complete
-      fft64::rows_inverse(s.spB, s.x, 1.0f / 4096.0f, tid);             // x = dP
+      fft64::rows_inverse(s.spB(), s.x, 1.0f / 4096.0f, tid);             // x = dP
       __syncthreads();
+      if (SmemB<HD>::ALIAS) {            // the spectra overwrote q|k|v: gather q and k again for dQ / dK
+        load_tile<HD, HS>(s.q, q, ldq, h * HD, s.row, tid);
+        load_tile<HD, HS>(s.k, kv, ldkv, h * HD, s.row, tid);
+      }
       if (dcoef && tid < nbands) atomicAdd(&dcoef[((int64_t)b * coef_bstride + h) * nbands + tid], s.ecoef[tid]);
     } else {
       tile_pv<HD, true>(s.p, s.dO, HS, dkv, 2 * C, C + h * HD, s.row, 1.0f, tid);   // dV = P^T.dO

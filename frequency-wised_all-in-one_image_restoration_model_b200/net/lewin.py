@@ -76,9 +76,10 @@ def linear_grads(g, x, W, dW, db, want_dx=True, dx=None, accumulate_dx=False):
 
 def linear_param_grads(g, x, W, b, want_dx=True, dx=None, accumulate_dx=False):
     """linear_grads with the parameter gradients routed through the sinks: returns (dx, dW_ret, db_ret)."""
-    db_ret = _bias_grad(g, b)
     dW, dW_ret = _wbuf(W)
-    ops.gemm(g, x, dW, transA=True, transB=False, accumulate=True)
+    db, db_ret = _wbuf(b) if b is not None else (None, None)
+    # dW += g^T x, and the bias gradient (column sums of g) taken from the same pass over g (FaGemmEpilogue.a_rowsum)
+    ops.gemm(g, x, dW, transA=True, transB=False, accumulate=True, a_rowsum=db)
     _ready(W, b)
     if not want_dx:
         return None, dW_ret, db_ret
@@ -106,9 +107,9 @@ def leff_fwd(xn2, w1, b1, wdw, bdw, w2, b2, B, H, W, residual, dp_scale, save):
 def leff_bwd(gs, sv, xn2, w1, b1, wdw, bdw, w2, b2, B, H, W):
     """gs: gradient wrt the LeFF output (DropPath scale already applied). Returns dxn2 and the parameter gradients
     (None where they were accumulated straight into the parameters' .grad buffers)."""
-    db2 = _bias_grad(gs, b2)
     dW2, dW2r = _wbuf(w2)
-    ops.gemm(gs, sv['h2'], dW2, transA=True, transB=False, accumulate=True)
+    db2b, db2 = _wbuf(b2)
+    ops.gemm(gs, sv['h2'], dW2, transA=True, transB=False, accumulate=True, a_rowsum=db2b)
     du2 = torch.empty_like(sv['u2'])
     ops.gemm(gs, w2, du2, transB=False, aux=sv['u2'], aux_act=ops.ACT_GELU)
     dwdw, dwdwr = _wbuf(wdw)

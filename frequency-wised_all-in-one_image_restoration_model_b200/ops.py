@@ -81,7 +81,7 @@ def _rows2d(t):
 
 def gemm(A, B, C, transA=False, transB=True, bias=None, act=ACT_NONE, act_param=0.0, aux=None, aux_act=ACT_NONE,
          aux_param=0.0, rowscale=None, rows_per_scale=1, residual=None, accumulate=False, alpha=1.0, preact=None,
-         backend=None):
+         backend=None, a_rowsum=None):
     """C = epi(alpha * op(A) @ op(B)); see fa_gemm in include/freqair.h.  A, B, C, aux, residual, preact are 2-D
     row-major views (row stride may exceed the width).  transB=True means B is an nn.Linear weight [N, K]."""
     ar, ac, lda = _rows2d(A)
@@ -115,6 +115,11 @@ def gemm(A, B, C, transA=False, transB=True, bias=None, act=ACT_NONE, act_param=
     if preact is not None:
         _, _, e.ldpre = _rows2d(preact)
         e.preact = preact.data_ptr()
+    if a_rowsum is not None:            # accumulated: a_rowsum[m] += sum_k op(A)[m, k]  (bias gradient of a transA GEMM)
+        _f32(a_rowsum)
+        if a_rowsum.numel() != M:
+            raise RuntimeError(f'freqair.gemm: a_rowsum has {a_rowsum.numel()} entries, expected M={M}')
+        e.a_rowsum = a_rowsum.data_ptr()
     _call('fa_gemm', _p(A), _p(B), _p(C), M, N, K, lda, ldb, ldc, int(transA), int(transB), ctypes.byref(e), backend,
           _stream())
     return C

@@ -57,6 +57,9 @@ typedef struct FaGemmEpilogue {
   int accumulate;
   float alpha;
   float* preact; int64_t ldpre;   /* if set: preact[m,n] = alpha*acc + bias[n] (value before act), for the backward */
+  float* a_rowsum;                /* if set: a_rowsum[m] += sum_k op(A)[m,k].  With transA = 1 (dW = dY^T X) this is the
+                                     column sum of the stored dY, i.e. the bias gradient, taken while the A tiles pass
+                                     through the kernel instead of in a second pass over dY (fa_colsum) */
 } FaGemmEpilogue;
 int fa_gemm(const float* A, const float* B, float* C, int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc,
             int transA, int transB, const FaGemmEpilogue* epi, int backend, fa_stream_t stream);

@@ -121,3 +121,21 @@ def test_gemm_tc_matches_simt_on_tf32_exact_inputs(ops):
     ops.gemm(A.cuda(), B.cuda(), C1, backend=1)
     ops.gemm(A.cuda(), B.cuda(), C2, backend=2)
     assert (C1 - C2).abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize('backend', [0, 1, 2])
+@pytest.mark.parametrize('M,N,K,tA', [(224, 56, 40000, True), (448, 448, 4096, True), (56, 224, 3000, True), (300, 64, 96, False)])
+def test_gemm_a_rowsum(ops, M, N, K, tA, backend):
+    """FaGemmEpilogue.a_rowsum: the bias gradient (column sums of the stored dY when transA) from the same pass."""
+    A = gen(K, M, scale=0.1) if tA else gen(M, K, scale=0.1)
+    B = gen(K, N, seed=1)
+    C0 = gen(M, N, seed=2)
+    rs0 = gen(M, seed=3)
+    C, rs = C0.cuda(), rs0.cuda()
+    ops.gemm(A.cuda(), B.cuda(), C, transA=tA, transB=False, accumulate=True, a_rowsum=rs, backend=backend)
+    opA = (A.t() if tA else A).double()
+    ref = C0.double() + opA @ B.double()
+    tol = 3e-6 * math.sqrt(K) * 0.1 * 4 + 1e-5
+    assert (C.double().cpu() - ref).abs().max().item() <= tol * 10
+    ref_rs = rs0.double() + opA.sum(1)
+    assert (rs.double().cpu() - ref_rs).abs().max().item() <= 2e-6 * K ** 0.5 * 0.1 * 8 + 1e-5
