@@ -133,9 +133,49 @@ def bench_misc():
         del h1, du2, u1
 
 
+def bench_attn():
+    """Fused window attention kernels at the step's shapes: time, effective TFLOP/s of the contractions (dense flops of
+    the unmasked blocks, fwd 2 products, bwd 5 + the recomputed score product) and GB/s of q,k,v,o(,grads)."""
+    print(f'{"kernel":46s} {"ms":>8s} {"TFLOP/s":>8s} {"GB/s":>8s}')
+    bob = None
+    from importlib import import_module
+    fd = import_module(PKG + '.net.utils.frequency_decompose')
+    for B, H, heads, hd, shift in [(16, 128, 2, 56, 4), (16, 128, 1, 56, 0), (16, 64, 4, 56, 4), (16, 32, 8, 56, 4), (16, 16, 16, 56, 4)]:
+        C = heads * hd; T = B * H * H
+        qkv = torch.randn(T, 3 * C, device='cuda') * 0.5
+        table = torch.randn(225, heads, device='cuda') * 0.3
+        coef = torch.randn(B, heads, 3, device='cuda') * 0.3
+        if bob is None:
+            bob = fd.half_band_map('frequency_decompose_1', 0.5, 64).cuda()
+        o = torch.empty(T, C, device='cuda'); dO = torch.randn(T, C, device='cuda')
+        dq = torch.empty(T, C, device='cuda'); dkv = torch.empty(T, 2 * C, device='cuda')
+        dtab = torch.zeros_like(table); dcf = torch.zeros_like(coef)
+        items = B * (H // 8) ** 2 * heads
+        fl = items * 2 * 64 * 64 * hd * 2
+        args = (B, H, H, heads, hd, shift, hd ** -0.5)
+        ms = timeit(lambda: ops.win_attn_fwd(qkv[:, :C], qkv[:, C:], o, *args, table, coef, heads, bob, 3))
+        print(f'{f"win_attn_fwd B{B} {H}x{H} h{heads} hd{hd} s{shift}":46s} {ms:8.3f} {fl / ms / 1e9:8.1f} {16 * T * C / ms / 1e6:8.0f}', flush=True)
+        ms = timeit(lambda: ops.win_attn_bwd(qkv[:, :C], qkv[:, C:], dO, dq, dkv, *args, table, dtab, coef, heads, dcf, bob, 3))
+        print(f'{f"win_attn_bwd B{B} {H}x{H} h{heads} hd{hd} s{shift}":46s} {ms:8.3f} {3 * fl / ms / 1e9:8.1f} {28 * T * C / ms / 1e6:8.0f}', flush=True)
+    L = 3
+    for B, H, heads in [(16, 128, 1), (16, 64, 2), (16, 32, 4), (16, 16, 8)]:
+        hd = 28; C = heads * hd; T = L * B * H * H
+        qkv = torch.randn(T, 3 * C, device='cuda') * 0.5
+        tables = torch.randn(L * L, 225, heads, device='cuda') * 0.3
+        o = torch.empty(T, C, device='cuda'); dO = torch.randn(T, C, device='cuda')
+        dq = torch.empty(T, C, device='cuda'); dkv = torch.empty(T, 2 * C, device='cuda'); dtab = torch.zeros_like(tables)
+        items = L * B * (H // 8) ** 2 * heads
+        for kind, nk in ((0, 64), (1, 128)):
+            fl = items * 2 * 64 * nk * hd * 2
+            ms = timeit(lambda: ops.joint_attn_fwd(qkv[:, :C], qkv[:, C:], o, L, B, H, H, heads, hd, 4, hd ** -0.5, tables, kind))
+            print(f'{f"joint_fwd kind{kind} B{B} {H}x{H} h{heads}":46s} {ms:8.3f} {fl / ms / 1e9:8.1f} {16 * T * C / ms / 1e6:8.0f}', flush=True)
+            ms = timeit(lambda: ops.joint_attn_bwd(qkv[:, :C], qkv[:, C:], dO, dq, dkv, L, B, H, H, heads, hd, 4, hd ** -0.5, tables, dtab, kind))
+            print(f'{f"joint_bwd kind{kind} B{B} {H}x{H} h{heads}":46s} {ms:8.3f} {3 * fl / ms / 1e9:8.1f} {28 * T * C / ms / 1e6:8.0f}', flush=True)
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
-    ap.add_argument('what', choices=['gemm', 'epi', 'misc'])
+    ap.add_argument('what', choices=['gemm', 'epi', 'misc', 'attn'])
     ap.add_argument('--backend', type=int, default=0)
     ap.add_argument('--only', default=None)
     ap.add_argument('--layouts', default='NT,NN,TN')
@@ -146,3 +186,5 @@ if __name__ == '__main__':
         bench_epi(a.backend)
     if a.what == 'misc':
         bench_misc()
+    if a.what == 'attn':
+        bench_attn()
