@@ -147,6 +147,56 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_inference(args):
+    """Per-image latency of tiled inference (test.py:48-71 geometry): a HxW image -> ceil(H/128)*ceil(W/128) tiles ->
+    ONE batched eval forward (query encoder trunk + decoder; the contrastive heads the reference computes and discards
+    are skipped) -> overlap-averaged reassembly.  e2e includes the H2D copy of the image and the D2H of the result."""
+    size = 512 if args.workload == 'infer512' else 1024
+    synth = importlib.import_module(PKG + '.synth')
+    model = importlib.import_module(PKG + '.net.model')
+    infer = importlib.import_module(PKG + '.infer')
+    ops = importlib.import_module(PKG + '.ops')
+    torch.manual_seed(0)
+    net = model.AirNet(make_opt(16)).cuda().eval()
+    img = synth.gaussian_noise(synth.clean_images(1, size, size, seed=4321), 25, 4322).pin_memory()
+    dimg = img.cuda()
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+    if args.no_graph:
+        run = lambda x: infer.restore_tiled(net, x)
+    else:
+        run = infer.GraphedRestorer(net, size, size)
+    for _ in range(W):
+        run(dimg)
+    torch.cuda.synchronize()
+    ops.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        run(dimg)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    launches = ops.launch_count()
+    out_host = torch.empty(1, 3, size, size).pin_memory()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(K):
+        out_host.copy_(run(img if not args.no_graph else img.cuda(non_blocking=True)), non_blocking=True)
+        torch.cuda.synchronize()
+    f1.record()
+    torch.cuda.synchronize()
+    ms_e2e = f0.elapsed_time(f1) / K
+    ntiles = (size // 128) ** 2
+    print(json.dumps({'metric': f'{size}x{size} inference ms/img (Uformer+Uformer all_3_bands, {ntiles} tiles of 128x128)',
+                      'value': ms, 'unit': 'ms/img', 'n_gpus': 1, 'steps': K, 'warmup': W, 'ms_per_step': ms,
+                      'higher_is_better': False, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                      'config': {'workload': f'tiled eval forward of one {size}x{size} sigma=25 image, random init', 'tiles': ntiles,
+                                 'launch': 'eager' if args.no_graph else 'cuda_graph'},
+                      'e2e': {'value': ms_e2e, 'unit': 'ms/img', 'h2d_bytes_per_step': img.numel() * 4,
+                              'd2h_bytes_per_step': img.numel() * 4},
+                      'gpu_launches': launches, 'tiles_per_s': ntiles / (ms * 1e-3)}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -157,6 +207,9 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-roofline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch the step kernel by kernel instead of replaying its CUDA graph')
+    ap.add_argument('--workload', default='train', choices=['train', 'infer512', 'infer1024'],
+                    help='train = the headline configs[1] step (default); infer512 / infer1024 = configs[3]-style tiled '
+                         'full-resolution inference latency (Uformer encoder + Uformer decoder), ms per image, 1 GPU')
     args = ap.parse_args()
     if os.environ.get('FREQAIR_WATCHDOG'):                 # debugging aid: dump every thread's stack and exit if stuck
         import faulthandler
@@ -169,6 +222,9 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device - the freqair path has no CPU fallback (use --impl reference for the CPU baseline)')
+    if args.workload != 'train':
+        run_inference(args)
+        return
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
     torch.cuda.set_device(local)

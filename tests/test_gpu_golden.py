@@ -80,6 +80,44 @@ def test_airnet_eval(airnet):
     assert maxerr(y, t(g['restored'])) < 1e-3
 
 
+def test_airnet_eval_psnr_ssim_parity(airnet):
+    """north_star: PSNR / SSIM of the restored image within 0.01 dB / 1e-4 of the reference's own output (golden vector
+    produced by the real reference), with the metrics defined as test.py / val_utils.py compute them."""
+    from oracle import metrics
+    g = load_golden('airnet_uu_eval.npz')
+    detfill.fill_state(airnet.state_dict())
+    airnet.eval()
+    xq, _, clean = synth.noisy_batch(2, 25)
+    with torch.no_grad():
+        y = airnet(xq[:1].cuda(), xq[:1].cuda()).cpu()
+    ref = t(g['restored'])
+    dp = abs(metrics.psnr(y[0], clean[0]) - metrics.psnr(ref[0], clean[0]))
+    ds = abs(metrics.ssim(y[0], clean[0]) - metrics.ssim(ref[0], clean[0]))
+    assert dp < 0.01 and ds < 1e-4, (dp, ds)
+
+
+def test_tiled_inference_matches_per_tile_forward(airnet):
+    """512x384 image -> 12 tiles of 128 (no overlap): the tiled front end equals the per-tile forwards put back in
+    place; 200x200 (overlapping last row / column): every pixel is the mean of the tiles that cover it."""
+    infer = importlib.import_module(PKG_NAME + '.infer')
+    detfill.fill_state(airnet.state_dict())
+    airnet.eval()
+    img = synth.gaussian_noise(synth.clean_images(1, 384, 512, seed=4321), 25, 4322).cuda()
+    out = infer.restore_tiled(airnet, img)
+    assert out.shape == img.shape
+    with torch.no_grad():
+        one = airnet(img[:, :, 128:256, 256:384].contiguous(), img[:, :, 128:256, 256:384].contiguous())
+    assert maxerr(out[:, :, 128:256, 256:384], one) < 1e-4
+    img2 = synth.gaussian_noise(synth.clean_images(1, 200, 200, seed=4323), 25, 4324).cuda()
+    out2 = infer.restore_tiled(airnet, img2)
+    tiles, origins = infer.tile(img2)
+    assert origins == [(0, 0), (0, 72), (72, 0), (72, 72)]
+    with torch.no_grad():
+        r = airnet(tiles, tiles)
+    assert maxerr(out2[0, :, :72, :72], r[0, :, :72, :72]) < 1e-5                     # covered once
+    assert maxerr(out2[0, :, 100, 100], (r[0, :, 100, 100] + r[1, :, 100, 28] + r[2, :, 28, 100] + r[3, :, 28, 28]) / 4) < 1e-5
+
+
 def test_airnet_train_step(airnet):
     losses = importlib.import_module(PKG_NAME + '.losses')
     g = load_golden('airnet_uu_train.npz')

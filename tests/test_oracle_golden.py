@@ -172,3 +172,18 @@ def test_dcn_known_answers():
     y = airnet.modulated_deform_conv2d(x, off, m, w)
     y2 = tv.deform_conv2d(x, off, w, None, padding=1, mask=m)
     assert (y - y2).abs().max() < 1e-4
+
+
+def test_metrics_known_answers():
+    """PSNR / SSIM restatement: identities and a hand-computed case (uniform offset image)."""
+    import torch
+    from oracle import metrics
+    a = torch.rand(3, 32, 32, generator=torch.Generator().manual_seed(0))
+    assert metrics.ssim(a, a) == pytest.approx(1.0, abs=1e-12)
+    b = (a + 0.1).clamp(0, 1)
+    mse = (a.double() - b.double()).pow(2).mean().item()
+    assert metrics.psnr(a, b) == pytest.approx(10 * __import__('math').log10(1.0 / mse), abs=1e-9)
+    # constant images x, y: SSIM = (2xy + C1) / (x^2 + y^2 + C1) (variances vanish, C2 cancels)
+    x, y = torch.full((1, 16, 16), 0.5), torch.full((1, 16, 16), 0.25)
+    c1 = 1e-4
+    assert metrics.ssim(x, y) == pytest.approx((2 * 0.5 * 0.25 + c1) / (0.25 + 0.0625 + c1), abs=1e-9)
