@@ -233,9 +233,13 @@ __device__ __forceinline__ float actg_c(float x, float p) {
 }
 
 // one float4 (4 consecutive columns of one output row) through the epilogue; ACT = the forward activation (FWD) or
-// the activation whose derivative multiplies the result (BWD); EPI_ANY takes both at run time (ACT ignored)
-template <int MODE, int ACT>
-__device__ __forceinline__ void epi_vec(float4 x, const EpiTC& e, float4 b4, int row, int col, float* __restrict__ cp) {
+// the activation whose derivative multiplies the result (BWD); EPI_ANY takes both at run time (ACT ignored).
+// PRE: the global operands of the row (aux / residual / previous C) were fetched by the caller into e1 / e2, so that
+// the loads of a batch of rows are all in flight before the first store (the compiler must assume C aliases them and
+// would otherwise serialise one global round trip per row: measured 3.5x on the gelu'(aux) epilogue).
+template <int MODE, int ACT, bool PRE>
+__device__ __forceinline__ void epi_vec(float4 x, const EpiTC& e, float4 b4, int row, int col, float* __restrict__ cp,
+                                        float4 e1, float4 e2) {
   if (MODE == EPI_PLAIN || MODE == EPI_ANY) {
     if (e.atomic) {
       atomicAdd(reinterpret_cast<float4*>(cp), make_float4(x.x * e.alpha, x.y * e.alpha, x.z * e.alpha, x.w * e.alpha));
@@ -254,7 +258,7 @@ __device__ __forceinline__ void epi_vec(float4 x, const EpiTC& e, float4 b4, int
   }
   if (MODE == EPI_BWD || MODE == EPI_ANY) {
     if (e.aux) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(e.aux + (int64_t)row * e.ldaux + col));
+      const float4 a = PRE ? e1 : __ldg(reinterpret_cast<const float4*>(e.aux + (int64_t)row * e.ldaux + col));
       if (MODE == EPI_ANY) {
         x.x *= act_grad_f(a.x, e.aux_act, e.aux_p); x.y *= act_grad_f(a.y, e.aux_act, e.aux_p);
         x.z *= act_grad_f(a.z, e.aux_act, e.aux_p); x.w *= act_grad_f(a.w, e.aux_act, e.aux_p);
@@ -270,28 +274,61 @@ __device__ __forceinline__ void epi_vec(float4 x, const EpiTC& e, float4 b4, int
       x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs;
     }
     if (e.residual) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(e.residual + (int64_t)row * e.ldr + col));
+      const float4 a = PRE ? e1 : __ldg(reinterpret_cast<const float4*>(e.residual + (int64_t)row * e.ldr + col));
       x.x += a.x; x.y += a.y; x.z += a.z; x.w += a.w;
     }
   }
   if (MODE != EPI_FWD) {
     if (e.accumulate) {
-      const float4 a = *reinterpret_cast<const float4*>(cp);
+      const float4 a = PRE ? (MODE == EPI_BWD ? e2 : e1) : *reinterpret_cast<const float4*>(cp);
       x.x += a.x; x.y += a.y; x.z += a.z; x.w += a.w;
     }
   }
   *reinterpret_cast<float4*>(cp) = x;
 }
 
-// the 8 row-quads of one 32 x 32 chunk (lane = 4 columns of row it*4 + lane/8)
+// the 8 row-quads of one 32 x 32 chunk (lane = 4 columns of row it*4 + lane/8), in two batches of four: first every
+// global read of the batch, then the arithmetic and the stores
 template <int MODE, int ACT>
 __device__ __forceinline__ void epi_rows(uint32_t stg_s, const EpiTC& e, float4 b4, int row0, int rsub, int c4, int col,
                                          int M, float* __restrict__ cp0, int64_t ldc) {
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool reads = (MODE == EPI_BWD && (e.aux || e.accumulate)) || (MODE == EPI_FWD && e.residual) ||
+                     (MODE == EPI_PLAIN && e.accumulate && !e.atomic);
+  if (MODE == EPI_ANY || !reads) {          // store-only epilogue (or the compact generic one): plain row loop
 #pragma unroll(MODE == EPI_ANY ? 1 : 4)
-  for (int it = 0; it < 8; ++it) {
-    const int r = it * 4 + rsub;
-    if (row0 + r < M)
-      epi_vec<MODE, ACT>(lds128(stg_s + 4 * stg_idx(r, c4)), e, b4, row0 + r, col, cp0 + (int64_t)it * 4 * ldc);
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + rsub;
+      if (row0 + r < M)
+        epi_vec<MODE, ACT, false>(lds128(stg_s + 4 * stg_idx(r, c4)), e, b4, row0 + r, col, cp0 + (int64_t)it * 4 * ldc, z4, z4);
+    }
+    return;
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float4 e1[4], e2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int it = h * 4 + j, row = row0 + it * 4 + rsub;
+      e1[j] = z4; e2[j] = z4;
+      if (row < M) {
+        const float* cp = cp0 + (int64_t)it * 4 * ldc;
+        if (MODE == EPI_BWD) {
+          if (e.aux) e1[j] = __ldg(reinterpret_cast<const float4*>(e.aux + (int64_t)row * e.ldaux + col));
+          if (e.accumulate) e2[j] = *reinterpret_cast<const float4*>(cp);
+        } else if (MODE == EPI_FWD) {
+          if (e.residual) e1[j] = __ldg(reinterpret_cast<const float4*>(e.residual + (int64_t)row * e.ldr + col));
+        } else {
+          if (e.accumulate && !e.atomic) e1[j] = *reinterpret_cast<const float4*>(cp);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int it = h * 4 + j, r = it * 4 + rsub;
+      if (row0 + r < M)
+        epi_vec<MODE, ACT, true>(lds128(stg_s + 4 * stg_idx(r, c4)), e, b4, row0 + r, col, cp0 + (int64_t)it * 4 * ldc, e1[j], e2[j]);
+    }
   }
 }
 
