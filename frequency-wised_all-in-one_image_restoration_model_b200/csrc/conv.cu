@@ -91,25 +91,36 @@ __global__ void __launch_bounds__(256) dwconv_strip_kernel(const float* __restri
   }
 }
 
-// dw[c][tap] += sum_p du2[p,c] * h1[p + delta(tap), c];  db[c] += sum_p du2[p,c]
-// Same strips, window over h1; 36 + 4 accumulators per thread persist over all the strips a thread visits, then the
-// 8 strip lanes of a block are reduced in shared memory and flushed with one atomic per (channel, tap) per block.
-__global__ void __launch_bounds__(256) dwconv_wgrad_strip_kernel(const float* __restrict__ du2,
-                                                                 const float* __restrict__ h1, float* __restrict__ dw,
-                                                                 float* __restrict__ db, StripGeom g, int nstrips) {
+// Backward of the LeFF depthwise conv in ONE sweep.  With q = p + delta(tap) the weight gradient
+//   dw[c][tap] = sum_p du2[p,c] * h1[p + delta(tap), c] = sum_q du2[q - delta(tap), c] * h1[q, c]
+// uses exactly the 3x3 window of du2 around q that the data gradient du1[q] = gelu'(u1[q]) * sum_tap w[tap]*du2[q-delta]
+// needs, so both come from one window over du2 plus the centre values of h1 and u1: 4.5 passes over the hidden tensor
+// (du2 x1.5, h1, u1, du1) instead of 6.2 for two kernels.  36 + 4 accumulators per thread persist over the strips a
+// thread visits; the 8 strip lanes of a block are reduced in shared memory, one atomic per (channel, tap) per block.
+__global__ void __launch_bounds__(256, 2) dwconv_bwd_strip_kernel(const float* __restrict__ du2,
+                                                               const float* __restrict__ h1,
+                                                               const float* __restrict__ u1,
+                                                               const float* __restrict__ w, float* __restrict__ du1,
+                                                               float* __restrict__ dw, float* __restrict__ db,
+                                                               StripGeom g, int nstrips) {
   __shared__ float red[8][32][41];
   const int c = (blockIdx.y * 32 + threadIdx.x) * 4;
   const bool cok = c < g.C;
-  float4 acc[9];
+  float4 wv[9], acc[9];
   float4 accb = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int t = 0; t < 9; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < 9; ++t) {
+    // window slot t = (ky,kx) holds du2[q + (ky-1, kx-1)] = du2[q - delta(8-t)]: it pairs with tap 8-t
+    wv[t] = cok ? make_float4(w[(c + 0) * 9 + 8 - t], w[(c + 1) * 9 + 8 - t], w[(c + 2) * 9 + 8 - t], w[(c + 3) * 9 + 8 - t])
+                : make_float4(0.f, 0.f, 0.f, 0.f);
+    acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   if (cok) {
     for (int strip = blockIdx.x * blockDim.y + threadIdx.y; strip < nstrips; strip += gridDim.x * blockDim.y) {
       int b, y0, x0;
       strip_decode(strip, g, b, y0, x0);
       const int64_t img = (int64_t)b * g.H * g.W * g.C + c;
-      const float* base = h1 + img;
+      const float* base = du2 + img;
       float4 win[3][DW_R + 2];
       strip_loadcol(base, x0 - 1, y0, g, win[1]);
       strip_loadcol(base, x0, y0, g, win[2]);
@@ -121,21 +132,35 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_strip_kernel(const float* __
 #pragma unroll
         for (int r = 0; r < DW_R; ++r) {
           if (y0 + r >= g.H) break;
-          const float4 gq = ld4(du2 + img + ((int64_t)(y0 + r) * g.W + x) * g.C);
-          accb.x += gq.x; accb.y += gq.y; accb.z += gq.z; accb.w += gq.w;
+          const int64_t o = img + ((int64_t)(y0 + r) * g.W + x) * g.C;
+          float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) acc[ky * 3 + kx] = fma4(gq, win[kx][r + ky], acc[ky * 3 + kx]);
+            for (int kx = 0; kx < 3; ++kx) d = fma4(win[kx][r + ky], wv[ky * 3 + kx], d);
+          if (u1) {
+            const float4 u = ld4(u1 + o);
+            d = make_float4(d.x * gelu_grad_f(u.x), d.y * gelu_grad_f(u.y), d.z * gelu_grad_f(u.z), d.w * gelu_grad_f(u.w));
+          }
+          st4(du1 + o, d);
+          if (dw) {
+            const float4 hq = ld4(h1 + o);
+            const float4 gc = win[1][r + 1];                       // du2[q]
+            accb.x += gc.x; accb.y += gc.y; accb.z += gc.z; accb.w += gc.w;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) acc[t] = fma4(win[t % 3][r + t / 3], hq, acc[t]);
+          }
         }
       }
     }
   }
+  if (!dw) return;                                                  // uniform over the block
   const int pl = threadIdx.y, cq = threadIdx.x;
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
-    red[pl][cq][t * 4 + 0] = acc[t].x; red[pl][cq][t * 4 + 1] = acc[t].y;
-    red[pl][cq][t * 4 + 2] = acc[t].z; red[pl][cq][t * 4 + 3] = acc[t].w;
+    // acc[t] belongs to tap 8-t
+    red[pl][cq][(8 - t) * 4 + 0] = acc[t].x; red[pl][cq][(8 - t) * 4 + 1] = acc[t].y;
+    red[pl][cq][(8 - t) * 4 + 2] = acc[t].z; red[pl][cq][(8 - t) * 4 + 3] = acc[t].w;
   }
   red[pl][cq][36] = accb.x; red[pl][cq][37] = accb.y; red[pl][cq][38] = accb.z; red[pl][cq][39] = accb.w;
   __syncthreads();
@@ -144,11 +169,11 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_strip_kernel(const float* __
     const int q = i / 40, v = i % 40;
     const int cc = (blockIdx.y * 32 + q) * 4;
     if (cc >= g.C) continue;
-    float s = 0.f;
+    float sum = 0.f;
 #pragma unroll
-    for (int l = 0; l < 8; ++l) s += red[l][q][v];
-    if (v < 36) atomicAdd(&dw[(cc + (v & 3)) * 9 + (v >> 2)], s);
-    else if (db) atomicAdd(&db[cc + (v - 36)], s);
+    for (int l = 0; l < 8; ++l) sum += red[l][q][v];
+    if (v < 36) atomicAdd(&dw[(cc + (v & 3)) * 9 + (v >> 2)], sum);
+    else if (db) atomicAdd(&db[cc + (v - 36)], sum);
   }
 }
 
@@ -506,14 +531,9 @@ int fa_dwconv3x3_bwd(const float* du2, const float* h1, const float* u1, const f
   if ((int64_t)B * H * W * C == 0) return FA_OK;
   int nstrips; dim3 grid;
   const StripGeom g = make_strips(B, H, W, C, nstrips, grid);
-  dwconv_strip_kernel<true><<<grid, dim3(32, 8), 0, st>>>(du2, w, nullptr, u1, du1, nullptr, g, nstrips);
-  FA_LAUNCH_CHECK("fa_dwconv3x3_bwd(data)");
-  if (dw) {
-    FA_REQUIRE(h1, "fa_dwconv3x3_bwd: h1 required for the weight gradient");
-    fa_count_launch(FA_K_DWCONV);
-    dwconv_wgrad_strip_kernel<<<grid, dim3(32, 8), 0, st>>>(du2, h1, dw, db, g, nstrips);
-    FA_LAUNCH_CHECK("fa_dwconv3x3_bwd(weight)");
-  }
+  FA_REQUIRE(!dw || h1, "fa_dwconv3x3_bwd: h1 required for the weight gradient");
+  dwconv_bwd_strip_kernel<<<grid, dim3(32, 8), 0, st>>>(du2, h1, u1, w, du1, dw, db, g, nstrips);
+  FA_LAUNCH_CHECK("fa_dwconv3x3_bwd");
   return FA_OK;
 }
 
