@@ -48,7 +48,7 @@ def gemm_cases():
                   (f'dec{res}/{dim} leff1', T, 4 * dim, dim), (f'dec{res}/{dim} leff2', T, dim, 4 * dim)]
     for res, dim in [(128, 28), (64, 56), (32, 112), (16, 224), (8, 448)]:
         T = 3 * B * res * res
-        cases += [(f'enc{res}/{dim} kv', T, 2 * dim, dim), (f'enc{res}/{dim} leff1', T, 4 * dim, dim)]
+        cases += [(f'enc{res}/{dim} q', T, dim, dim), (f'enc{res}/{dim} kv', T, 2 * dim, dim), (f'enc{res}/{dim} leff1', T, 4 * dim, dim)]
     cases += [('head 448->65536', B * 64, 65536, 448)]
     return cases
 
