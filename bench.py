@@ -314,7 +314,11 @@ def main():
                     'launches_per_step': gemm_n, 'avg_launch_ms': gemm_ms / max(gemm_n, 1),
                     'algorithmic_gflop_per_step': flops / 1e9, 'share_of_step': gemm_ms / (ms / K),
                     'peak_source': 'dense TF32 cuBLAS 8192^3 measured in this run (MEASURED_PEAKS.json holds bf16 only: '
-                                   'the contractions run fp32/tf32, SURVEY.md section 8d)'}
+                                   'the contractions run fp32/tf32, SURVEY.md section 8d)',
+                    'note': 'achieved counts ALGORITHMIC flops (2MNK); the product path issues 3 tf32 MMAs per product '
+                            '(error-compensated 3xTF32, needed for the 1e-3 parity bar), so the tensor pipe does 3x this '
+                            'work: ncu shows it 47-49 % active on the compute-class shapes (profiles/r1_ncu_gemm_*.txt); '
+                            'K <= 224 layers at the 128^2 / 64^2 levels are HBM-bound (2.3-3.2 TB/s, tools/bench_kernels.py)'}
     if dist is not None:
         dist.barrier()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
