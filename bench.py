@@ -200,7 +200,7 @@ def run_inference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='freqair', choices=['freqair', 'reference'])
     ap.add_argument('--batch', type=int, default=BATCH, help='crops per GPU (the headline config uses 16)')
@@ -324,9 +324,11 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         sb = 2
-        t = oracle_train_step_time(sb, cores, 1)
+        oracle_train_step_time(sb, cores, 1)                 # warm-up (allocator, thread pool)
+        t = oracle_train_step_time(sb, cores, 3)
         cpu_baseline = {'value': sb / t, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                        'sample': f'oracle/ CPU restatement of the same train step at batch {sb} (1 step, {t:.1f} s)'}
+                        'sample': f'oracle/ CPU restatement of the same train step at batch {sb} (best of 3 steps after 1 '
+                                  f'warm-up, {t:.1f} s/step; CPU step time is linear in batch)'}
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
                 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
