@@ -120,9 +120,124 @@ __global__ void __launch_bounds__(256) sft_bwd_kernel(const float* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------- band-weight (lambda) predictor of one decoder block
+// e = fc_w (s * ln_w + ln_b) + fc_b ;  h = lrelu(W0 e + b0, 0.1) ;  out = W2 h + b2      (decoder_Uformer.py:178-193,280-284
+// with the LayerNorm statistics and the token mean hoisted out: s = mean_tokens(LN_noaffine(inter)), shared by all blocks)
+// One CTA per sample; heads <= 32, D <= 1024.  ~10 torch kernels forward and ~25 backward per (block, band) otherwise.
+struct CoefP {
+  const float *ln_w, *ln_b, *fc_w, *fc_b, *w0, *b0, *w2, *b2;
+};
+struct CoefG {
+  float *ln_w, *ln_b, *fc_w, *fc_b, *w0, *b0, *w2, *b2;
+};
+
+__device__ __forceinline__ void coef_forward(const float* __restrict__ s, const CoefP& p, int D, int heads, float* z,
+                                             float* e, float* pre, float* h) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for (int d = tid; d < D; d += blockDim.x) z[d] = s[d] * p.ln_w[d] + p.ln_b[d];
+  __syncthreads();
+  for (int j = w; j < heads; j += (blockDim.x >> 5)) {
+    float a = 0.f;
+    for (int d = lane; d < D; d += 32) a = fmaf(p.fc_w[(int64_t)j * D + d], z[d], a);
+    a = warp_sum(a);
+    if (lane == 0) e[j] = a + p.fc_b[j];
+  }
+  __syncthreads();
+  if (tid < heads) {
+    float a = p.b0[tid];
+    for (int i = 0; i < heads; ++i) a = fmaf(p.w0[tid * heads + i], e[i], a);
+    pre[tid] = a;
+    h[tid] = a > 0.f ? a : 0.1f * a;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) band_coef_fwd_kernel(const float* __restrict__ stats, CoefP p, float* __restrict__ out,
+                                                            int D, int heads, int64_t ld_b, int64_t ld_h) {
+  __shared__ float z[1024], e[32], pre[32], h[32];
+  const int b = blockIdx.x;
+  coef_forward(stats + (int64_t)b * D, p, D, heads, z, e, pre, h);
+  if (threadIdx.x < heads) {
+    float a = p.b2[threadIdx.x];
+    for (int i = 0; i < heads; ++i) a = fmaf(p.w2[threadIdx.x * heads + i], h[i], a);
+    out[b * ld_b + threadIdx.x * ld_h] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256) band_coef_bwd_kernel(const float* __restrict__ stats, CoefP p,
+                                                            const float* __restrict__ dout, int64_t ld_b, int64_t ld_h,
+                                                            float* __restrict__ dstats, CoefG g, int D, int heads) {
+  __shared__ float z[1024], e[32], pre[32], h[32], dh[32], dpre[32], de[32], dz[1024];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* s = stats + (int64_t)b * D;
+  coef_forward(s, p, D, heads, z, e, pre, h);
+  if (tid < heads) {
+    const float go = dout[b * ld_b + tid * ld_h];
+    atomicAdd(&g.b2[tid], go);
+    for (int i = 0; i < heads; ++i) atomicAdd(&g.w2[tid * heads + i], go * h[i]);
+    dh[tid] = go;                 // reused below as dout
+  }
+  __syncthreads();
+  if (tid < heads) {
+    float a = 0.f;
+    for (int j = 0; j < heads; ++j) a = fmaf(p.w2[j * heads + tid], dh[j], a);
+    dpre[tid] = a * (pre[tid] > 0.f ? 1.0f : 0.1f);
+  }
+  __syncthreads();
+  if (tid < heads) {
+    atomicAdd(&g.b0[tid], dpre[tid]);
+    for (int i = 0; i < heads; ++i) atomicAdd(&g.w0[tid * heads + i], dpre[tid] * e[i]);
+    float a = 0.f;
+    for (int j = 0; j < heads; ++j) a = fmaf(p.w0[j * heads + tid], dpre[j], a);
+    de[tid] = a;
+    atomicAdd(&g.fc_b[tid], a);
+  }
+  __syncthreads();
+  for (int d = tid; d < D; d += blockDim.x) {
+    float a = 0.f;
+    for (int j = 0; j < heads; ++j) {
+      atomicAdd(&g.fc_w[(int64_t)j * D + d], de[j] * z[d]);
+      a = fmaf(p.fc_w[(int64_t)j * D + d], de[j], a);
+    }
+    atomicAdd(&g.ln_w[d], a * s[d]);
+    atomicAdd(&g.ln_b[d], a);
+    if (dstats) atomicAdd(&dstats[(int64_t)b * D + d], a * p.ln_w[d]);
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int fa_band_coef_fwd(const float* stats, const float* const* params, float* out, int B, int D, int heads, int64_t ld_b,
+                     int64_t ld_h, fa_stream_t stream) {
+  FA_REQUIRE(stats && params && out, "fa_band_coef_fwd: null pointer");
+  FA_REQUIRE(D >= 1 && D <= 1024 && heads >= 1 && heads <= 32, "fa_band_coef_fwd: D=%d (<=1024), heads=%d (<=32)", D, heads);
+  for (int i = 0; i < 8; ++i) FA_REQUIRE(params[i], "fa_band_coef_fwd: null parameter %d", i);
+  if (B == 0) return FA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_ELEMWISE, st);
+  CoefP p{params[0], params[1], params[2], params[3], params[4], params[5], params[6], params[7]};
+  band_coef_fwd_kernel<<<B, 256, 0, st>>>(stats, p, out, D, heads, ld_b, ld_h);
+  FA_LAUNCH_CHECK("fa_band_coef_fwd");
+  return FA_OK;
+}
+
+int fa_band_coef_bwd(const float* stats, const float* const* params, const float* dout, int64_t ld_b, int64_t ld_h,
+                     float* dstats, float* const* grads, int B, int D, int heads, fa_stream_t stream) {
+  FA_REQUIRE(stats && params && dout && grads, "fa_band_coef_bwd: null pointer");
+  FA_REQUIRE(D >= 1 && D <= 1024 && heads >= 1 && heads <= 32, "fa_band_coef_bwd: D=%d (<=1024), heads=%d (<=32)", D, heads);
+  for (int i = 0; i < 8; ++i) FA_REQUIRE(params[i] && grads[i], "fa_band_coef_bwd: null parameter / gradient %d", i);
+  if (B == 0) return FA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_ELEMWISE, st);
+  CoefP p{params[0], params[1], params[2], params[3], params[4], params[5], params[6], params[7]};
+  CoefG g{grads[0], grads[1], grads[2], grads[3], grads[4], grads[5], grads[6], grads[7]};
+  band_coef_bwd_kernel<<<B, 256, 0, st>>>(stats, p, dout, ld_b, ld_h, dstats, g, D, heads);
+  FA_LAUNCH_CHECK("fa_band_coef_bwd");
+  return FA_OK;
+}
+
 
 int fa_act_fwd(const float* x, float* y, int64_t n, int act, float p, fa_stream_t stream) {
   FA_REQUIRE(x && y, "fa_act_fwd: null pointer");

@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import ops
 from .lewin import DecoderBlockFn
 from .uformer_parts import (WIN, Downsample, InputProj, LinearProjection, OutputProj, Upsample, draw_drop_path,
                             init_uformer_weights, leff_params, relative_position_index, trunc_normal_)
@@ -60,11 +61,19 @@ class WindowAttention(nn.Module):
         self.qkv = LinearProjection(dim, num_heads, dim // num_heads, bias=True)
         self.proj = nn.Linear(dim, dim)
 
+    def _predictor_params(self, i):
+        ln, fc, m = self.mlp_head[i][0], self.mlp_head[i][1], self.mlp[i]
+        return (ln.weight, ln.bias, fc.weight, fc.bias, m[0].weight, m[0].bias, m[2].weight, m[2].bias)
+
     def band_coefficients(self, inter_stats):
         """[B, heads, num_bands] filter coefficients (band 0 unused -> 0) from the shared per-band
         token-mean of the normalised encoder features ``inter_stats[i]`` [B, 448]."""
         if not self.num_bands:
             return None
+        if inter_stats[1].is_cuda:
+            # one fused kernel per band (forward) / per band (backward) instead of ~10 + ~25 tiny torch kernels
+            flat = [p for i in range(1, self.num_bands) for p in self._predictor_params(i)]
+            return BandCoefFn.apply(self.num_bands, self.num_heads, *inter_stats[1:self.num_bands], *flat)
         cols = [torch.zeros_like(inter_stats[1][:, :1]).expand(-1, self.num_heads)]
         for i in range(1, self.num_bands):
             ln, fc = self.mlp_head[i][0], self.mlp_head[i][1]
@@ -72,6 +81,40 @@ class WindowAttention(nn.Module):
             e = self.mlp[i][2](F.leaky_relu(self.mlp[i][0](e), 0.1))
             cols.append(e)
         return torch.stack(cols, -1).contiguous()
+
+
+class BandCoefFn(torch.autograd.Function):
+    """coef[B, heads, nb] = the lambda predictors of bands 1..nb-1 (band 0 -> 0), fa_band_coef_fwd/bwd.
+    Arguments after (nb, heads): nb-1 statistics tensors [B, D], then 8 parameters per band."""
+
+    @staticmethod
+    def forward(ctx, nb, heads, *args):
+        stats = [t.contiguous() for t in args[:nb - 1]]
+        params = args[nb - 1:]
+        coef = torch.zeros(stats[0].shape[0], heads, nb, device=stats[0].device, dtype=torch.float32)
+        for i in range(1, nb):
+            ops.band_coef_fwd(stats[i - 1], [p.contiguous() for p in params[8 * (i - 1):8 * i]], coef, i)
+        ctx.nb, ctx.heads = nb, heads
+        ctx.params = params
+        ctx.save_for_backward(*stats)
+        return coef
+
+    @staticmethod
+    def backward(ctx, dcoef):
+        from .lewin import _wbuf, _ready
+        stats = ctx.saved_tensors
+        nb = ctx.nb
+        dcoef = dcoef.contiguous()
+        dstats, gret = [], []
+        for i in range(1, nb):
+            ps = ctx.params[8 * (i - 1):8 * i]
+            bufs = [_wbuf(p) for p in ps]
+            ds = torch.zeros_like(stats[i - 1]) if ctx.needs_input_grad[2 + i - 1] else None
+            ops.band_coef_bwd(stats[i - 1], [p.contiguous() for p in ps], dcoef, i, ds, [b[0] for b in bufs])
+            _ready(*ps)
+            dstats.append(ds)
+            gret += [b[1] for b in bufs]
+        return (None, None, *dstats, *gret)
 
 
 class LeWinTransformerBlock(nn.Module):

@@ -47,6 +47,10 @@ class MoCo(nn.Module):
             self.queue[i] = nn.functional.normalize(self.queue[i], dim=0)
         self.register_buffer('queue_ptr', torch.zeros(1, dtype=torch.long))
         self._flat_q = self._flat_k = None
+        # the key encoder (no gradient) is independent of the query encoder: run it on a side stream so that its
+        # latency-bound kernels (small grids at the 16x16 / 8x8 levels) fill the gaps of the query branch
+        self.key_stream = None
+        self.overlap_key_encoder = True
 
     def _ensure_flat(self):
         pq = list(self.encoder_q.parameters())
@@ -75,13 +79,24 @@ class MoCo(nn.Module):
 
     def forward(self, im_q, im_k):
         if self.training:
+            side = None
+            if self.overlap_key_encoder and im_q.is_cuda:
+                if self.key_stream is None:
+                    self.key_stream = torch.cuda.Stream()
+                side = self.key_stream
+                side.wait_stream(torch.cuda.current_stream())
+            with torch.no_grad(), torch.cuda.stream(side):
+                self._momentum_update_key_encoder()
+                _, k, _ = self.encoder_k(im_k)
+                k = [nn.functional.normalize(ki, dim=1) for ki in k]
             embedding, q, inter = self.encoder_q(im_q)
             n = min(self.num_losses, len(q))
             q = [nn.functional.normalize(q[i], dim=1) for i in range(n)]
-            with torch.no_grad():
-                self._momentum_update_key_encoder()
-                _, k, _ = self.encoder_k(im_k)
-                k = [nn.functional.normalize(k[i], dim=1) for i in range(n)]
+            if side is not None:
+                torch.cuda.current_stream().wait_stream(side)
+                for ki in k:
+                    ki.record_stream(torch.cuda.current_stream())
+            k = k[:n]
             logits, labels = [], []
             for i in range(n):
                 l_pos = torch.einsum('nc,nc->n', [q[i], k[i]]).unsqueeze(-1)

@@ -441,3 +441,28 @@ def adam_step_dev(p, g, m, v, hyper, beta1, beta2, eps, grad_scale=1.0):
     """Adam with {lr/(1-b1^t), 1/sqrt(1-b2^t)} read from the 2-float device tensor ``hyper`` (graph-replay safe)."""
     _f32(p, g, m, v, hyper)
     _call('fa_adam_step_dev', _p(p), _p(g), _p(m), _p(v), p.numel(), _p(hyper), beta1, beta2, eps, grad_scale, _stream())
+
+
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        _f32(t)
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def band_coef_fwd(stats, params, out, band):
+    """out[:, :, band] = lambda predictor of one band; params = (ln_w, ln_b, fc_w, fc_b, w0, b0, w2, b2)."""
+    _f32(stats)
+    B, D = stats.shape
+    heads, nb = out.shape[1], out.shape[2]
+    _call('fa_band_coef_fwd', _p(stats), _ptr_array(params), ctypes.c_void_p(out.data_ptr() + 4 * band), B, D, heads,
+          heads * nb, nb, _stream())
+
+
+def band_coef_bwd(stats, params, dout, band, dstats, grads):
+    _f32(stats, dout, dstats)
+    B, D = stats.shape
+    heads, nb = dout.shape[1], dout.shape[2]
+    _call('fa_band_coef_bwd', _p(stats), _ptr_array(params), ctypes.c_void_p(dout.data_ptr() + 4 * band), heads * nb, nb,
+          _p(dstats), _ptr_array(grads), B, D, heads, _stream())

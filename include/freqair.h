@@ -207,6 +207,17 @@ int fa_sft_fuse_fwd(const float* x, const float* dcn, const float* gamma, const 
 int fa_sft_fuse_bwd(const float* x, const float* dcn, const float* gamma, const float* beta, const float* dout,
                     float* dx, float* ddcn, float* dgamma, float* dbeta, int64_t n, float slope, fa_stream_t stream);
 
+/* ------------------------------------------------------------------ band-weight (lambda) predictor (a10)
+ * out[b][h] (at out + b*ld_b + h*ld_h) = W2 lrelu(W0 (fc_w (stats[b] * ln_w + ln_b) + fc_b) + b0, 0.1) + b2 with
+ * stats [B, D] = the token mean of the affine-free LayerNorm of one band's encoder features.
+ * params / grads: 8 HOST-side arrays of device pointers {ln_w[D], ln_b[D], fc_w[heads,D], fc_b[heads], w0[heads,heads],
+ * b0[heads], w2[heads,heads], b2[heads]}.  bwd ACCUMULATES into grads[i] and dstats [B, D] (dstats may be NULL).
+ * ref: WindowAttention.__init__ / forward, decoder_Uformer.py:178-193,280-284 (mlp_head[i], avg[i], mlp[i]). */
+int fa_band_coef_fwd(const float* stats, const float* const* params, float* out, int B, int D, int heads, int64_t ld_b,
+                     int64_t ld_h, fa_stream_t stream);
+int fa_band_coef_bwd(const float* stats, const float* const* params, const float* dout, int64_t ld_b, int64_t ld_h,
+                     float* dstats, float* const* grads, int B, int D, int heads, fa_stream_t stream);
+
 /* ------------------------------------------------------------------ elementwise / loss / optimiser (K10, K11)
  * y = act(x) and dx = dy * act'(x) */
 int fa_act_fwd(const float* x, float* y, int64_t n, int act, float p, fa_stream_t stream);

@@ -193,6 +193,31 @@ def test_conv3x3_out(ops, C, Co, H, W):
     close(db, b.grad, 2e-5, 'conv3x3_out db')
 
 
+@pytest.mark.parametrize('B,D,heads,nb', [(3, 448, 16, 3), (2, 448, 1, 3), (5, 100, 4, 2)])
+def test_band_coef(ops, B, D, heads, nb):
+    """Fused lambda predictor (LN affine -> fc -> Linear, LeakyReLU(0.1), Linear) and its backward vs torch."""
+    band = nb - 1
+    s = gen(B, D).requires_grad_(True)
+    shapes = [(D,), (D,), (heads, D), (heads,), (heads, heads), (heads,), (heads, heads), (heads,)]
+    ps = [(gen(*sh, seed=10 + i) * (0.2 if len(sh) == 2 else 1.0)).requires_grad_(True) for i, sh in enumerate(shapes)]
+    e = F.linear(s * ps[0] + ps[1], ps[2], ps[3])
+    ref = F.linear(F.leaky_relu(F.linear(e, ps[4], ps[5]), 0.1), ps[6], ps[7])
+    dout = gen(B, heads, nb, seed=5)
+    ref.backward(dout[:, :, band])
+    dps = [dev(p.detach()) for p in ps]
+    out = torch.zeros(B, heads, nb, device='cuda')
+    ops.band_coef_fwd(dev(s.detach()), dps, out, band)
+    close(out[:, :, band], ref, 2e-4, 'band_coef fwd')
+    assert out[:, :, :band].abs().max().item() == 0
+    ds = torch.zeros(B, D, device='cuda')
+    init = [gen(*sh, seed=30 + i) for i, sh in enumerate(shapes)]      # kernels accumulate into the gradient buffers
+    gs = [dev(t.clone()) for t in init]
+    ops.band_coef_bwd(dev(s.detach()), dps, dev(dout), band, ds, gs)
+    close(ds, s.grad, 2e-4, 'band_coef dstats')
+    for i, (g, p, g0) in enumerate(zip(gs, ps, init)):
+        close(g.cpu() - g0, p.grad, 2e-4, f'band_coef grad {i}')
+
+
 def test_pixel_shuffle_and_layout(ops):
     B, H, W, Ci, Co = 2, 4, 4, 16, 8
     x = gen(B, H * W, Ci)
