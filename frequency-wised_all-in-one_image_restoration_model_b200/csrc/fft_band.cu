@@ -182,6 +182,53 @@ __global__ void __launch_bounds__(256) band_energy_generic_kernel(const float* _
     atomicAdd(&out[((map / maps_per_group) * heads + map % heads) * nbands + threadIdx.x], ebin[threadIdx.x]);
 }
 
+
+// Spectral L1 (train.py:70,91): mean | decompose(a) - decompose(b) | with inverse=False.  The band masks partition the
+// spectrum and the FFT is linear, so the [nb, maps, n, n, 2] stack never exists: with F = fft2(a - b)
+//   loss = (1 / (nb * maps * n^2 * 2)) * sum over banded bins (|Re F| + |Im F|)
+//   dloss/da = Re(sum_k (sign Re F_k + i sign Im F_k) e^{+i theta}) = n^2 * irfft2(sign spectrum)   (Hermitian)
+// One CTA per map: read a, b once, write the gradient once.
+__global__ void __launch_bounds__(256) spectral_l1_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                          float* __restrict__ loss, float* __restrict__ grad,
+                                                          int64_t nmaps, int n, int logn,
+                                                          const uint8_t* __restrict__ band_of_bin, int nbands,
+                                                          float gscale) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red[8];
+  GenSmem s = gen_carve(smem, n);
+  const int nh = n / 2 + 1, rs = n + 1;
+  const int64_t map = blockIdx.x;
+  const float* am = a + map * n * n;
+  const float* bm = b + map * n * n;
+  for (int i = threadIdx.x; i < n * n; i += blockDim.x) s.re[(i / n) * rs + (i % n)] = am[i] - bm[i];
+  __syncthreads();
+  gen_forward(s, n, logn);
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n * nh; i += blockDim.x) {
+    const int u = i / nh, k = i % nh;
+    const bool edge = (k == 0 || k == n / 2);
+    float2 v = s.sp[i];
+    if (edge && (u == 0 || u == n / 2)) v.y = 0.f;          // self-conjugate bins are real
+    if (band_of_bin[i] >= nbands) v = make_float2(0.f, 0.f);
+    acc += (edge ? 1.0f : 2.0f) * (fabsf(v.x) + fabsf(v.y));
+    s.sp[i] = make_float2(v.x > 0.f ? 1.f : (v.x < 0.f ? -1.f : 0.f), v.y > 0.f ? 1.f : (v.y < 0.f ? -1.f : 0.f));
+  }
+  const float inv = 1.0f / ((float)nbands * (float)nmaps * (float)n * (float)n * 2.0f);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    atomicAdd(loss, t * inv);
+  }
+  if (!grad) return;
+  gen_inverse(s, n, logn);                                   // normalised by 1/n^2
+  const float gs = gscale * inv * (float)n * (float)n;
+  float* gm = grad + map * n * n;
+  for (int i = threadIdx.x; i < n * n; i += blockDim.x) gm[i] = s.re[(i / n) * rs + (i % n)] * gs;
+}
+
 // ------------------------------------------------------------------ n = 64 fast path (288 threads)
 __global__ void __launch_bounds__(288) band64_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t nmaps,
                                                      const uint8_t* __restrict__ band_of_bin, int nbands, int mode,
@@ -296,6 +343,21 @@ int fa_band_energy(const float* a, const float* b, float* out, int64_t nmaps, in
   band_energy_generic_kernel<<<(unsigned)nmaps, 256, smem, st>>>(a, b, out, n, ilog2(n), band_of_bin, nbands,
                                                                  maps_per_group, heads);
   FA_LAUNCH_CHECK("fa_band_energy");
+  return FA_OK;
+}
+
+int fa_spectral_l1(const float* a, const float* b, float* loss, float* grad, int64_t nmaps, int n,
+                   const uint8_t* band_of_bin, int nbands, float gscale, fa_stream_t stream) {
+  FA_REQUIRE(a && b && loss && band_of_bin, "fa_spectral_l1: null pointer");
+  FA_REQUIRE(pow2_ok(n), "fa_spectral_l1: n=%d unsupported (power of two in 8..128)", n);
+  FA_REQUIRE(nbands >= 1 && nbands <= 255, "fa_spectral_l1: nbands=%d unsupported (1..255)", nbands);
+  FA_REQUIRE(nmaps > 0 && nmaps < (1ll << 31), "fa_spectral_l1: bad map count");
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_BAND_FILTER, st);
+  const size_t smem = gen_smem_bytes(n, 256);
+  FA_CUDA(cudaFuncSetAttribute(spectral_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  spectral_l1_kernel<<<(unsigned)nmaps, 256, smem, st>>>(a, b, loss, grad, nmaps, n, ilog2(n), band_of_bin, nbands, gscale);
+  FA_LAUNCH_CHECK("fa_spectral_l1");
   return FA_OK;
 }
 

@@ -427,6 +427,17 @@ def l1_loss(a, b, want_grad=True, gscale=1.0):
     return loss, grad
 
 
+def spectral_l1(a, b, bob, nbands, want_grad=True, gscale=1.0):
+    """(loss[1], grad) of mean|D(a) - D(b)| over the [nbands, ..., n, n, 2] spectrum stack (train.py:91)."""
+    _f32(a, b)
+    n = a.shape[-1]
+    assert a.shape == b.shape and a.shape[-2] == n
+    loss = torch.zeros(1, device=a.device, dtype=torch.float32)
+    grad = torch.empty_like(a) if want_grad else None
+    _call('fa_spectral_l1', _p(a), _p(b), _p(loss), _p(grad), a.numel() // (n * n), n, _p(bob), nbands, gscale, _stream())
+    return loss, grad
+
+
 def momentum_update(k, q, m):
     _f32(k, q)
     _call('fa_momentum_update', _p(k), _p(q), k.numel(), m, _stream())

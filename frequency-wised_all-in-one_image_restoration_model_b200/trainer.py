@@ -10,7 +10,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from .losses import l1_loss
+from .losses import l1_loss, spectral_l1_loss
 from .net import lewin
 
 
@@ -139,12 +139,27 @@ class BucketedAllReduce:
 
 
 class TrainStep:
+    """The body of the reference's training loop (train.py:80-96).
+
+    ``encoder_only=True`` is the first phase (``epoch < opt.epochs_encoder``, train.py:84-87): contrastive loss on
+    ``net.E`` alone; the decoder receives no gradient and - as torch.optim.Adam skips parameters without a gradient -
+    neither its weights nor its Adam state / step count move.  ``num_frequency_bands_l1 != -1`` adds the spectral L1
+    term of train.py:69-70,90-91 with weight ``frequency_l1_loss_weight``."""
+
     def __init__(self, net, lr=2e-4, contrast_loss_weight=0.6, betas=(0.9, 0.999), eps=1e-8, distributed=False,
-                 bucket_mb=64):
+                 bucket_mb=64, encoder_only=False, num_frequency_bands_l1=-1, frequency_l1_loss_weight=0.1,
+                 patch_size=128):
         self.net = net
         self.lr, self.betas, self.eps = lr, betas, eps
         self.w = contrast_loss_weight
-        self.t = 0
+        self.encoder_only = encoder_only
+        self.w_freq = frequency_l1_loss_weight
+        self.decompose = None
+        if num_frequency_bands_l1 != -1:
+            from .net.utils.frequency_decompose import FrequencyDecompose
+            self.decompose = FrequencyDecompose('frequency_decompose', 1. / num_frequency_bands_l1, patch_size, patch_size,
+                                                inverse=False)                       # train.py:70
+        self.ts = [0, 0]                # Adam step count of the encoder / decoder segment
         moco = net.E.E
         fq, _ = moco._ensure_flat()
         enc_params = [p for p in moco.encoder_q.parameters()]
@@ -162,8 +177,16 @@ class TrainStep:
         self.static_in = None
         self.static_out = None
         dev = self.segments[0].flat.device
-        self.hyper = torch.zeros(2, device=dev, dtype=torch.float32)
-        self.hyper_host = torch.zeros(2, dtype=torch.float32).pin_memory() if dev.type == 'cuda' else torch.zeros(2)
+        self.hyper = torch.zeros(4, device=dev, dtype=torch.float32)
+        self.hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory() if dev.type == 'cuda' else torch.zeros(4)
+
+    @property
+    def t(self):
+        return self.ts[0]
+
+    @t.setter
+    def t(self, v):
+        self.ts = [v, v]
 
     def zero_grad(self):
         for s in self.segments:
@@ -173,28 +196,47 @@ class TrainStep:
         n = len(logits)
         ce = sum(F.cross_entropy(logits[i], labels[i]) for i in range(n)) / n        # train.py:88
         l1 = l1_loss(restored, clean)                                                # train.py:89
+        if self.decompose is not None:                                               # train.py:90-91
+            l1 = l1 + self.w_freq * spectral_l1_loss(restored, clean, self.decompose)
         return l1 + self.w * ce, l1, ce                                              # train.py:92
+
+    def _active(self):
+        return self.segments[:1] if self.encoder_only else self.segments
 
     def _body(self, x_query, x_key, clean, use_hyper):
         self.zero_grad()
-        restored, logits, labels = self.net(x_query, x_key)
-        loss, l1, ce = self.loss(restored, logits, labels, clean)
+        if self.encoder_only:                                                        # train.py:84-87
+            _, logits, labels, _ = self.net.E(x_query, x_key)
+            n = len(logits)
+            loss = ce = sum(F.cross_entropy(logits[i], labels[i]) for i in range(n)) / n
+            l1 = torch.zeros((), device=ce.device)
+        else:
+            restored, logits, labels = self.net(x_query, x_key)
+            loss, l1, ce = self.loss(restored, logits, labels, clean)
         loss.backward()
         if self.ddp is not None:
             self.ddp.finish()
         gscale = 1.0 / self.ddp.world if self.ddp is not None else 1.0       # mean over ranks, fused into Adam
-        for s in self.segments:
+        for i, s in enumerate(self._active()):
             if use_hyper:
-                ops.adam_step_dev(s.flat, s.grad, s.m, s.v, self.hyper, self.betas[0], self.betas[1], self.eps, gscale)
+                ops.adam_step_dev(s.flat, s.grad, s.m, s.v, self.hyper[2 * i:2 * i + 2], self.betas[0], self.betas[1],
+                                  self.eps, gscale)
             else:
-                ops.adam_step(s.flat, s.grad, s.m, s.v, self.lr, self.betas[0], self.betas[1], self.eps, self.t, gscale)
+                ops.adam_step(s.flat, s.grad, s.m, s.v, self.lr, self.betas[0], self.betas[1], self.eps, self.ts[i], gscale)
         return dict(loss=loss.detach(), l1=l1.detach(), ce=ce.detach())
 
+    def _tick(self, d=1):
+        for i in range(len(self._active())):
+            self.ts[i] += d
+
     def _advance(self):
-        """t += 1 and the step-dependent Adam scalars {lr/(1-b1^t), 1/sqrt(1-b2^t)} pushed to the device."""
-        self.t += 1
-        self.hyper_host[0] = self.lr / (1.0 - self.betas[0] ** self.t)
-        self.hyper_host[1] = 1.0 / (1.0 - self.betas[1] ** self.t) ** 0.5
+        """step counts += 1 and the step-dependent Adam scalars {lr/(1-b1^t), 1/sqrt(1-b2^t)} of each segment pushed to
+        the device."""
+        self._tick()
+        for i, t in enumerate(self.ts):
+            if t >= 1:
+                self.hyper_host[2 * i] = self.lr / (1.0 - self.betas[0] ** t)
+                self.hyper_host[2 * i + 1] = 1.0 / (1.0 - self.betas[1] ** t) ** 0.5
         self.hyper.copy_(self.hyper_host, non_blocking=True)
 
     def step(self, x_query, x_key, clean):
@@ -207,7 +249,7 @@ class TrainStep:
             self.graph.replay()
             self.last = self.static_out
             return self.last['loss']
-        self.t += 1
+        self._tick()
         self.last = self._body(x_query, x_key, clean, False)
         return self.last['loss']
 
@@ -231,7 +273,7 @@ class TrainStep:
         with torch.cuda.graph(graph):
             self.static_out = self._body(*self.static_in, True)
         self.graph_launches = ops.launch_count() - n0        # libfreqair kernels recorded in the graph (per replay)
-        self.t -= 1                     # capture records the step without executing it
+        self._tick(-1)                  # capture records the step without executing it
         self.graph = graph
         self.last = self.static_out
         return self.static_out['loss']

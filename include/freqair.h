@@ -85,6 +85,12 @@ int fa_band_filter(const float* x, float* y, int64_t nmaps, int n, const uint8_t
                    const float* coef, int maps_per_group, int heads, fa_stream_t stream);
 int fa_band_energy(const float* a, const float* b, float* out, int64_t nmaps, int n, const uint8_t* band_of_bin,
                    int nbands, int maps_per_group, int heads, fa_stream_t stream);
+/* Spectral L1 term of the loss: loss[0] += mean| D(a) - D(b) | with D = FrequencyDecompose('frequency_decompose',
+ * 1/nbands, n, n, inverse=False), i.e. the mean over the [nbands, maps, n, n, 2] (re, im) stack; grad (may be NULL) =
+ * gscale * dloss/da.  The bands partition the spectrum, so the stack is never materialised: one fft2 of a - b per map.
+ * ref: train.py:69-70,90-91 + frequency_decompose.py:28-68. */
+int fa_spectral_l1(const float* a, const float* b, float* loss, float* grad, int64_t nmaps, int n,
+                   const uint8_t* band_of_bin, int nbands, float gscale, fa_stream_t stream);
 /* mean / residual split (frequency_decompose.py:109-118): y[0]=mean broadcast, y[1]=x-mean */
 int fa_dc_split(const float* x, float* y, int64_t nmaps, int n, fa_stream_t stream);
 

@@ -218,6 +218,28 @@ def test_band_coef(ops, B, D, heads, nb):
         close(g.cpu() - g0, p.grad, 2e-4, f'band_coef grad {i}')
 
 
+@pytest.mark.parametrize('n,nb,maps', [(128, 4, 6), (16, 2, 5), (64, 8, 3)])
+def test_spectral_l1(ops, n, nb, maps):
+    """Spectral L1 term (train.py:70,91): l1(D(a), D(b)), D = decompose(inverse=False), vs the oracle under autograd.
+    |.| has a sign-discontinuous derivative: a bin whose real or imaginary part is within fp32 FFT round-off of zero
+    may flip, which moves the gradient by 2/n of its typical magnitude - so the gradient is held to relative L2 1e-4
+    and max error 5 % of the typical magnitude; the loss itself to 1e-5 relative."""
+    fd = importlib.import_module(PKG_NAME + '.net.utils.frequency_decompose')
+    a = gen(maps, 1, n, n).requires_grad_(True)
+    b = gen(maps, 1, n, n, seed=1)
+    ref = (freq.decompose(a, 'frequency_decompose', 1. / nb, inverse=False)
+           - freq.decompose(b, 'frequency_decompose', 1. / nb, inverse=False)).abs().mean()
+    ref.backward()
+    bob = fd.half_band_map('frequency_decompose', 1. / nb, n).cuda()
+    loss, grad = ops.spectral_l1(dev(a.detach()), dev(b), bob, nb)
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    g, gr = grad.cpu().double(), a.grad.double()
+    assert (g - gr).norm().item() <= 1e-4 * gr.norm().item() + 2.0 / n * gr.abs().mean().item() * 3
+    assert (g - gr).abs().max().item() <= 0.05 * gr.abs().mean().item() * 4
+    loss2, none = ops.spectral_l1(dev(a.detach()), dev(b), bob, nb, want_grad=False)
+    assert none is None and abs(loss2.item() - loss.item()) <= 1e-6 * abs(loss.item())
+
+
 def test_pixel_shuffle_and_layout(ops):
     B, H, W, Ci, Co = 2, 4, 4, 16, 8
     x = gen(B, H * W, Ci)

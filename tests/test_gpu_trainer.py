@@ -86,3 +86,38 @@ def test_graph_replay_matches_eager_and_adam_matches_torch():
     assert ts.graph_launches > 1000
     for a, b in zip(eager_losses, graph_losses):
         assert abs(a - b) <= 2e-4 * max(abs(a), 1.0), (eager_losses, graph_losses)
+
+
+def test_encoder_only_phase_and_spectral_l1_term():
+    """train.py:84-87 (encoder phase: contrastive loss only; decoder weights and Adam state untouched) and
+    train.py:90-91 (spectral L1 term) against torch autograd on the oracle's decompose."""
+    from oracle import freq
+    trainer = importlib.import_module(PKG_NAME + '.trainer')
+    net, ts, x = build()
+    ts.encoder_only = True
+    dec0 = ts.segments[1].flat.clone()
+    enc0 = ts.segments[0].flat.clone()
+    l = ts.step(*x)
+    assert torch.isfinite(l).all() and ts.last['l1'].item() == 0.0
+    assert torch.equal(ts.segments[1].flat, dec0) and ts.segments[1].m.abs().max().item() == 0
+    assert not torch.equal(ts.segments[0].flat, enc0)
+    assert ts.ts == [1, 0]
+    ts.capture(*x, warmup=0)                       # the encoder-only step is graph-capturable as well
+    l2 = ts.step(*x)
+    assert torch.isfinite(l2).all() and ts.ts == [2, 0] and torch.equal(ts.segments[1].flat, dec0)
+
+    net, _, x = build()
+    ts = trainer.TrainStep(net, lr=2e-4, contrast_loss_weight=0.6, num_frequency_bands_l1=4, frequency_l1_loss_weight=0.1)
+    restored = torch.rand(2, 3, 128, 128, device='cuda').requires_grad_(True)
+    logits = [torch.randn(2, 7, device='cuda') for _ in range(3)]
+    labels = [torch.zeros(2, dtype=torch.long, device='cuda') for _ in range(3)]
+    loss, l1, ce = ts.loss(restored, logits, labels, x[2])
+    loss.backward()
+    r = restored.detach().cpu().requires_grad_(True)
+    c = x[2].cpu()
+    D = lambda t: freq.decompose(t, 'frequency_decompose', 0.25, inverse=False)
+    ref = (r - c).abs().mean() + 0.1 * (D(r) - D(c)).abs().mean()
+    ref.backward()
+    assert abs(l1.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    d = (restored.grad.cpu() - r.grad)
+    assert d.norm().item() <= 2e-3 * r.grad.norm().item()
