@@ -97,13 +97,40 @@ __global__ void __launch_bounds__(256) dwconv_strip_kernel(const float* __restri
 // needs, so both come from one window over du2 plus the centre values of h1 and u1: 4.5 passes over the hidden tensor
 // (du2 x1.5, h1, u1, du1) instead of 6.2 for two kernels.  36 + 4 accumulators per thread persist over the strips a
 // thread visits; the 8 strip lanes of a block are reduced in shared memory, one atomic per (channel, tap) per block.
-__global__ void __launch_bounds__(256, 2) dwconv_bwd_strip_kernel(const float* __restrict__ du2,
+//
+// Memory-level parallelism comes from a THREAD-PRIVATE cp.async ring in shared memory (the first version kept every
+// load in registers: 128 registers, spills, 16 warps/SM and 7.5 warps stalled on long-scoreboard per issue at 1.4
+// TB/s).  Step x needs 14 float4 per thread - the du2 column x+1 (DW_R+2 rows), u1 and h1 at column x (DW_R rows
+// each); a thread copies exactly the values it will read itself, so cp.async.wait_group is the only synchronisation.
+// With DWB_RING steps per thread and 256 threads, ~115 KB per SM are always in flight (HBM latency x 6.5 TB/s / 148
+// SMs ~ 45 KB), one persistent block per SM.
+constexpr int DWB_RING = 3;
+constexpr int DWB_SLOT = (DW_R + 2) + 2 * DW_R;                  // float4 per thread per step
+constexpr int DWB_SMEM = DWB_RING * DWB_SLOT * 256 * 16;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool ok) {
+  const int sz = ok ? 16 : 0;                                      // src-size 0: zero fill, nothing is read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256, 1) dwconv_bwd_strip_kernel(const float* __restrict__ du2,
                                                                const float* __restrict__ h1,
                                                                const float* __restrict__ u1,
                                                                const float* __restrict__ w, float* __restrict__ du1,
                                                                float* __restrict__ dw, float* __restrict__ db,
                                                                StripGeom g, int nstrips) {
-  __shared__ float red[8][32][41];
+  extern __shared__ __align__(16) float dwb_smem[];
+  float (*red)[32][41] = reinterpret_cast<float (*)[32][41]>(dwb_smem);          // aliases the ring after the sweep
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(dwb_smem) + tid * 16;
   const int c = (blockIdx.y * 32 + threadIdx.x) * 4;
   const bool cok = c < g.C;
   float4 wv[9], acc[9];
@@ -121,14 +148,46 @@ __global__ void __launch_bounds__(256, 2) dwconv_bwd_strip_kernel(const float* _
       strip_decode(strip, g, b, y0, x0);
       const int64_t img = (int64_t)b * g.H * g.W * g.C + c;
       const float* base = du2 + img;
+      const int x1 = min(g.W, x0 + g.seg);
+      // copies of step x into ring slot s
+      auto issue = [&](int x, int s) {
+        const uint32_t a = ring + (uint32_t)(s * DWB_SLOT) * 4096u;
+        if (x < x1) {                                              // past the strip: an empty group keeps the count
+#pragma unroll
+          for (int rr = 0; rr < DW_R + 2; ++rr) {
+            const int yy = y0 - 1 + rr;
+            const bool ok = x + 1 < g.W && yy >= 0 && yy < g.H;
+            cp_async16(a + rr * 4096u, ok ? base + ((int64_t)yy * g.W + x + 1) * g.C : base, ok);
+          }
+#pragma unroll
+          for (int r = 0; r < DW_R; ++r) {
+            const bool ok = y0 + r < g.H;
+            const int64_t o = ok ? img + ((int64_t)(y0 + r) * g.W + x) * g.C : 0;
+            if (u1) cp_async16(a + (DW_R + 2 + r) * 4096u, u1 + o, ok);
+            if (dw) cp_async16(a + (2 * DW_R + 2 + r) * 4096u, h1 + o, ok);
+          }
+        }
+        cp_async_commit();
+      };
+#pragma unroll
+      for (int s = 0; s < DWB_RING; ++s) issue(x0 + s, s);
       float4 win[3][DW_R + 2];
       strip_loadcol(base, x0 - 1, y0, g, win[1]);
       strip_loadcol(base, x0, y0, g, win[2]);
-      const int x1 = min(g.W, x0 + g.seg);
+      int s = 0;
       for (int x = x0; x < x1; ++x) {
+        cp_async_wait<DWB_RING - 1>();
+        const uint32_t a = ring + (uint32_t)(s * DWB_SLOT) * 4096u;
 #pragma unroll
-        for (int rr = 0; rr < DW_R + 2; ++rr) { win[0][rr] = win[1][rr]; win[1][rr] = win[2][rr]; }
-        strip_loadcol(base, x + 1, y0, g, win[2]);
+        for (int rr = 0; rr < DW_R + 2; ++rr) { win[0][rr] = win[1][rr]; win[1][rr] = win[2][rr]; win[2][rr] = lds4(a + rr * 4096u); }
+        float4 uq[DW_R], hq[DW_R];
+#pragma unroll
+        for (int r = 0; r < DW_R; ++r) {
+          if (u1) uq[r] = lds4(a + (DW_R + 2 + r) * 4096u);
+          if (dw) hq[r] = lds4(a + (2 * DW_R + 2 + r) * 4096u);
+        }
+        issue(x + DWB_RING, s);                                   // the slot's values are in registers now
+        s = (s + 1 == DWB_RING) ? 0 : s + 1;
 #pragma unroll
         for (int r = 0; r < DW_R; ++r) {
           if (y0 + r >= g.H) break;
@@ -139,22 +198,23 @@ __global__ void __launch_bounds__(256, 2) dwconv_bwd_strip_kernel(const float* _
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) d = fma4(win[kx][r + ky], wv[ky * 3 + kx], d);
           if (u1) {
-            const float4 u = ld4(u1 + o);
+            const float4 u = uq[r];
             d = make_float4(d.x * gelu_grad_f(u.x), d.y * gelu_grad_f(u.y), d.z * gelu_grad_f(u.z), d.w * gelu_grad_f(u.w));
           }
           st4(du1 + o, d);
           if (dw) {
-            const float4 hq = ld4(h1 + o);
             const float4 gc = win[1][r + 1];                       // du2[q]
             accb.x += gc.x; accb.y += gc.y; accb.z += gc.z; accb.w += gc.w;
 #pragma unroll
-            for (int t = 0; t < 9; ++t) acc[t] = fma4(win[t % 3][r + t / 3], hq, acc[t]);
+            for (int t = 0; t < 9; ++t) acc[t] = fma4(win[t % 3][r + t / 3], hq[r], acc[t]);
           }
         }
       }
+      cp_async_wait<0>();                                          // only zero-size tail copies are left
     }
   }
   if (!dw) return;                                                  // uniform over the block
+  __syncthreads();                                                  // every thread is done with its ring slots
   const int pl = threadIdx.y, cq = threadIdx.x;
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
@@ -164,7 +224,6 @@ __global__ void __launch_bounds__(256, 2) dwconv_bwd_strip_kernel(const float* _
   }
   red[pl][cq][36] = accb.x; red[pl][cq][37] = accb.y; red[pl][cq][38] = accb.z; red[pl][cq][39] = accb.w;
   __syncthreads();
-  const int tid = threadIdx.y * 32 + threadIdx.x;
   for (int i = tid; i < 32 * 40; i += 256) {
     const int q = i / 40, v = i % 40;
     const int cc = (blockIdx.y * 32 + q) * 4;
@@ -508,6 +567,31 @@ static StripGeom make_strips(int B, int H, int W, int C, int& nstrips, dim3& gri
   return g;
 }
 
+// One persistent block per SM for the ring kernel: pick the strip length (32 or 16 columns) and the block count so
+// that every warp walks the same number of strips (wave quantisation was 13 % of the first version's time).
+static StripGeom make_strips_persistent(int B, int H, int W, int C, int& nstrips, dim3& grid) {
+  const int gy = (C / 4 + 31) / 32;
+  const int max_gx = kNumSMs / gy > 0 ? kNumSMs / gy : 1;
+  StripGeom best{}; double best_eff = -1.0; int best_gx = 1, best_n = 0;
+  for (int seg = 32; seg >= 16; seg >>= 1) {
+    StripGeom g;
+    g.B = B; g.H = H; g.W = W; g.C = C;
+    g.seg = W < seg ? W : seg;
+    g.nys = (H + DW_R - 1) / DW_R;
+    g.nxs = (W + g.seg - 1) / g.seg;
+    const int n = B * g.nys * g.nxs;
+    const int nb = (n + 7) / 8;                                  // blocks' worth of strips (8 warps per block)
+    const int rounds = (nb + max_gx - 1) / max_gx;
+    const int gx = (nb + rounds - 1) / rounds;
+    const double eff = (double)n / ((double)gx * 8 * rounds) * (seg == 32 ? 1.0 : 0.95);   // short strips: more halo
+    if (eff > best_eff) { best_eff = eff; best = g; best_gx = gx; best_n = n; }
+    if (W <= 16) break;
+  }
+  nstrips = best_n;
+  grid = dim3((unsigned)best_gx, (unsigned)gy);
+  return best;
+}
+
 int fa_dwconv3x3_fwd(const float* h1, const float* w, const float* b, float* u2, float* h2, int B, int H, int W, int C,
                      fa_stream_t stream) {
   FA_REQUIRE(h1 && w && u2, "fa_dwconv3x3_fwd: null pointer");
@@ -530,9 +614,14 @@ int fa_dwconv3x3_bwd(const float* du2, const float* h1, const float* u1, const f
   FaProfScope prof(FA_K_DWCONV, st);
   if ((int64_t)B * H * W * C == 0) return FA_OK;
   int nstrips; dim3 grid;
-  const StripGeom g = make_strips(B, H, W, C, nstrips, grid);
+  const StripGeom g = make_strips_persistent(B, H, W, C, nstrips, grid);
   FA_REQUIRE(!dw || h1, "fa_dwconv3x3_bwd: h1 required for the weight gradient");
-  dwconv_bwd_strip_kernel<<<grid, dim3(32, 8), 0, st>>>(du2, h1, u1, w, du1, dw, db, g, nstrips);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FA_CUDA(cudaFuncSetAttribute(dwconv_bwd_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DWB_SMEM));
+    attr_set = true;
+  }
+  dwconv_bwd_strip_kernel<<<grid, dim3(32, 8), DWB_SMEM, st>>>(du2, h1, u1, w, du1, dw, db, g, nstrips);
   FA_LAUNCH_CHECK("fa_dwconv3x3_bwd");
   return FA_OK;
 }

@@ -136,8 +136,8 @@ def test_batchnorm_head(ops):
 
 
 # ----------------------------------------------------------------------------- conv pieces
-def test_dwconv(ops):
-    B, H, W, C = 2, 16, 16, 40
+@pytest.mark.parametrize('B,H,W,C', [(2, 16, 16, 40), (1, 10, 70, 136), (3, 8, 8, 4), (1, 64, 64, 224), (5, 33, 17, 12)])
+def test_dwconv(ops, B, H, W, C):
     u1 = gen(B, H * W, C).requires_grad_(True)
     w, b = (gen(C, 1, 3, 3, seed=1) * 0.3).requires_grad_(True), gen(C, seed=2).requires_grad_(True)
     dh2 = gen(B, H * W, C, seed=3)
