@@ -37,35 +37,74 @@ __device__ __forceinline__ void strip_loadcol(const float* __restrict__ base, in
   }
 }
 
-// BWD = false: u2 = dwconv(h1) + b ; h2 = gelu(u2)
-// BWD = true : du1 = gelu'(u1) * dwconv^T(du2)   (the adjoint is the same stencil with the taps reversed)
-template <bool BWD>
-__global__ void __launch_bounds__(256) dwconv_strip_kernel(const float* __restrict__ in, const float* __restrict__ w,
-                                                           const float* __restrict__ bias, const float* __restrict__ u1,
-                                                           float* __restrict__ outA, float* __restrict__ outB,
-                                                           StripGeom g, int nstrips) {
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool ok) {
+  const int sz = ok ? 16 : 0;                                      // src-size 0: zero fill, nothing is read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+
+// u2 = dwconv(h1) + b ; h2 = gelu(u2).  The input column x+1 of every step comes through a thread-private cp.async
+// ring in shared memory (see the backward kernel below for the reasoning): DWF_RING steps of DW_R+2 float4 per
+// thread stay in flight, DWF_WARPS warps per block, one persistent block per SM.
+constexpr int DWF_WARPS = 12;
+constexpr int DWF_RING = 4;
+constexpr int DWF_SLOT = DW_R + 2;
+constexpr int DWF_THREADS = DWF_WARPS * 32;
+constexpr int DWF_SMEM = DWF_RING * DWF_SLOT * DWF_THREADS * 16;
+
+__global__ void __launch_bounds__(DWF_THREADS, 1) dwconv_strip_kernel(const float* __restrict__ in,
+                                                                      const float* __restrict__ w,
+                                                                      const float* __restrict__ bias,
+                                                                      float* __restrict__ outA, float* __restrict__ outB,
+                                                                      StripGeom g, int nstrips) {
+  extern __shared__ __align__(16) float dwf_smem[];
   const int c = (blockIdx.y * 32 + threadIdx.x) * 4;
   if (c >= g.C) return;
+  constexpr uint32_t PL = DWF_THREADS * 16;                         // bytes between consecutive values of a thread
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(dwf_smem) + (threadIdx.y * 32 + threadIdx.x) * 16;
   float4 wv[9];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const int ti = BWD ? 8 - t : t;
-    wv[t] = make_float4(w[(c + 0) * 9 + ti], w[(c + 1) * 9 + ti], w[(c + 2) * 9 + ti], w[(c + 3) * 9 + ti]);
-  }
-  const float4 bv = (!BWD && bias) ? ld4(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < 9; ++t)
+    wv[t] = make_float4(w[(c + 0) * 9 + t], w[(c + 1) * 9 + t], w[(c + 2) * 9 + t], w[(c + 3) * 9 + t]);
+  const float4 bv = bias ? ld4(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
   for (int strip = blockIdx.x * blockDim.y + threadIdx.y; strip < nstrips; strip += gridDim.x * blockDim.y) {
     int b, y0, x0;
     strip_decode(strip, g, b, y0, x0);
     const int64_t img = (int64_t)b * g.H * g.W * g.C + c;
     const float* base = in + img;
+    const int x1 = min(g.W, x0 + g.seg);
+    auto issue = [&](int x, int s) {
+      if (x < x1) {
+        const uint32_t a = ring + (uint32_t)(s * DWF_SLOT) * PL;
+#pragma unroll
+        for (int rr = 0; rr < DW_R + 2; ++rr) {
+          const int yy = y0 - 1 + rr;
+          const bool ok = x + 1 < g.W && yy >= 0 && yy < g.H;
+          cp_async16(a + rr * PL, ok ? base + ((int64_t)yy * g.W + x + 1) * g.C : base, ok);
+        }
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int s = 0; s < DWF_RING; ++s) issue(x0 + s, s);
     float4 win[3][DW_R + 2];
     strip_loadcol(base, x0 - 1, y0, g, win[1]);
     strip_loadcol(base, x0, y0, g, win[2]);
-    const int x1 = min(g.W, x0 + g.seg);
+    int s = 0;
     for (int x = x0; x < x1; ++x) {
+      cp_async_wait<DWF_RING - 1>();
+      const uint32_t a = ring + (uint32_t)(s * DWF_SLOT) * PL;
 #pragma unroll
-      for (int rr = 0; rr < DW_R + 2; ++rr) { win[0][rr] = win[1][rr]; win[1][rr] = win[2][rr]; }
-      strip_loadcol(base, x + 1, y0, g, win[2]);
+      for (int rr = 0; rr < DW_R + 2; ++rr) { win[0][rr] = win[1][rr]; win[1][rr] = win[2][rr]; win[2][rr] = lds4(a + rr * PL); }
+      issue(x + DWF_RING, s);
+      s = (s + 1 == DWF_RING) ? 0 : s + 1;
 #pragma unroll
       for (int r = 0; r < DW_R; ++r) {
         if (y0 + r >= g.H) break;
@@ -75,19 +114,11 @@ __global__ void __launch_bounds__(256) dwconv_strip_kernel(const float* __restri
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) acc = fma4(win[kx][r + ky], wv[ky * 3 + kx], acc);
         const int64_t o = img + ((int64_t)(y0 + r) * g.W + x) * g.C;
-        if (!BWD) {
-          st4(outA + o, acc);
-          if (outB) st4(outB + o, make_float4(gelu_f(acc.x), gelu_f(acc.y), gelu_f(acc.z), gelu_f(acc.w)));
-        } else {
-          if (u1) {
-            const float4 u = ld4(u1 + o);
-            acc = make_float4(acc.x * gelu_grad_f(u.x), acc.y * gelu_grad_f(u.y), acc.z * gelu_grad_f(u.z),
-                              acc.w * gelu_grad_f(u.w));
-          }
-          st4(outA + o, acc);
-        }
+        st4(outA + o, acc);
+        if (outB) st4(outB + o, make_float4(gelu_f(acc.x), gelu_f(acc.y), gelu_f(acc.z), gelu_f(acc.w)));
       }
     }
+    cp_async_wait<0>();
   }
 }
 
@@ -107,19 +138,6 @@ __global__ void __launch_bounds__(256) dwconv_strip_kernel(const float* __restri
 constexpr int DWB_RING = 3;
 constexpr int DWB_SLOT = (DW_R + 2) + 2 * DW_R;                  // float4 per thread per step
 constexpr int DWB_SMEM = DWB_RING * DWB_SLOT * 256 * 16;
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool ok) {
-  const int sz = ok ? 16 : 0;                                      // src-size 0: zero fill, nothing is read
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ float4 lds4(uint32_t a) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
-  return v;
-}
 
 __global__ void __launch_bounds__(256, 1) dwconv_bwd_strip_kernel(const float* __restrict__ du2,
                                                                const float* __restrict__ h1,
@@ -552,40 +570,26 @@ static int conv_out_launch(int what, const float* t, const float* wk, const floa
 
 extern "C" {
 
-static StripGeom make_strips(int B, int H, int W, int C, int& nstrips, dim3& grid) {
-  StripGeom g;
-  g.B = B; g.H = H; g.W = W; g.C = C;
-  g.seg = W < 32 ? W : 32;
-  g.nys = (H + DW_R - 1) / DW_R;
-  g.nxs = (W + g.seg - 1) / g.seg;
-  nstrips = B * g.nys * g.nxs;
-  const int gy = (C / 4 + 31) / 32;
-  int gx = (nstrips + 7) / 8;
-  const int cap = (kNumSMs * 8 + gy - 1) / gy;          // ~8 resident blocks per SM in total
-  if (gx > cap) gx = cap;
-  grid = dim3((unsigned)(gx > 0 ? gx : 1), (unsigned)gy);
-  return g;
-}
-
-// One persistent block per SM for the ring kernel: pick the strip length (32 or 16 columns) and the block count so
-// that every warp walks the same number of strips (wave quantisation was 13 % of the first version's time).
-static StripGeom make_strips_persistent(int B, int H, int W, int C, int& nstrips, dim3& grid) {
+// One persistent block per SM for the ring kernels: pick the strip length (32, 16 or 8 columns) that minimises
+// rounds x (strip length + halo / pipeline-fill cost) - every warp of every block walks `rounds` strips (wave
+// quantisation was 13 % of the first version's time, and the 32^2...8^2 levels have too few long strips for 148 SMs).
+static StripGeom make_strips_persistent(int B, int H, int W, int C, int warps, int& nstrips, dim3& grid) {
   const int gy = (C / 4 + 31) / 32;
   const int max_gx = kNumSMs / gy > 0 ? kNumSMs / gy : 1;
-  StripGeom best{}; double best_eff = -1.0; int best_gx = 1, best_n = 0;
-  for (int seg = 32; seg >= 16; seg >>= 1) {
+  StripGeom best{}; double best_cost = 1e30; int best_gx = 1, best_n = 0;
+  for (int seg = 32; seg >= 8; seg >>= 1) {
     StripGeom g;
     g.B = B; g.H = H; g.W = W; g.C = C;
     g.seg = W < seg ? W : seg;
     g.nys = (H + DW_R - 1) / DW_R;
     g.nxs = (W + g.seg - 1) / g.seg;
     const int n = B * g.nys * g.nxs;
-    const int nb = (n + 7) / 8;                                  // blocks' worth of strips (8 warps per block)
+    const int nb = (n + warps - 1) / warps;                      // blocks' worth of strips
     const int rounds = (nb + max_gx - 1) / max_gx;
     const int gx = (nb + rounds - 1) / rounds;
-    const double eff = (double)n / ((double)gx * 8 * rounds) * (seg == 32 ? 1.0 : 0.95);   // short strips: more halo
-    if (eff > best_eff) { best_eff = eff; best = g; best_gx = gx; best_n = n; }
-    if (W <= 16) break;
+    const double cost = (double)rounds * (g.seg + 2.5);
+    if (cost < best_cost) { best_cost = cost; best = g; best_gx = gx; best_n = n; }
+    if (W <= seg) break;
   }
   nstrips = best_n;
   grid = dim3((unsigned)best_gx, (unsigned)gy);
@@ -600,8 +604,13 @@ int fa_dwconv3x3_fwd(const float* h1, const float* w, const float* b, float* u2,
   FaProfScope prof(FA_K_DWCONV, st);
   if ((int64_t)B * H * W * C == 0) return FA_OK;
   int nstrips; dim3 grid;
-  const StripGeom g = make_strips(B, H, W, C, nstrips, grid);
-  dwconv_strip_kernel<false><<<grid, dim3(32, 8), 0, st>>>(h1, w, b, nullptr, u2, h2, g, nstrips);
+  const StripGeom g = make_strips_persistent(B, H, W, C, DWF_WARPS, nstrips, grid);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FA_CUDA(cudaFuncSetAttribute(dwconv_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DWF_SMEM));
+    attr_set = true;
+  }
+  dwconv_strip_kernel<<<grid, dim3(32, DWF_WARPS), DWF_SMEM, st>>>(h1, w, b, u2, h2, g, nstrips);
   FA_LAUNCH_CHECK("fa_dwconv3x3_fwd");
   return FA_OK;
 }
@@ -614,7 +623,7 @@ int fa_dwconv3x3_bwd(const float* du2, const float* h1, const float* u1, const f
   FaProfScope prof(FA_K_DWCONV, st);
   if ((int64_t)B * H * W * C == 0) return FA_OK;
   int nstrips; dim3 grid;
-  const StripGeom g = make_strips_persistent(B, H, W, C, nstrips, grid);
+  const StripGeom g = make_strips_persistent(B, H, W, C, 8, nstrips, grid);
   FA_REQUIRE(!dw || h1, "fa_dwconv3x3_bwd: h1 required for the weight gradient");
   static bool attr_set = false;
   if (!attr_set) {
