@@ -21,18 +21,29 @@ template <> struct Pitch<28> { static constexpr int KP = 32, HS = 36, HSV = 40; 
 template <> struct Pitch<56> { static constexpr int KP = 56, HS = 60, HSV = 72; };
 template <> struct Pitch<64> { static constexpr int KP = 64, HS = 68, HSV = 72; };
 
-// gather a 64-token window tile: dst[t][0..KP) = src[rows[t]*ld + col0 + d] (zero for d >= HD: k-padding)
+// gather a 64-token window tile: dst[t][0..KP) = src[rows[t]*ld + col0 + d] (zero for d >= HD: k-padding).
+// The copies are cp.async (16 B, L2 only): every tile of an item is in flight at once and the caller waits once with
+// load_wait() before the barrier that publishes the tiles - the first version (ld.global -> st.shared per tile) spent
+// a third of the backward kernel's samples on four serialised global-memory latencies per item.
 template <int HD, int HS, int NTHR>
 __device__ __forceinline__ void load_tile(float* dst, const float* __restrict__ src, int64_t ld, int col0,
                                           const int* rows, int tid) {
   constexpr int KP = Pitch<HD>::KP;
   constexpr int V4 = KP / 4;
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(dst);
   for (int i = tid; i < NTOK * V4; i += NTHR) {
     const int t = i / V4, d = (i % V4) * 4;
-    const float4 v = d < HD ? *reinterpret_cast<const float4*>(src + (int64_t)rows[t] * ld + col0 + d)
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-    *reinterpret_cast<float4*>(dst + t * HS + d) = v;
+    if (d < HD) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + (uint32_t)(t * HS + d) * 4u),
+                   "l"(src + (int64_t)rows[t] * ld + col0 + d)
+                   : "memory");
+    } else {
+      *reinterpret_cast<float4*>(dst + t * HS + d) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
+}
+__device__ __forceinline__ void load_wait() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
 __device__ __forceinline__ float rel_bias(const float* bias, int i, int j) {

@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(256) joint_fwd_kernel(const float* __restrict_
     attn::load_tile<HD, S::HS, 256>(s.k + n * NTOK * S::HS, kv, ldkv, h * HD, s.rowk[n], tid);
     attn::load_tile<HD, S::HSV, 256>(s.v + n * NTOK * S::HSV, kv, ldkv, C + h * HD, s.rowk[n], tid);
   }
+  attn::load_wait();
   __syncthreads();
 #pragma unroll
   for (int n = 0; n < NKB; ++n)
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(256) joint_bwd_kernel(const float* __restrict_
       attn::load_tile<HD, S::HS, 256>(s.k + n * NTOK * S::HS, kv, ldkv, h * HD, s.rowk[n], tid);
       attn::load_tile<HD, S::HS, 256>(s.v + n * NTOK * S::HS, kv, ldkv, C + h * HD, s.rowk[n], tid);
     }
+    attn::load_wait();
     __syncthreads();
 #pragma unroll
     for (int n = 0; n < NKB; ++n)
@@ -278,7 +280,14 @@ int launch_jbwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, cons
     done = true;
   }
   const int items = g.B * g.nWy * g.nWx * g.heads;
-  int gx = ((4 * kNumSMs / g.L + g.heads - 1) / g.heads) * g.heads;      // ~4 CTAs per SM in total, multiple of heads
+  // persistent: exactly one resident wave (a 4-per-SM guess on a 3-per-SM kernel ran 1.33 waves = 2 rounds)
+  static int per_sm = 0;
+  if (!per_sm) {
+    FA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, joint_bwd_kernel<HD, NKB, ATOMIC>, 256, smem));
+    if (per_sm < 1) per_sm = 1;
+  }
+  int gx = (per_sm * kNumSMs / g.L / g.heads) * g.heads;                 // multiple of heads
+  if (gx < g.heads) gx = g.heads;
   if (gx > items) gx = items;                                           // items is a multiple of heads
   dim3 grid((unsigned)gx, (unsigned)g.L);
   joint_bwd_kernel<HD, NKB, ATOMIC><<<grid, 256, smem, st>>>(q, ldq, kv, ldkv, dout, dq, dkv, g, scale, tables, dtables, items);

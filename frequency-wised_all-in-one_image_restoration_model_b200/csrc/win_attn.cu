@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(NTHR) win_attn_fwd_kernel(const float* __restr
   load_tile<HD, HS>(s.q, q, ldq, h * HD, s.row, tid);
   load_tile<HD, HS>(s.k, kv, ldkv, h * HD, s.row, tid);
   load_tile<HD, HSV>(s.v, kv, ldkv, C + h * HD, s.row, tid);
+  attn::load_wait();
   __syncthreads();
   tile_abt<HD, true>(s.q, HS, s.k, HS, s.p, scale, s.bias, s.label, tid);
   __syncthreads();
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(NTHR) win_attn_bwd_kernel(const float* __restr
     load_tile<HD, HS>(s.k, kv, ldkv, h * HD, s.row, tid);
     load_tile<HD, HS>(s.v, kv, ldkv, C + h * HD, s.row, tid);
     load_tile<HD, HS>(s.dO, dout, C, h * HD, s.row, tid);
+    attn::load_wait();
     __syncthreads();
     tile_abt<HD, true>(s.q, HS, s.k, HS, s.p, scale, s.bias, s.label, tid);     // S
     tile_abt<HD, false>(s.dO, HS, s.v, HS, s.x, 1.0f, nullptr, nullptr, tid);   // dP' = dO.V^T
@@ -271,6 +273,7 @@ __global__ void __launch_bounds__(NTHR) win_attn_bwd_kernel(const float* __restr
         }
       }
     }
+    attn::load_wait();                                                  // the q|k reload (ALIAS) overlapped the dS pass
     __syncthreads();
     tile_pv<HD, false>(s.x, s.k, HS, dq, C, h * HD, s.row, scale, tid);        // dQ = scale * dS.K
     tile_pv<HD, true>(s.x, s.q, HS, dkv, 2 * C, h * HD, s.row, scale, tid);    // dK = scale * dS^T.Q
@@ -297,7 +300,12 @@ int launch_bwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, const
   const size_t smem = sizeof(SmemB<HD>);
   FA_CUDA(cudaFuncSetAttribute(win_attn_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int items = g.B * g.nWy * g.nWx * g.heads;
-  int grid = (4 * kNumSMs / g.heads) * g.heads;
+  static int per_sm = 0;                       // persistent: exactly one resident wave
+  if (!per_sm) {
+    FA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, win_attn_bwd_kernel<HD>, NTHR, smem));
+    if (per_sm < 1) per_sm = 1;
+  }
+  int grid = (per_sm * kNumSMs / g.heads) * g.heads;
   if (grid < g.heads) grid = g.heads;
   if (grid > items) grid = items;          // items is a multiple of heads
   win_attn_bwd_kernel<HD><<<grid, NTHR, smem, st>>>(q, ldq, kv, ldkv, dout, dq, dkv, g, scale, table, dtable, coef, cbs,
