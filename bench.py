@@ -93,17 +93,22 @@ def measure_tf32_peak():
     return 2 * n ** 3 / (best * 1e-3) / 1e12
 
 
-def oracle_train_step_time(batch, threads, steps=1):
-    """Seconds per train step of the CPU oracle (reference algorithm) at ``batch`` crops: forward q/k/decoder,
-    loss, backward, Adam-equivalent update."""
+def oracle_train_step_time(batch, threads, steps=1, device='cpu'):
+    """Seconds per train step of the oracle (reference algorithm in plain torch ops) at ``batch`` crops: forward
+    q/k/decoder, loss, backward, Adam update.  device='cpu' is the contract's reference arm; device='cuda' runs the very
+    same torch program on the GPU through stock cuBLAS / cuFFT / ATen kernels ("the reference on
+    the same B200 via stock torch CUDA - the real bar the kernels must beat")."""
     from oracle import airnet as oa
     synth = importlib.import_module(PKG + '.synth')
     model = importlib.import_module(PKG + '.net.model')
     torch.set_num_threads(threads)
     torch.manual_seed(0)
     net = model.AirNet(make_opt(batch))               # parameter container only (CPU); the math below is oracle/
-    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    sd = {k: v.detach().clone().to(device) for k, v in net.state_dict().items()}
     del net
+    cuda = device != 'cpu'
+    if cuda:
+        torch.set_default_device(device)              # the oracle builds its constant tables with bare factories
     pnames = [k[len('E.E.encoder_q.'):] for k in sd if k.startswith('E.E.encoder_q.')
               and not any(s in k for s in ('running_', 'num_batches', 'relative_position_index', 'mask_freq'))]
     train_keys = [k for k in sd if sd[k].is_floating_point() and not k.startswith('E.E.encoder_k.')
@@ -111,19 +116,50 @@ def oracle_train_step_time(batch, threads, steps=1):
     for k in train_keys:
         sd[k].requires_grad_(True)
     opt = torch.optim.Adam([sd[k] for k in train_keys], lr=2e-4)
-    xq, xk, clean = synth.noisy_batch(batch, 25)
+    torch.set_default_device('cpu')
+    xq, xk, clean = (t.to(device) for t in synth.noisy_batch(batch, 25))
+    if cuda:
+        torch.set_default_device(device)
     times = []
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        opt.zero_grad()
-        restored, logits, _ = oa.airnet_uformer_forward(sd, xq, xk, True, param_names=pnames)
-        labels = torch.zeros(batch, dtype=torch.long)
-        ce = sum(torch.nn.functional.cross_entropy(l, labels) for l in logits) / len(logits)
-        loss = (restored - clean).abs().mean() + 0.6 * ce
-        loss.backward()
-        opt.step()
-        times.append(time.perf_counter() - t0)
+    try:
+        for _ in range(steps):
+            if cuda:
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            opt.zero_grad()
+            restored, logits, _ = oa.airnet_uformer_forward(sd, xq, xk, True, param_names=pnames)
+            labels = torch.zeros(batch, dtype=torch.long, device=device)
+            ce = sum(torch.nn.functional.cross_entropy(l, labels) for l in logits) / len(logits)
+            loss = (restored - clean).abs().mean() + 0.6 * ce
+            loss.backward()
+            opt.step()
+            if cuda:
+                loss.item()
+                torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+    finally:
+        torch.set_default_device('cpu')
     return min(times)
+
+
+def run_reference_cuda(args):
+    """Not the contract's reference arm (that one is the CPU run below): the oracle's torch program on cuda:0 with
+    stock kernels, fp32 (allow_tf32 off, the parity-equivalent setting) and with allow_tf32 on."""
+    out = {'impl': 'reference-torch-cuda', 'metric': METRIC, 'unit': UNIT, 'n_gpus': 1, 'dtype': 'f32', 'data': 'synthetic',
+           'config': {'workload': 'configs[1]: Uformer+Uformer all_3_bands train step, 128x128, sigma=25',
+                      'batch': args.batch, 'note': 'oracle/ torch program on cuda:0, stock cuBLAS/cuFFT/ATen kernels, eager'}}
+    k = max(1, min(args.steps, 5))
+    for name, tf32 in (('fp32', False), ('tf32', True)):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        oracle_train_step_time(args.batch, os.cpu_count() or 1, 2, 'cuda')
+        t = oracle_train_step_time(args.batch, os.cpu_count() or 1, k, 'cuda')
+        out[name] = {'value': args.batch / t, 'ms_per_step': t * 1e3}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    out['value'] = out['fp32']['value']
+    out['ms_per_step'] = out['fp32']['ms_per_step']
+    print(json.dumps(out), flush=True)
 
 
 def run_reference(args, rank, world):
@@ -204,6 +240,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='freqair', choices=['freqair', 'reference'])
     ap.add_argument('--batch', type=int, default=BATCH, help='crops per GPU (the headline config uses 16)')
+    ap.add_argument('--ref-device', default='cpu', choices=['cpu', 'cuda'],
+                    help='with --impl reference: cpu = the contract arm (default); cuda = the same oracle torch program on '
+                         'cuda:0 through stock torch kernels (informational: the stock-library bar on this GPU)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-roofline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch the step kernel by kernel instead of replaying its CUDA graph')
@@ -218,6 +257,10 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if args.impl == 'reference':
+        if args.ref_device == 'cuda':
+            if rank == 0:
+                run_reference_cuda(args)
+            return
         run_reference(args, rank, world)
         return
     if not torch.cuda.is_available():

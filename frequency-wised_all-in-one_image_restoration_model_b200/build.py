@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, 'csrc')
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, 'libfreqair.so')
 SOURCES = ['api.cu', 'gemm_simt.cu', 'gemm_tc.cu', 'norm.cu', 'conv.cu', 'fft_band.cu', 'win_attn.cu', 'joint_attn.cu',
-           'elementwise.cu', 'dcn.cu']
+           'elementwise.cu', 'dcn.cu', 'datagen.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--use_fast_math=false',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-O2', '-I', os.path.join(ROOT, 'include'), '-I', CSRC]
 

@@ -438,6 +438,17 @@ def spectral_l1(a, b, bob, nbands, want_grad=True, gscale=1.0):
     return loss, grad
 
 
+def crop_augment(pool, meta, sigma, noise, P):
+    """(degraded, clean) [B,3,P,P] training patches from the uint8 image pool (fa_crop_augment)."""
+    B = meta.shape[0]
+    assert pool.dtype == torch.uint8 and meta.dtype == torch.int64 and meta.shape[1] == 8 and meta.is_contiguous()
+    _f32(sigma, noise)
+    deg = torch.empty(B, 3, P, P, device=pool.device, dtype=torch.float32)
+    clean = torch.empty_like(deg)
+    _call('fa_crop_augment', _p(pool), _p(meta), _p(sigma), _p(noise), _p(deg), _p(clean), B, P, _stream())
+    return deg, clean
+
+
 def momentum_update(k, q, m):
     _f32(k, q)
     _call('fa_momentum_update', _p(k), _p(q), k.numel(), m, _stream())

@@ -230,6 +230,16 @@ int fa_act_fwd(const float* x, float* y, int64_t n, int act, float p, fa_stream_
 int fa_act_bwd(const float* dy, const float* x, float* dx, int64_t n, int act, float p, fa_stream_t stream);
 /* loss[0] += mean|a-b| ; grad = sign(a-b) * gscale / n   (nn.L1Loss, train.py:65,89) */
 int fa_l1_loss(const float* a, const float* b, float* loss, float* grad, int64_t n, float gscale, fa_stream_t stream);
+/* Training-pair generator (utils/dataset_utils.py:97-135 pixel work, whole batch per launch): for sample i,
+ * meta[i] = {clean_offset, degraded_offset or -1, H, W, y0, x0, mode, seed} (int64; offsets into the uint8 HWC image
+ * pool; W = row length of the image).  Cuts the P x P patch at (y0, x0) from the clean and the degraded image, applies
+ * augmentation `mode` (0..7 = image_utils.data_augmentation) and ToTensor: out_* [B,3,P,P] float in [0,1].
+ * degraded_offset = -1 synthesises the degradation as the reference does for 'denoising_*':
+ *   clip(clean + n * sigma[i], 0, 255).astype(uint8), n ~ N(0,1) either read from noise [B,P,P,3] (patch coordinates
+ *   BEFORE augmentation) or, when noise is NULL, drawn from a stateless generator keyed on (seed, absolute pixel,
+ *   channel) so that the two crops of a pair share the noise of their overlap, as one noisy image would give. */
+int fa_crop_augment(const uint8_t* pool, const int64_t* meta, const float* sigma, const float* noise, float* out_degraded,
+                    float* out_clean, int B, int P, fa_stream_t stream);
 /* k = k*m + q*(1-m) over a flat buffer (moco.py:45-50) */
 int fa_momentum_update(float* k, const float* q, int64_t n, float m, fa_stream_t stream);
 /* torch.optim.Adam step over a flat buffer (train.py:63,96); step >= 1 */

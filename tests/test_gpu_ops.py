@@ -480,3 +480,98 @@ def test_act_l1_momentum_adam(ops):
         pt.grad = g.clone()
         opt.step()
     close(pd, pt.detach(), 1e-6, 'adam vs torch.optim')
+
+
+# ----------------------------------------------------------------------------- training-pair generator (section 8f)
+def test_crop_augment_matches_reference_golden(ops):
+    """fa_crop_augment against the golden vectors made by the reference's own pipeline functions: bit exact."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'datagen.npz'))
+    P = int(g['P'])
+    gt, noisy = g['gt'], g['noisy']
+    H, W = gt.shape[:2]
+    pool = torch.from_numpy(np.concatenate([gt.reshape(-1), noisy.reshape(-1)])).cuda()
+    meta = torch.tensor([[0, gt.size, H, W, int(g[f'origin{m}'][0]), int(g[f'origin{m}'][1]), m, 0] for m in range(8)],
+                        dtype=torch.int64).cuda()
+    deg, clean = ops.crop_augment(pool, meta, torch.zeros(8, device='cuda'), None, P)
+    for m in range(8):
+        assert np.array_equal(deg[m].cpu().numpy(), g[f'deg{m}']), m
+        assert np.array_equal(clean[m].cpu().numpy(), g[f'clean{m}']), m
+
+
+def test_crop_augment_noise_synthesis(ops):
+    """Synthesised degradation: explicit noise -> bit exact against the oracle; stateless generator -> integer side
+    exact by construction, Box-Muller to float round-off: at most 1 LSB on < 0.5 % of the pixels; overlapping crops of
+    one image share their noise."""
+    import numpy as np
+    from oracle import datagen as od
+    rng = np.random.RandomState(3)
+    H, W, P = 48, 64, 16
+    img = rng.randint(0, 256, size=(H, W, 3)).astype(np.uint8)
+    pool = torch.from_numpy(img.reshape(-1)).cuda()
+    draws = [(5, 7, 1), (0, 0, 2), (32, 48, 7), (11, 40, 4), (20, 20, 6), (20, 24, 0)]
+    meta = torch.tensor([[0, -1, H, W, y, x, m, 99] for y, x, m in draws], dtype=torch.int64).cuda()
+    sig = torch.tensor([15., 25., 50., 25., 25., 25.]).cuda()
+    noise = torch.from_numpy(rng.randn(len(draws), P, P, 3).astype(np.float32))
+    deg, clean = ops.crop_augment(pool, meta, sig, noise.cuda(), P)
+    for i, (y, x, m) in enumerate(draws):
+        patch = img[y:y + P, x:x + P]
+        ref = od.to_tensor(od.augment(od.add_noise(patch, noise[i].numpy(), float(sig[i])), m))
+        assert np.array_equal(deg[i].cpu().numpy(), ref), i
+        assert np.array_equal(clean[i].cpu().numpy(), od.to_tensor(od.augment(patch, m))), i
+    deg2, _ = ops.crop_augment(pool, meta, sig, None, P)
+    field = od.normal_field(99, H, W)
+    bad = 0
+    for i, (y, x, m) in enumerate(draws):
+        noisy = od.add_noise(img, field, float(sig[i]))
+        ref = od.to_tensor(od.augment(noisy[y:y + P, x:x + P], m))
+        d = np.abs(deg2[i].cpu().numpy() - ref) * 255
+        assert d.max() <= 1.001, i
+        bad += int((d > 0.5).sum())
+    assert bad <= 0.005 * len(draws) * P * P * 3
+    # samples 4 and 5 (mode 6 / mode 0, origins 4 columns apart) overlap: undo the augmentation and compare
+    a = np.rot90(deg2[4].cpu().numpy().transpose(1, 2, 0), k=-3)            # back to patch coordinates
+    b = deg2[5].cpu().numpy().transpose(1, 2, 0)
+    assert np.array_equal(a[:, 4:], b[:, :P - 4])
+
+
+def test_device_train_set_mirrors_reference_draws(ops):
+    """DeviceTrainSet: same host-side draws as TrainDataset.__getitem__ for a seeded ``random`` (type round-robin,
+    per-type shuffle at wrap-around, two crop + augmentation draws per sample), patches cut by the kernel."""
+    import random
+    import numpy as np
+    from oracle import datagen as od
+    dg = importlib.import_module(PKG_NAME + '.datagen')
+    rng = np.random.RandomState(5)
+    imgs = {'denoising_25': [(f'n{i}', rng.randint(0, 256, size=(40 + i, 50, 3)).astype(np.uint8), None) for i in range(3)],
+            'deraining': [(f'r{i}', rng.randint(0, 256, size=(37, 45 + i, 3)).astype(np.uint8),
+                           rng.randint(0, 256, size=(37, 45 + i, 3)).astype(np.uint8)) for i in range(2)]}
+    P = 16
+    ds = dg.DeviceTrainSet(['denoising_25', 'deraining'], imgs, patch_size=P, rng=random.Random(17))
+    (names, de_ids), d1, d2, c1, c2 = ds.next_batch(6)
+    assert de_ids == ['denoising_25', 'deraining'] * 3 and d1.shape == (6, 3, P, P)
+    # replay the reference's draw order with the same generator
+    r = random.Random(17)
+    order = {0: list(range(3)), 1: list(range(2))}
+    it = [0, 0]
+    for i in range(6):
+        t = i % 2
+        if it[t] == 0:
+            for k in reversed(range(1, len(order[t]))):
+                j = r.randrange(1, k + 1)
+                order[t][k], order[t][j] = order[t][j], order[t][k]
+        idx = order[t][it[t]]
+        name, clean, degraded = imgs[de_ids[i]][idx]
+        assert names[i] == name
+        clean = dg.crop_img(clean, 16)
+        for v, (dv, cv) in enumerate(((d1, c1), (d2, c2))):
+            y0 = r.randint(0, clean.shape[0] - P); x0 = r.randint(0, clean.shape[1] - P); mode = r.randint(1, 7)
+            assert ds.last_meta[v * 6 + i, 4:7].tolist() == [y0, x0, mode]
+            assert np.array_equal(cv[i].cpu().numpy(), od.to_tensor(od.augment(clean[y0:y0 + P, x0:x0 + P], mode)))
+            if degraded is not None:
+                dimg = dg.crop_img(degraded, 16)
+                assert np.array_equal(dv[i].cpu().numpy(), od.to_tensor(od.augment(dimg[y0:y0 + P, x0:x0 + P], mode)))
+            else:
+                assert not torch.equal(dv[i], cv[i]) and (dv[i] - cv[i]).abs().mean().item() < 0.15
+        it[t] = (it[t] + 1) % len(order[t])

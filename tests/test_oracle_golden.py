@@ -187,3 +187,29 @@ def test_metrics_known_answers():
     x, y = torch.full((1, 16, 16), 0.5), torch.full((1, 16, 16), 0.25)
     c1 = 1e-4
     assert metrics.ssim(x, y) == pytest.approx((2 * 0.5 * 0.25 + c1) / (0.25 + 0.0625 + c1), abs=1e-9)
+
+
+def test_datagen_oracle_matches_reference_pipeline():
+    """oracle/datagen.py against tests/golden/datagen.npz (tools/make_golden_data.py: the reference's _crop_patch,
+    data_augmentation, crop_img and ToTensor on a seeded image, all 8 augmentation modes)."""
+    import os
+    import numpy as np
+    from oracle import datagen as od
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'datagen.npz'))
+    P = int(g['P'])
+    gt, noisy = g['gt'], g['noisy']
+    assert gt.shape[0] % 16 == 0 and gt.shape[1] % 16 == 0
+    for mode in range(8):
+        y0, x0 = (int(v) for v in g[f'origin{mode}'])
+        d, c = od.training_pair(gt, noisy, y0, x0, mode, P)
+        assert np.array_equal(d, g[f'deg{mode}']), mode            # byte work: bit exact
+        assert np.array_equal(c, g[f'clean{mode}']), mode
+    # noise synthesis: the reference adds float64 noise, the restatement (and the kernel) float32: identical except
+    # where the sum lands within float32 round-off of an integer
+    mine = od.add_noise(gt, g['noise'], int(g['sigma']))
+    diff = np.abs(mine.astype(np.int32) - noisy.astype(np.int32))
+    assert diff.max() <= 1 and (diff != 0).mean() < 5e-3
+    # the stateless generator: standard normal to sampling accuracy, and reproducible
+    z = od.normal_field(3, 64, 64)
+    assert abs(float(z.mean())) < 0.03 and abs(float(z.std()) - 1.0) < 0.03
+    assert np.array_equal(z, od.normal_field(3, 64, 64)) and not np.array_equal(z, od.normal_field(4, 64, 64))
