@@ -96,9 +96,9 @@ def test_colsum(ops):
 
 
 # ----------------------------------------------------------------------------- norms
-@pytest.mark.parametrize('C', [28, 56, 112, 448, 768, 896])
-def test_layernorm(ops, C):
-    rows = 333
+@pytest.mark.parametrize('rows', [333, 5, 4099])
+@pytest.mark.parametrize('C', [28, 56, 112, 224, 448, 768, 896])
+def test_layernorm(ops, C, rows):
     x = gen(rows, C).requires_grad_(True)
     g, b = (1 + 0.1 * gen(C, seed=1)).requires_grad_(True), gen(C, seed=2).requires_grad_(True)
     dy, dres = gen(rows, C, seed=3), gen(rows, C, seed=4)
