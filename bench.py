@@ -73,6 +73,26 @@ class ClockSampler(threading.Thread):
                 'samples': len(self.rows)}
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1 when
+    NCCL_DEBUG is set in the environment), so the real stdout is kept aside for the JSON line and fd 1 is pointed at
+    stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    claim_stdout()
+    _JSON_OUT.write(json.dumps(obj) + '\n')
+    _JSON_OUT.flush()
+
+
 def measure_tf32_peak():
     """Dense TF32 tensor-core throughput of this GPU measured the way MEASURED_PEAKS.json measures bf16
     (8192^3 matmul, best of 5).  Only a roofline denominator - cuBLAS is never on the product path."""
@@ -159,7 +179,7 @@ def run_reference_cuda(args):
     torch.backends.cudnn.allow_tf32 = False
     out['value'] = out['fp32']['value']
     out['ms_per_step'] = out['fp32']['ms_per_step']
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def run_reference(args, rank, world):
@@ -180,7 +200,7 @@ def run_reference(args, rank, world):
             'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                              'sample': f'oracle/ CPU restatement of the reference train step, batch {sample_b}, {k} step(s)'},
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_inference(args):
@@ -223,14 +243,14 @@ def run_inference(args):
     torch.cuda.synchronize()
     ms_e2e = f0.elapsed_time(f1) / K
     ntiles = (size // 128) ** 2
-    print(json.dumps({'metric': f'{size}x{size} inference ms/img (Uformer+Uformer all_3_bands, {ntiles} tiles of 128x128)',
+    emit({'metric': f'{size}x{size} inference ms/img (Uformer+Uformer all_3_bands, {ntiles} tiles of 128x128)',
                       'value': ms, 'unit': 'ms/img', 'n_gpus': 1, 'steps': K, 'warmup': W, 'ms_per_step': ms,
                       'higher_is_better': False, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                       'config': {'workload': f'tiled eval forward of one {size}x{size} sigma=25 image, random init', 'tiles': ntiles,
                                  'launch': 'eager' if args.no_graph else 'cuda_graph'},
                       'e2e': {'value': ms_e2e, 'unit': 'ms/img', 'h2d_bytes_per_step': img.numel() * 4,
                               'd2h_bytes_per_step': img.numel() * 4},
-                      'gpu_launches': launches, 'tiles_per_s': ntiles / (ms * 1e-3)}), flush=True)
+                      'gpu_launches': launches, 'tiles_per_s': ntiles / (ms * 1e-3)})
 
 
 def main():
@@ -250,6 +270,7 @@ def main():
                     help='train = the headline configs[1] step (default); infer512 / infer1024 = configs[3]-style tiled '
                          'full-resolution inference latency (Uformer encoder + Uformer decoder), ms per image, 1 GPU')
     args = ap.parse_args()
+    claim_stdout()
     if os.environ.get('FREQAIR_WATCHDOG'):                 # debugging aid: dump every thread's stack and exit if stuck
         import faulthandler
         faulthandler.dump_traceback_later(int(os.environ['FREQAIR_WATCHDOG']), exit=True)
@@ -388,7 +409,7 @@ def main():
                 'gpu_launches': launches, 'gpu_launches_per_step': launches / K,
                 'step_tflop': STEP_GFLOP_PER_CROP * B / 1e3,
                 'roofline': roofline, 'cpu_baseline': cpu_baseline}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
