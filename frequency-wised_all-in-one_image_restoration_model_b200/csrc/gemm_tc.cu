@@ -751,20 +751,36 @@ int fa_gemm_tc_launch(const float* A, const float* B, float* C, int M, int N, in
   int64_t tiles = (int64_t)g.tiles_m * ((N + bn - 1) / bn);
   g.splits = 1;
   g.k_chunk = K;
-  if (tiles < kNumSMs) {
-    if (plain && e.vec && K >= 1024) {
-      int splits = (int)((2 * kNumSMs + tiles - 1) / tiles);
-      int maxs = K / 256; if (maxs < 1) maxs = 1;
-      if (splits > maxs) splits = maxs;
-      g.k_chunk = ((K + splits - 1) / splits + BK - 1) / BK * BK;
-      g.splits = (K + g.k_chunk - 1) / g.k_chunk;
-      if (g.splits > 1) {
-        e.atomic = 1;
-        if (!e.accumulate) FA_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st));
-      }
-    } else {
-      while (bn > 32 && (bn == 96 || (int64_t)g.tiles_m * ((N + bn - 1) / bn) < kNumSMs)) bn = (bn == 96) ? 64 : bn >> 1;
+  bool split_done = false;
+  if (plain && e.vec && K >= 512) {
+    // Persistent CTAs walk `rounds` work units each, so the cost of a launch is rounds x (k-extent of a unit + the
+    // per-unit pipeline fill / epilogue, ~6 k-blocks).  Splitting the reduction changes how tiles x splits units
+    // quantise onto 148 SMs (56 tiles x 6 splits = 336 units = 3 rounds of K/6, but x 5 = 280 units = 2 rounds of K/5);
+    // pick the split with the least cost.  A split output is reduced with fp32 atomics (zero-filled first unless the
+    // call accumulates); each split also bounds the length of one truncating tensor-core accumulation.
+    int maxs = K / 256; if (maxs < 1) maxs = 1;
+    const int cap = (int)(4 * kNumSMs / tiles) > 64 ? (int)(4 * kNumSMs / tiles) : 64;
+    if (maxs > cap) maxs = cap;
+    double best = 1e30; int best_kc = K, best_sp = 1;
+    for (int sp = 1; sp <= maxs; ++sp) {
+      const int kc = ((K + sp - 1) / sp + BK - 1) / BK * BK;
+      const int spe = (K + kc - 1) / kc;
+      const int64_t units = tiles * spe;
+      const int64_t rounds = (units + kNumSMs - 1) / kNumSMs;
+      double cost = (double)rounds * (kc + 192);
+      if (spe > 1) cost += e.accumulate ? 32 : 96;               // atomic epilogue (+ zero fill)
+      if (cost < best - 1e-9) { best = cost; best_kc = kc; best_sp = spe; }
     }
+    if (best_sp > 1) {
+      g.k_chunk = best_kc;
+      g.splits = best_sp;
+      e.atomic = 1;
+      if (!e.accumulate) FA_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st));
+      split_done = true;
+    }
+  }
+  if (!split_done && tiles < kNumSMs && !(plain && e.vec && K >= 1024)) {
+    while (bn > 32 && (bn == 96 || (int64_t)g.tiles_m * ((N + bn - 1) / bn) < kNumSMs)) bn = (bn == 96) ? 64 : bn >> 1;
   }
   g.tiles_n = (N + bn - 1) / bn;
 
