@@ -19,7 +19,7 @@ class FaGemmEpilogue(ctypes.Structure):
                 ('aux_param', ctypes.c_float), ('rowscale', ctypes.c_void_p), ('rows_per_scale', ctypes.c_int),
                 ('residual', ctypes.c_void_p), ('ldr', ctypes.c_int64), ('accumulate', ctypes.c_int),
                 ('alpha', ctypes.c_float), ('preact', ctypes.c_void_p), ('ldpre', ctypes.c_int64),
-                ('a_rowsum', ctypes.c_void_p)]
+                ('a_rowsum', ctypes.c_void_p), ('a_kscale', ctypes.c_void_p), ('a_k_rows_per_scale', ctypes.c_int)]
 
 
 _SCALARS = {'int': ctypes.c_int, 'int64_t': ctypes.c_int64, 'float': ctypes.c_float, 'double': ctypes.c_double,

@@ -92,6 +92,11 @@ int fa_gemm(const float* A, const float* B, float* C, int M, int N, int K, int64
       return FA_ERR_UNSUPPORTED;
     }
   }
+  if (epi && epi->a_kscale) {
+    fa_set_error("fa_gemm: a_kscale needs the tcgen05 path (M=%d N=%d K=%d tA=%d tB=%d, a_k_rows_per_scale=%d)", M, N, K,
+                 transA, transB, epi->a_k_rows_per_scale);
+    return FA_ERR_UNSUPPORTED;
+  }
   FaGemmEpilogue e2;
   if (epi && epi->a_rowsum) {
     // the SIMT kernel has no fused row-sum: take it in a separate pass over A, then contract without it

@@ -205,6 +205,7 @@ struct EpiTC {
   float* preact; int64_t ldpre;
   int vec;     // every epilogue array is 16-byte aligned with a row pitch that is a multiple of 4 floats, and N % 4 == 0
   float* a_rowsum;   // a_tmem only: a_rowsum[m] += sum_k op(A)[m,k], accumulated by the split warps (thread = A row)
+  const float* a_kscale; int a_krps;   // a_tmem only: op(A)[m,k] *= a_kscale[k / a_krps] (a_krps % 32 == 0: one scalar per k-block)
 };
 
 struct TcGeom {
@@ -266,6 +267,10 @@ __device__ __forceinline__ void epi_vec(float4 x, const EpiTC& e, float4 b4, int
         x.x *= actg_c<ACT>(a.x, e.aux_p); x.y *= actg_c<ACT>(a.y, e.aux_p);
         x.z *= actg_c<ACT>(a.z, e.aux_p); x.w *= actg_c<ACT>(a.w, e.aux_p);
       }
+    }
+    if (MODE == EPI_BWD && e.rowscale) {
+      const float rs = __ldg(e.rowscale + row / e.rows_per_scale);
+      x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs;
     }
   }
   if (MODE == EPI_FWD || MODE == EPI_ANY) {
@@ -493,6 +498,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
             for (int i = 0; i < NB; ++i) rb[i] = lds128(b + i * SPLIT_WARPS * 512);
             const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + TMEM_A_COL0 + s * 64;
+            if (epi.a_kscale) {                         // DropPath scale of the k-block's sample, folded into A
+              const float sc = __ldg(epi.a_kscale + (kbeg + kb * BK) / epi.a_krps);
+#pragma unroll
+              for (int k = 0; k < 32; ++k) av[k] *= sc;
+            }
             if (epi.a_rowsum) {
 #pragma unroll
               for (int k = 0; k < 32; ++k) rsum += av[k];
@@ -723,12 +733,15 @@ int fa_gemm_tc_launch(const float* A, const float* B, float* C, int M, int N, in
     e.residual = ep->residual; e.ldr = ep->ldr; e.accumulate = ep->accumulate; e.alpha = ep->alpha;
     e.preact = ep->preact; e.ldpre = ep->ldpre;
     e.a_rowsum = ep->a_rowsum;
+    e.a_kscale = ep->a_kscale; e.a_krps = ep->a_k_rows_per_scale;
+    if (e.a_kscale && (e.a_krps <= 0 || e.a_krps % BK)) return FA_ERR_UNSUPPORTED;
   }
   e.vec = (N % 4 == 0) && al16(C) && (ldc % 4 == 0) && (!e.bias || al16(e.bias)) &&
           (!e.aux || (al16(e.aux) && e.ldaux % 4 == 0)) && (!e.residual || (al16(e.residual) && e.ldr % 4 == 0)) &&
           (!e.preact || (al16(e.preact) && e.ldpre % 4 == 0));
-  const bool fwd_like = e.bias || e.act != ACT_NONE || e.rowscale || e.residual || e.preact;
-  const bool plain = !fwd_like && !e.aux;
+  // a row scale alone rides the FWD flavour, with act'(aux) the BWD flavour (dX through an activation and a DropPath)
+  const bool fwd_like = e.bias || e.act != ACT_NONE || (e.rowscale && !e.aux) || e.residual || e.preact;
+  const bool plain = !fwd_like && !e.aux && !e.rowscale;
   int mode;
   if (plain) mode = EPI_PLAIN;
   else if (!e.aux && !e.accumulate) mode = EPI_FWD;
@@ -745,7 +758,7 @@ int fa_gemm_tc_launch(const float* A, const float* B, float* C, int M, int N, in
   g.a_mn = a_mn; g.b_mn = b_mn; g.x3 = single_pass ? 0 : 1;
   static const bool atmem_env = [] { const char* e = getenv("FREQAIR_GEMM_ATMEM"); return !(e && e[0] == '0'); }();
   g.a_tmem = (g.x3 && atmem_env) ? 1 : 0;
-  if (e.a_rowsum && !g.a_tmem) return FA_ERR_UNSUPPORTED;      // fused row sums ride the TMEM staging of A
+  if ((e.a_rowsum || e.a_kscale) && !g.a_tmem) return FA_ERR_UNSUPPORTED;      // both ride the TMEM staging of A
   g.tiles_m = (M + BM - 1) / BM;
   int bn = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 96 ? 96 : 128));
   int64_t tiles = (int64_t)g.tiles_m * ((N + bn - 1) / bn);

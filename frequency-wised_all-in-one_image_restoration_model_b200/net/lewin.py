@@ -23,6 +23,7 @@ def _z(t):
 # (the post-accumulate hooks no longer fire for these parameters).  With DIRECT_GRAD off, or for a parameter without
 # a .grad buffer, gradients are returned to autograd as usual (what the parity tests exercise).
 DIRECT_GRAD = False
+FOLD_DROPPATH = True          # fold the DropPath backward scale into the consuming contractions (see _fold)
 GRAD_READY = None
 
 
@@ -86,18 +87,30 @@ class _QKV:
         return self.buf[:T * C].view(T, C), self.buf[T * C:].view(T, 2 * C)
 
 
-def linear_param_grads(g, x, W, b, want_dx=True, dx=None, accumulate_dx=False):
-    """linear_grads with the parameter gradients routed through the sinks: returns (dx, dW_ret, db_ret)."""
+def _fold(g, dp, rps):
+    """DropPath backward g * dp[sample]: either folded into the consumers (returns g, dp) - the weight-gradient
+    contraction scales its A operand per k-block (FaGemmEpilogue.a_kscale), the data-gradient contraction its output rows
+    - or, when a sample is not a whole number of 32-token k-blocks, materialised with fa_scale_rows (returns g*dp, None)."""
+    if dp is None:
+        return g, None
+    if FOLD_DROPPATH and rps % 32 == 0:
+        return g, dp
+    return ops.scale_rows(g, dp, rps), None
+
+
+def linear_param_grads(g, x, W, b, want_dx=True, dx=None, accumulate_dx=False, dp=None, rps=1):
+    """linear_grads with the parameter gradients routed through the sinks: returns (dx, dW_ret, db_ret).
+    dp / rps: per-sample scale of g (DropPath backward) folded into both contractions."""
     dW, dW_ret = _wbuf(W)
     db, db_ret = _wbuf(b) if b is not None else (None, None)
     # dW += g^T x, and the bias gradient (column sums of g) taken from the same pass over g (FaGemmEpilogue.a_rowsum)
-    ops.gemm(g, x, dW, transA=True, transB=False, accumulate=True, a_rowsum=db)
+    ops.gemm(g, x, dW, transA=True, transB=False, accumulate=True, a_rowsum=db, a_kscale=dp, a_k_rows_per_scale=rps)
     _ready(W, b)
     if not want_dx:
         return None, dW_ret, db_ret
     if dx is None:
         dx = torch.empty_like(x)
-    ops.gemm(g, W, dx, transB=False, accumulate=accumulate_dx)
+    ops.gemm(g, W, dx, transB=False, accumulate=accumulate_dx, rowscale=dp, rows_per_scale=rps)
     return dx, dW_ret, db_ret
 
 
@@ -116,14 +129,16 @@ def leff_fwd(xn2, w1, b1, wdw, bdw, w2, b2, B, H, W, residual, dp_scale, save):
     return out
 
 
-def leff_bwd(gs, sv, xn2, w1, b1, wdw, bdw, w2, b2, B, H, W):
-    """gs: gradient wrt the LeFF output (DropPath scale already applied). Returns dxn2 and the parameter gradients
-    (None where they were accumulated straight into the parameters' .grad buffers)."""
+def leff_bwd(gs, sv, xn2, w1, b1, wdw, bdw, w2, b2, B, H, W, dp=None):
+    """gs: gradient wrt the LeFF output; dp: its per-sample DropPath scale when it is folded into the two contractions
+    that consume gs (None: already applied). Returns dxn2 and the parameter gradients (None where they were
+    accumulated straight into the parameters' .grad buffers)."""
     dW2, dW2r = _wbuf(w2)
     db2b, db2 = _wbuf(b2)
-    ops.gemm(gs, sv['h2'], dW2, transA=True, transB=False, accumulate=True, a_rowsum=db2b)
+    ops.gemm(gs, sv['h2'], dW2, transA=True, transB=False, accumulate=True, a_rowsum=db2b, a_kscale=dp,
+             a_k_rows_per_scale=H * W)
     du2 = torch.empty_like(sv['u2'])
-    ops.gemm(gs, w2, du2, transB=False, aux=sv['u2'], aux_act=ops.ACT_GELU)
+    ops.gemm(gs, w2, du2, transB=False, aux=sv['u2'], aux_act=ops.ACT_GELU, rowscale=dp, rows_per_scale=H * W)
     dwdw, dwdwr = _wbuf(wdw)
     dbdw, dbdwr = _wbuf(bdw)
     du1 = ops.dwconv_bwd(du2, sv['h1'], sv['u1'], wdw, dwdw, dbdw, B, H, W, wdw.shape[0])
@@ -174,15 +189,15 @@ class DecoderBlockFn(torch.autograd.Function):
         T, C = x2d.shape
         hd = C // heads
         g = dx2.reshape(T, C).contiguous()
-        gs = ops.scale_rows(g, dp_m, H * W)
+        gs, dpf = _fold(g, dp_m, H * W)
         dxn2, (dW1, db1, dwdw, dbdw, dW2, db2) = leff_bwd(gs, dict(u1=u1, h1=h1, u2=u2, h2=h2), xn2, P_w1, P_b1, P_wdw,
-                                                         P_bdw, P_w2, P_b2, B, H, W)
+                                                         P_bdw, P_w2, P_b2, B, H, W, dp=dpf)
         dn2w, dn2wr = _wbuf(P_n2w)
         dn2b, dn2br = _wbuf(P_n2b)
         g1 = ops.layernorm_bwd(dxn2, x1, mean2, rstd2, n2w, g, dn2w, dn2b)
         _ready(P_n2w, P_n2b)
-        gs1 = ops.scale_rows(g1, dp_a, H * W)
-        do, dWp, dbp = linear_param_grads(gs1, o, P_wp, P_bp)
+        gs1, dpf = _fold(g1, dp_a, H * W)
+        do, dWp, dbp = linear_param_grads(gs1, o, P_wp, P_bp, dp=dpf, rps=H * W)
         dq = torch.empty(T, C, device=g.device)
         dkv = torch.empty(T, 2 * C, device=g.device)
         dtable, dtabler = _wbuf(P_table)
@@ -263,25 +278,25 @@ class EncoderBlockFn(torch.autograd.Function):
         scale = hd ** -0.5
         dev = x2d.device
         g = dx2.reshape(T, C).contiguous()
-        gs = ops.scale_rows(g, dp_m, H * W)
+        gs, dpf = _fold(g, dp_m, H * W)
         dxn2, (dW1, db1, dwdw, dbdw, dW2, db2) = leff_bwd(gs, dict(u1=u1, h1=h1, u2=u2, h2=h2), xn2, P_w1, P_b1, P_wdw,
-                                                         P_bdw, P_w2, P_b2, LB, H, W)
+                                                         P_bdw, P_w2, P_b2, LB, H, W, dp=dpf)
         dn2w, dn2wr = _wbuf(P_n2w)
         dn2b, dn2br = _wbuf(P_n2b)
         g1 = ops.layernorm_bwd(dxn2, x1, mean2, rstd2, n2w, g, dn2w, dn2b)
         _ready(P_n2w, P_n2b)
-        gs1 = ops.scale_rows(g1, dp_a, H * W)
+        gs1, dpf = _fold(g1, dp_a, H * W)
         dq = torch.empty(T, C, device=dev)
         dkv = torch.empty(T, 2 * C, device=dev)
         gB = [None] * 7
         if msa == 'origin':
-            doA, dWpA, dbpA = linear_param_grads(gs1, oA, P_wpA, P_bpA)
+            doA, dWpA, dbpA = linear_param_grads(gs1, oA, P_wpA, P_bpA, dp=dpf, rps=H * W)
             dtabA = _z(tabA)
             qA_, kvA_ = _QKV(buf=qkvA).views(T, C)
             ops.win_attn_bwd(qA_, kvA_, doA, dq, dkv, LB, H, W, heads, hd, shift, scale, tabA, dtabA, None,
                              heads, None, None, 0)
         else:
-            doB, dWpB, dbpB = linear_param_grads(gs1, oB, P_wpB, P_bpB)
+            doB, dWpB, dbpB = linear_param_grads(gs1, oB, P_wpB, P_bpB, dp=dpf, rps=H * W)
             dtabB = _z(tabB)
             qB_, kvB_ = _QKV(buf=qkvB).views(T, C)
             ops.joint_attn_bwd(qB_, kvB_, doB, dq, dkv, L, B, H, W, heads, hd, shift, scale, tabB, dtabB, 1)

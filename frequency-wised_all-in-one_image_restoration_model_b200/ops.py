@@ -81,7 +81,7 @@ def _rows2d(t):
 
 def gemm(A, B, C, transA=False, transB=True, bias=None, act=ACT_NONE, act_param=0.0, aux=None, aux_act=ACT_NONE,
          aux_param=0.0, rowscale=None, rows_per_scale=1, residual=None, accumulate=False, alpha=1.0, preact=None,
-         backend=None, a_rowsum=None):
+         backend=None, a_rowsum=None, a_kscale=None, a_k_rows_per_scale=1):
     """C = epi(alpha * op(A) @ op(B)); see fa_gemm in include/freqair.h.  A, B, C, aux, residual, preact are 2-D
     row-major views (row stride may exceed the width).  transB=True means B is an nn.Linear weight [N, K]."""
     ar, ac, lda = _rows2d(A)
@@ -120,6 +120,12 @@ def gemm(A, B, C, transA=False, transB=True, bias=None, act=ACT_NONE, act_param=
         if a_rowsum.numel() != M:
             raise RuntimeError(f'freqair.gemm: a_rowsum has {a_rowsum.numel()} entries, expected M={M}')
         e.a_rowsum = a_rowsum.data_ptr()
+    if a_kscale is not None:            # op(A)[m, k] *= a_kscale[k // a_k_rows_per_scale] inside the contraction
+        _f32(a_kscale)
+        if a_kscale.numel() * a_k_rows_per_scale < K:
+            raise RuntimeError(f'freqair.gemm: a_kscale covers {a_kscale.numel() * a_k_rows_per_scale} of K={K}')
+        e.a_kscale = a_kscale.data_ptr()
+        e.a_k_rows_per_scale = a_k_rows_per_scale
     _call('fa_gemm', _p(A), _p(B), _p(C), M, N, K, lda, ldb, ldc, int(transA), int(transB), ctypes.byref(e), backend,
           _stream())
     return C

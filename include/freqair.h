@@ -60,6 +60,12 @@ typedef struct FaGemmEpilogue {
   float* a_rowsum;                /* if set: a_rowsum[m] += sum_k op(A)[m,k].  With transA = 1 (dW = dY^T X) this is the
                                      column sum of the stored dY, i.e. the bias gradient, taken while the A tiles pass
                                      through the kernel instead of in a second pass over dY (fa_colsum) */
+  /* if a_kscale is set: op(A)[m,k] is multiplied by a_kscale[k / a_k_rows_per_scale] on its way into the contraction
+     (and into a_rowsum).  With transA = 1 and k = token index this is the per-sample DropPath scale of timm's DropPath
+     backward folded into dW = (D dY)^T X, so the scaled gradient is never materialised.  a_k_rows_per_scale % 32 == 0;
+     tcgen05 path only (an ineligible shape is an error, not a fallback). */
+  const float* a_kscale;
+  int a_k_rows_per_scale;
 } FaGemmEpilogue;
 int fa_gemm(const float* A, const float* B, float* C, int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc,
             int transA, int transB, const FaGemmEpilogue* epi, int backend, fa_stream_t stream);

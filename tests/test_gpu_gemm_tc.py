@@ -139,3 +139,35 @@ def test_gemm_a_rowsum(ops, M, N, K, tA, backend):
     assert (C.double().cpu() - ref).abs().max().item() <= tol * 10
     ref_rs = rs0.double() + opA.sum(1)
     assert (rs.double().cpu() - ref_rs).abs().max().item() <= 2e-6 * K ** 0.5 * 0.1 * 8 + 1e-5
+
+
+@pytest.mark.parametrize('backend', [0, 2])
+def test_gemm_a_kscale_and_bwd_rowscale(ops, backend):
+    """DropPath backward folded into the contractions: dW += (D dY)^T X with D = per-sample scale along the reduction
+    (FaGemmEpilogue.a_kscale, also applied to a_rowsum), and dX = D (dY W) * gelu'(aux) with the row scale in the BWD
+    epilogue."""
+    T, Co, Ci, rps = 6 * 64, 56, 224, 64
+    dY, X = gen(T, Co, scale=0.1), gen(T, Ci, seed=1)
+    dp = torch.tensor([0.0, 1 / 0.9, 1 / 0.9, 0.0, 1 / 0.9, 1 / 0.9])
+    sc = dp.repeat_interleave(rps)[:, None]
+    G0, b0 = gen(Co, Ci, seed=2), gen(Co, seed=3)
+    G, bsum = G0.cuda(), b0.cuda()
+    ops.gemm(dY.cuda(), X.cuda(), G, transA=True, transB=False, accumulate=True, a_rowsum=bsum, a_kscale=dp.cuda(),
+             a_k_rows_per_scale=rps, backend=backend)
+    ref = G0.double() + (dY * sc).double().t() @ X.double()
+    assert (G.double().cpu() - ref).abs().max().item() <= 2e-5
+    assert (bsum.double().cpu() - (b0.double() + (dY * sc).double().sum(0))).abs().max().item() <= 2e-5
+    W, aux = gen(Co, Ci, seed=4, scale=0.1), gen(T, Ci, seed=5)
+    dX = torch.empty(T, Ci, device='cuda')
+    ops.gemm(dY.cuda(), W.cuda(), dX, transB=False, aux=aux.cuda(), aux_act=ops.ACT_GELU, rowscale=dp.cuda(),
+             rows_per_scale=rps, backend=backend)
+    ag = aux.clone().double().requires_grad_(True)
+    F.gelu(ag).sum().backward()
+    refx = (dY * sc).double() @ W.double() * ag.grad
+    assert (dX.double().cpu() - refx).abs().max().item() <= 2e-5
+    dX2 = torch.empty(T, Ci, device='cuda')
+    ops.gemm(dY.cuda(), W.cuda(), dX2, transB=False, rowscale=dp.cuda(), rows_per_scale=rps, backend=backend)
+    assert (dX2.double().cpu() - (dY * sc).double() @ W.double()).abs().max().item() <= 2e-5
+    with pytest.raises(RuntimeError):            # no silent fallback: the SIMT kernel has no a_kscale
+        ops.gemm(dY.cuda(), X.cuda(), G, transA=True, transB=False, accumulate=True, a_kscale=dp.cuda(),
+                 a_k_rows_per_scale=rps, backend=1)

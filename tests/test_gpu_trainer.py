@@ -121,3 +121,33 @@ def test_encoder_only_phase_and_spectral_l1_term():
     assert abs(l1.item() - ref.item()) <= 1e-5 * abs(ref.item())
     d = (restored.grad.cpu() - r.grad)
     assert d.norm().item() <= 2e-3 * r.grad.norm().item()
+
+
+def test_folded_droppath_equals_materialised_scale():
+    """DropPath backward folded into the contractions (a_kscale / epilogue row scale) against the fa_scale_rows path:
+    same DropPath draws (forced), same gradients."""
+    lewin = importlib.import_module(PKG_NAME + '.net.lewin')
+    net, ts, x = build()
+    g = torch.Generator(device='cuda').manual_seed(3)
+    for m in net.modules():
+        if hasattr(m, 'forced_dp'):
+            B = 2 * (3 if 'encoder' in type(m).__module__ else 1)
+            draw = lambda: (torch.rand(B, device='cuda', generator=g) > 0.3).float() / 0.7
+            m.forced_dp = (draw(), draw())
+    grads = {}
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    try:
+        for fold in (True, False):
+            net.load_state_dict(sd0)                 # the forward moves the MoCo queue, key encoder and BN statistics
+            lewin.FOLD_DROPPATH = fold
+            ts.zero_grad()
+            restored, logits, labels = net(*x[:2])
+            loss, _, _ = ts.loss(restored, logits, labels, x[2])
+            loss.backward()
+            grads[fold] = [s.grad.clone() for s in ts.segments]
+    finally:
+        lewin.FOLD_DROPPATH = True
+    for a, b in zip(grads[True], grads[False]):
+        scale = b.abs().max().item()
+        assert (a - b).abs().max().item() <= 2e-5 * scale + 1e-8
+        assert a.abs().sum().item() > 0
