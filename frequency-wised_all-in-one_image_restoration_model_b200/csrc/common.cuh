@@ -78,7 +78,8 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // activations shared by GEMM epilogues / conv kernels
-enum { ACT_NONE = 0, ACT_GELU = 1, ACT_LRELU = 2, ACT_SIGMOID = 3 };
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_LRELU = 2, ACT_SIGMOID = 3,
+       ACT_MUL = 4 };   // aux_act only: aux already holds the derivative (gelu'(u) stored by the forward), multiply by it
 
 // Exact-erf GELU (nn.GELU default) and its derivative.  Phi(x) = 0.5 (1 + erf(x / sqrt 2)) is evaluated as
 // 0.5 erfc(|z|) = 0.5 poly5(t) exp(-z^2), t = 1 / (1 + p |z|)  (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7 on erf)
@@ -107,6 +108,13 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   const float cdf = gelu_cdf(x, e);
   return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
+// gelu(x) and gelu'(x) from one cdf / exp evaluation
+__device__ __forceinline__ float gelu_pair_f(float x, float& dg) {
+  float e;
+  const float cdf = gelu_cdf(x, e);
+  dg = fmaf(x * 0.39894228040143267794f, e, cdf);
+  return x * cdf;
+}
 __device__ __forceinline__ float act_f(float x, int act, float p) {
   if (act == ACT_GELU) return gelu_f(x);
   if (act == ACT_LRELU) return x > 0.f ? x : x * p;
@@ -117,6 +125,7 @@ __device__ __forceinline__ float act_grad_f(float x, int act, float p) {   // d 
   if (act == ACT_GELU) return gelu_grad_f(x);
   if (act == ACT_LRELU) return x > 0.f ? 1.0f : p;
   if (act == ACT_SIGMOID) { float s = 1.0f / (1.0f + __expf(-x)); return s * (1.0f - s); }
+  if (act == ACT_MUL) return x;
   return 1.0f;
 }
 #endif

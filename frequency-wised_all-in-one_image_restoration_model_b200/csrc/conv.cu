@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(DWF_THREADS, 1) dwconv_strip_kernel(const floa
                                                                       const float* __restrict__ w,
                                                                       const float* __restrict__ bias,
                                                                       float* __restrict__ outA, float* __restrict__ outB,
-                                                                      StripGeom g, int nstrips) {
+                                                                      StripGeom g, int nstrips, int a_mode) {
   extern __shared__ __align__(16) float dwf_smem[];
   const int c = (blockIdx.y * 32 + threadIdx.x) * 4;
   if (c >= g.C) return;
@@ -114,8 +114,16 @@ __global__ void __launch_bounds__(DWF_THREADS, 1) dwconv_strip_kernel(const floa
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) acc = fma4(win[kx][r + ky], wv[ky * 3 + kx], acc);
         const int64_t o = img + ((int64_t)(y0 + r) * g.W + x) * g.C;
-        st4(outA + o, acc);
-        if (outB) st4(outB + o, make_float4(gelu_f(acc.x), gelu_f(acc.y), gelu_f(acc.z), gelu_f(acc.w)));
+        if (a_mode == 0) {
+          if (outA) st4(outA + o, acc);
+          if (outB) st4(outB + o, make_float4(gelu_f(acc.x), gelu_f(acc.y), gelu_f(acc.z), gelu_f(acc.w)));
+        } else {                                   // outA = gelu'(u2): what the backward multiplies by, from the same cdf / exp
+          float4 dgv, gv;
+          gv.x = gelu_pair_f(acc.x, dgv.x); gv.y = gelu_pair_f(acc.y, dgv.y);
+          gv.z = gelu_pair_f(acc.z, dgv.z); gv.w = gelu_pair_f(acc.w, dgv.w);
+          st4(outA + o, dgv);
+          if (outB) st4(outB + o, gv);
+        }
       }
     }
     cp_async_wait<0>();
@@ -596,9 +604,10 @@ static StripGeom make_strips_persistent(int B, int H, int W, int C, int warps, i
   return best;
 }
 
-int fa_dwconv3x3_fwd(const float* h1, const float* w, const float* b, float* u2, float* h2, int B, int H, int W, int C,
-                     fa_stream_t stream) {
-  FA_REQUIRE(h1 && w && u2, "fa_dwconv3x3_fwd: null pointer");
+int fa_dwconv3x3_fwd(const float* h1, const float* w, const float* b, float* u2, float* h2, int u2_mode, int B, int H,
+                     int W, int C, fa_stream_t stream) {
+  FA_REQUIRE(h1 && w && (u2 || h2), "fa_dwconv3x3_fwd: null pointer");
+  FA_REQUIRE(u2_mode == 0 || (u2_mode == 1 && u2), "fa_dwconv3x3_fwd: u2_mode must be 0, or 1 with u2 set");
   FA_REQUIRE(C % 4 == 0, "fa_dwconv3x3_fwd: C=%d must be a multiple of 4", C);
   cudaStream_t st = (cudaStream_t)stream;
   FaProfScope prof(FA_K_DWCONV, st);
@@ -610,7 +619,7 @@ int fa_dwconv3x3_fwd(const float* h1, const float* w, const float* b, float* u2,
     FA_CUDA(cudaFuncSetAttribute(dwconv_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DWF_SMEM));
     attr_set = true;
   }
-  dwconv_strip_kernel<<<grid, dim3(32, DWF_WARPS), DWF_SMEM, st>>>(h1, w, b, u2, h2, g, nstrips);
+  dwconv_strip_kernel<<<grid, dim3(32, DWF_WARPS), DWF_SMEM, st>>>(h1, w, b, u2, h2, g, nstrips, u2_mode);
   FA_LAUNCH_CHECK("fa_dwconv3x3_fwd");
   return FA_OK;
 }

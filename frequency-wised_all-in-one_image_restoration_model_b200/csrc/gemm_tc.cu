@@ -230,6 +230,7 @@ __device__ __forceinline__ float actg_c(float x, float p) {
   if (ACT == ACT_GELU) return gelu_grad_f(x);
   if (ACT == ACT_LRELU) return x > 0.f ? 1.0f : p;
   if (ACT == ACT_SIGMOID) { const float sg = 1.0f / (1.0f + __expf(-x)); return sg * (1.0f - sg); }
+  if (ACT == ACT_MUL) return x;
   return 1.0f;
 }
 
@@ -603,6 +604,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
               if (act == ACT_GELU) epi_rows<MODE, ACT_GELU>(stg_s, epi, b4, row0, rsub, c4, col, g.M, cp0, g.ldc);
               else if (act == ACT_LRELU) epi_rows<MODE, ACT_LRELU>(stg_s, epi, b4, row0, rsub, c4, col, g.M, cp0, g.ldc);
               else if (act == ACT_SIGMOID) epi_rows<MODE, ACT_SIGMOID>(stg_s, epi, b4, row0, rsub, c4, col, g.M, cp0, g.ldc);
+              else if (MODE == EPI_BWD && act == ACT_MUL) epi_rows<MODE, ACT_MUL>(stg_s, epi, b4, row0, rsub, c4, col, g.M, cp0, g.ldc);
               else epi_rows<MODE, ACT_NONE>(stg_s, epi, b4, row0, rsub, c4, col, g.M, cp0, g.ldc);
             }
           } else {

@@ -118,10 +118,11 @@ def linear_param_grads(g, x, W, b, want_dx=True, dx=None, accumulate_dx=False, d
 def leff_fwd(xn2, w1, b1, wdw, bdw, w2, b2, B, H, W, residual, dp_scale, save):
     T, C = xn2.shape
     Ch = w1.shape[0]
-    u1 = torch.empty(T, Ch, device=xn2.device, dtype=torch.float32)
-    h1 = torch.empty_like(u1)
+    h1 = torch.empty(T, Ch, device=xn2.device, dtype=torch.float32)
+    u1 = torch.empty_like(h1) if save is not None else None          # pre-activation: only the backward reads it
     ops.gemm(xn2, w1, h1, bias=b1, act=ops.ACT_GELU, preact=u1)
-    u2, h2 = ops.dwconv_fwd(h1, wdw, bdw, B, H, W, Ch)
+    # saved for the backward: gelu'(u2), not u2 - it only ever multiplies dh2 (leff_bwd); nothing in inference
+    u2, h2 = ops.dwconv_fwd(h1, wdw, bdw, B, H, W, Ch, u2_mode=1 if save is not None else None)
     out = torch.empty(T, w2.shape[0], device=xn2.device, dtype=torch.float32)
     ops.gemm(h2, w2, out, bias=b2, rowscale=dp_scale, rows_per_scale=H * W, residual=residual)
     if save is not None:
@@ -138,7 +139,7 @@ def leff_bwd(gs, sv, xn2, w1, b1, wdw, bdw, w2, b2, B, H, W, dp=None):
     ops.gemm(gs, sv['h2'], dW2, transA=True, transB=False, accumulate=True, a_rowsum=db2b, a_kscale=dp,
              a_k_rows_per_scale=H * W)
     du2 = torch.empty_like(sv['u2'])
-    ops.gemm(gs, w2, du2, transB=False, aux=sv['u2'], aux_act=ops.ACT_GELU, rowscale=dp, rows_per_scale=H * W)
+    ops.gemm(gs, w2, du2, transB=False, aux=sv['u2'], aux_act=ops.ACT_MUL, rowscale=dp, rows_per_scale=H * W)   # u2 = gelu'
     dwdw, dwdwr = _wbuf(wdw)
     dbdw, dbdwr = _wbuf(bdw)
     du1 = ops.dwconv_bwd(du2, sv['h1'], sv['u1'], wdw, dwdw, dbdw, B, H, W, wdw.shape[0])
@@ -170,8 +171,11 @@ class DecoderBlockFn(torch.autograd.Function):
         x1 = torch.empty(T, C, device=x.device, dtype=torch.float32)
         ops.gemm(o, wp, x1, bias=bp, rowscale=dp_a, rows_per_scale=H * W, residual=x2d)
         xn2, mean2, rstd2 = ops.layernorm_fwd(x1, n2w, n2b)
-        sv = {}
+        need_bwd = any(ctx.needs_input_grad)
+        sv = {} if need_bwd else None                 # inference: the LeFF intermediates u1, u2 are never stored
         x2 = leff_fwd(xn2, w1, b1, wdw, bdw, w2, b2, B, H, W, x1, dp_m, sv)
+        if not need_bwd:
+            return x2.view(B, H * W, C)
         ctx.cfg = cfg
         ctx.has = (coef is not None, dp_a is not None, dp_m is not None)
         ctx.params = (n1w, n1b, table, wq, bq, wkv, bkv, wp, bp, n2w, n2b, w1, b1, wdw, bdw, w2, b2)
@@ -255,8 +259,11 @@ class EncoderBlockFn(torch.autograd.Function):
             ops.joint_attn_fwd(qB_, kvB_, oB, L, B, H, W, heads, hd, shift, scale, tabB, 1)
             ops.gemm(oB, wpB, x1, bias=bpB, rowscale=dp_a, rows_per_scale=H * W, residual=x2d)
         xn2, mean2, rstd2 = ops.layernorm_fwd(x1, n2w, n2b)
-        sv = {}
+        need_bwd = any(ctx.needs_input_grad)
+        sv = {} if need_bwd else None
         x2 = leff_fwd(xn2, w1, b1, wdw, bdw, w2, b2, LB, H, W, x1, dp_m, sv)
+        if not need_bwd:
+            return x2.view(LB, H * W, C)
         ctx.cfg = cfg
         ctx.params = (n1w, n1b, wqA, bqA, wkvA, bkvA, wpA, bpA, wqB, bqB, wkvB, bkvB, wpB, bpB, n2w, n2b, w1, b1, wdw,
                       bdw, w2, b2)

@@ -13,6 +13,7 @@ from . import _lib
 from ._lib import FaGemmEpilogue
 
 ACT_NONE, ACT_GELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
+ACT_MUL = 4                     # aux_act only: aux already holds the derivative, multiply by it
 FLOP_COUNTER = [None]          # bench.py roofline leg: set to 0 to accumulate 2*M*N*K of every fa_gemm call
 # fa_gemm backend used when a call does not name one: 0 = auto (tcgen05 3xTF32 where eligible, else fp32 SIMT).
 # FREQAIR_GEMM_BACKEND=1 forces the fp32 SIMT kernel everywhere (A/B accuracy and speed comparisons).
@@ -285,11 +286,13 @@ def token_mean_bwd(dy, B, HW, C):
 
 
 # ----------------------------------------------------------------------------- conv pieces
-def dwconv_fwd(h1, w, b, B, H, W, C, want_act=True):
+def dwconv_fwd(h1, w, b, B, H, W, C, want_act=True, u2_mode=0):
+    """(u2, h2) = (dwconv(h1) + b, gelu(u2)).  u2_mode=1: the first output is gelu'(u2) (what the backward multiplies by);
+    u2_mode=None: u2 is not stored at all (inference)."""
     _f32(h1, w, b)
-    u2 = torch.empty_like(h1)
+    u2 = torch.empty_like(h1) if u2_mode is not None else None
     h2 = torch.empty_like(h1) if want_act else None
-    _call('fa_dwconv3x3_fwd', _p(h1), _p(w), _p(b), _p(u2), _p(h2), B, H, W, C, _stream())
+    _call('fa_dwconv3x3_fwd', _p(h1), _p(w), _p(b), _p(u2), _p(h2), u2_mode or 0, B, H, W, C, _stream())
     return u2, h2
 
 

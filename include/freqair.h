@@ -167,10 +167,12 @@ int fa_token_mean_bwd(const float* dy, float* dx, int B, int HW, int C, fa_strea
 /* ------------------------------------------------------------------ convolutions on tokens (K4, K5)
  * depthwise 3x3 of LeFF in token layout with the second GELU fused (leff.py:85-86,100-112); the first GELU is the
  * producing GEMM's epilogue (which also stores the pre-activation u1 for the backward):
- *   fwd: u2 = dwconv(h1) + b ; h2 = gelu(u2)            (h1 = gelu(u1))
+ *   fwd: u2 = dwconv(h1) + b ; h2 = gelu(u2)            (h1 = gelu(u1)).  u2_mode = 1 stores gelu'(u2) in `u2` instead
+ *        (the only thing the backward needs u2 for: the dX contraction then multiplies by it with aux_act = 4, no
+ *        transcendental in its epilogue); u2 or h2 may be NULL (inference stores h2 only).
  *   bwd: du1 = gelu'(u1) * dwconv^T(du2)  (u1 NULL: plain adjoint) ; dw, db ACCUMULATE (dw NULL: skipped). */
-int fa_dwconv3x3_fwd(const float* h1, const float* w, const float* b, float* u2, float* h2, int B, int H, int W, int C,
-                     fa_stream_t stream);
+int fa_dwconv3x3_fwd(const float* h1, const float* w, const float* b, float* u2, float* h2, int u2_mode, int B, int H,
+                     int W, int C, fa_stream_t stream);
 int fa_dwconv3x3_bwd(const float* du2, const float* h1, const float* u1, const float* w, float* du1, float* dw,
                      float* db, int B, int H, int W, int C, fa_stream_t stream);
 /* patch gather / its adjoint for dense convs run as GEMMs: col[(b,oy,ox)][(ky,kx,ci)].

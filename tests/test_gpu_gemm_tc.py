@@ -98,6 +98,8 @@ def test_gemm_tc_epilogues(ops):
     F.gelu(ag).sum().backward()
     ops.gemm(dA, dW, C, aux=aux.cuda(), aux_act=ops.ACT_GELU, backend=2)
     tf32_close(C, (A @ W.t()) * ag.grad, K, 'dgelu')
+    ops.gemm(dA, dW, C, aux=aux.cuda(), aux_act=ops.ACT_MUL, backend=2)        # aux already holds the derivative
+    tf32_close(C, (A @ W.t()) * aux, K, 'aux multiply')
     big = torch.zeros(M, 2 * N, device='cuda'); big[:, N:] = R.cuda()
     ops.gemm(dA, dW, big[:, N:], accumulate=True, alpha=0.5, backend=2)
     tf32_close(big[:, N:], R + 0.5 * (A @ W.t()), K, 'accumulate strided')

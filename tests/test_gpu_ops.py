@@ -148,6 +148,12 @@ def test_dwconv(ops, B, H, W, C):
     h1d = dev(h1.detach())
     u2k, h2k = ops.dwconv_fwd(h1d, dev(w.detach()), dev(b.detach()), B, H, W, C)
     close(u2k, u2, 1e-5, 'dw u2'); close(h2k, h2, 1e-5, 'dw h2')
+    d2k, h2k2 = ops.dwconv_fwd(h1d, dev(w.detach()), dev(b.detach()), B, H, W, C, u2_mode=1)      # stores gelu'(u2)
+    ug = u2.detach().clone().requires_grad_(True)
+    F.gelu(ug).sum().backward()
+    close(d2k, ug.grad, 1e-5, "dw gelu'(u2)"); assert torch.equal(h2k2, h2k)
+    none, h2k3 = ops.dwconv_fwd(h1d, dev(w.detach()), dev(b.detach()), B, H, W, C, u2_mode=None)  # inference: h2 only
+    assert none is None and torch.equal(h2k3, h2k)
     du2 = ops.act_bwd(dev(dh2), u2k, ops.ACT_GELU)
     dw, db = torch.zeros(C, 1, 3, 3, device='cuda'), torch.zeros(C, device='cuda')
     du1 = ops.dwconv_bwd(du2, h1d, dev(u1.detach()), dev(w.detach()), dw, db, B, H, W, C)
