@@ -97,6 +97,7 @@ def bench_epi(backend):
         ('leff2 +bias+rs+res', lambda: ops.gemm(Hh, W2, Y, bias=b2, rowscale=rs, rows_per_scale=16384, residual=R, backend=backend), 4 * (2 * M * C + M * Hd)),
         ('dX2 plain (NN)', lambda: ops.gemm(G, W2, dU, transB=False, backend=backend), 4 * (M * C + M * Hd)),
         ('dX2 *gelu\'(aux) (NN)', lambda: ops.gemm(G, W2, dU, transB=False, aux=U, aux_act=ops.ACT_GELU, backend=backend), 4 * (M * C + 2 * M * Hd)),
+        ('dX2 *aux (NN, ACT_MUL)', lambda: ops.gemm(G, W2, dU, transB=False, aux=U, aux_act=ops.ACT_MUL, backend=backend), 4 * (M * C + 2 * M * Hd)),
         ('dX1 accumulate (NN)', lambda: ops.gemm(dU, W1, Y, transB=False, accumulate=True, backend=backend), 4 * (2 * M * C + M * Hd)),
     ]
     for name, fn, byts in cases:
