@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256, 1) dwconv_bwd_strip_kernel(const float* _
             const bool ok = y0 + r < g.H;
             const int64_t o = ok ? img + ((int64_t)(y0 + r) * g.W + x) * g.C : 0;
             if (u1) cp_async16(a + (DW_R + 2 + r) * 4096u, u1 + o, ok);
-            if (dw) cp_async16(a + (2 * DW_R + 2 + r) * 4096u, h1 + o, ok);
+            if (dw && h1) cp_async16(a + (2 * DW_R + 2 + r) * 4096u, h1 + o, ok);
           }
         }
         cp_async_commit();
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256, 1) dwconv_bwd_strip_kernel(const float* _
 #pragma unroll
         for (int r = 0; r < DW_R; ++r) {
           if (u1) uq[r] = lds4(a + (DW_R + 2 + r) * 4096u);
-          if (dw) hq[r] = lds4(a + (2 * DW_R + 2 + r) * 4096u);
+          if (dw && h1) hq[r] = lds4(a + (2 * DW_R + 2 + r) * 4096u);
         }
         issue(x + DWB_RING, s);                                   // the slot's values are in registers now
         s = (s + 1 == DWB_RING) ? 0 : s + 1;
@@ -225,7 +225,11 @@ __global__ void __launch_bounds__(256, 1) dwconv_bwd_strip_kernel(const float* _
             for (int kx = 0; kx < 3; ++kx) d = fma4(win[kx][r + ky], wv[ky * 3 + kx], d);
           if (u1) {
             const float4 u = uq[r];
-            d = make_float4(d.x * gelu_grad_f(u.x), d.y * gelu_grad_f(u.y), d.z * gelu_grad_f(u.z), d.w * gelu_grad_f(u.w));
+            float4 dg, gv;                                       // gelu'(u1) and h1 = gelu(u1) from one cdf / exp
+            gv.x = gelu_pair_f(u.x, dg.x); gv.y = gelu_pair_f(u.y, dg.y);
+            gv.z = gelu_pair_f(u.z, dg.z); gv.w = gelu_pair_f(u.w, dg.w);
+            d = make_float4(d.x * dg.x, d.y * dg.y, d.z * dg.z, d.w * dg.w);
+            if (!h1) hq[r] = gv;                                 // h1 not passed: recomputed, one stream less to read
           }
           st4(du1 + o, d);
           if (dw) {
@@ -633,7 +637,7 @@ int fa_dwconv3x3_bwd(const float* du2, const float* h1, const float* u1, const f
   if ((int64_t)B * H * W * C == 0) return FA_OK;
   int nstrips; dim3 grid;
   const StripGeom g = make_strips_persistent(B, H, W, C, 8, nstrips, grid);
-  FA_REQUIRE(!dw || h1, "fa_dwconv3x3_bwd: h1 required for the weight gradient");
+  FA_REQUIRE(!dw || h1 || u1, "fa_dwconv3x3_bwd: the weight gradient needs h1, or u1 to recompute h1 = gelu(u1)");
   static bool attr_set = false;
   if (!attr_set) {
     FA_CUDA(cudaFuncSetAttribute(dwconv_bwd_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DWB_SMEM));

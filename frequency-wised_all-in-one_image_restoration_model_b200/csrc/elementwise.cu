@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256) band_coef_fwd_kernel(const float* __restr
 __global__ void __launch_bounds__(256) band_coef_bwd_kernel(const float* __restrict__ stats, CoefP p,
                                                             const float* __restrict__ dout, int64_t ld_b, int64_t ld_h,
                                                             float* __restrict__ dstats, CoefG g, int D, int heads) {
-  __shared__ float z[1024], e[32], pre[32], h[32], dh[32], dpre[32], de[32], dz[1024];
+  __shared__ float z[1024], e[32], pre[32], h[32], dh[32], dpre[32], de[32];
   const int b = blockIdx.x, tid = threadIdx.x;
   const float* s = stats + (int64_t)b * D;
   coef_forward(s, p, D, heads, z, e, pre, h);

@@ -126,7 +126,7 @@ def leff_fwd(xn2, w1, b1, wdw, bdw, w2, b2, B, H, W, residual, dp_scale, save):
     out = torch.empty(T, w2.shape[0], device=xn2.device, dtype=torch.float32)
     ops.gemm(h2, w2, out, bias=b2, rowscale=dp_scale, rows_per_scale=H * W, residual=residual)
     if save is not None:
-        save.update(u1=u1, h1=h1, u2=u2, h2=h2)
+        save.update(u1=u1, u2=u2, h2=h2)          # h1 = gelu(u1) is recomputed by the depthwise-conv backward
     return out
 
 
@@ -142,7 +142,7 @@ def leff_bwd(gs, sv, xn2, w1, b1, wdw, bdw, w2, b2, B, H, W, dp=None):
     ops.gemm(gs, w2, du2, transB=False, aux=sv['u2'], aux_act=ops.ACT_MUL, rowscale=dp, rows_per_scale=H * W)   # u2 = gelu'
     dwdw, dwdwr = _wbuf(wdw)
     dbdw, dbdwr = _wbuf(bdw)
-    du1 = ops.dwconv_bwd(du2, sv['h1'], sv['u1'], wdw, dwdw, dbdw, B, H, W, wdw.shape[0])
+    du1 = ops.dwconv_bwd(du2, None, sv['u1'], wdw, dwdw, dbdw, B, H, W, wdw.shape[0])      # h1 = gelu(u1) recomputed
     _ready(w2, b2, wdw, bdw)
     dxn2, dW1r, db1r = linear_param_grads(du1, xn2, w1, b1)
     return dxn2, (dW1r, db1r, dwdwr, dbdwr, dW2r, db2)
@@ -179,13 +179,13 @@ class DecoderBlockFn(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.has = (coef is not None, dp_a is not None, dp_m is not None)
         ctx.params = (n1w, n1b, table, wq, bq, wkv, bkv, wp, bp, n2w, n2b, w1, b1, wdw, bdw, w2, b2)
-        ctx.save_for_backward(x2d, mean1, rstd1, xn, qkv, o, x1, mean2, rstd2, xn2, sv['u1'], sv['h1'], sv['u2'],
+        ctx.save_for_backward(x2d, mean1, rstd1, xn, qkv, o, x1, mean2, rstd2, xn2, sv['u1'], sv['u2'],
                               sv['h2'], coef, dp_a, dp_m, n1w, table, wq, wkv, wp, n2w, w1, wdw, w2)
         return x2.view(B, H * W, C)
 
     @staticmethod
     def backward(ctx, dx2):
-        (x2d, mean1, rstd1, xn, qkv, o, x1, mean2, rstd2, xn2, u1, h1, u2, h2, coef, dp_a, dp_m, n1w, table, wq, wkv,
+        (x2d, mean1, rstd1, xn, qkv, o, x1, mean2, rstd2, xn2, u1, u2, h2, coef, dp_a, dp_m, n1w, table, wq, wkv,
          wp, n2w, w1, wdw, w2) = ctx.saved_tensors
         (P_n1w, P_n1b, P_table, P_wq, P_bq, P_wkv, P_bkv, P_wp, P_bp, P_n2w, P_n2b, P_w1, P_b1, P_wdw, P_bdw, P_w2,
          P_b2) = ctx.params
@@ -194,7 +194,7 @@ class DecoderBlockFn(torch.autograd.Function):
         hd = C // heads
         g = dx2.reshape(T, C).contiguous()
         gs, dpf = _fold(g, dp_m, H * W)
-        dxn2, (dW1, db1, dwdw, dbdw, dW2, db2) = leff_bwd(gs, dict(u1=u1, h1=h1, u2=u2, h2=h2), xn2, P_w1, P_b1, P_wdw,
+        dxn2, (dW1, db1, dwdw, dbdw, dW2, db2) = leff_bwd(gs, dict(u1=u1, u2=u2, h2=h2), xn2, P_w1, P_b1, P_wdw,
                                                          P_bdw, P_w2, P_b2, B, H, W, dp=dpf)
         dn2w, dn2wr = _wbuf(P_n2w)
         dn2b, dn2br = _wbuf(P_n2b)
@@ -267,14 +267,14 @@ class EncoderBlockFn(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.params = (n1w, n1b, wqA, bqA, wkvA, bkvA, wpA, bpA, wqB, bqB, wkvB, bkvB, wpB, bpB, n2w, n2b, w1, b1, wdw,
                       bdw, w2, b2)
-        ctx.save_for_backward(x2d, mean1, rstd1, xn, qkvA, oA, yA, qkvB, oB, x1, mean2, rstd2, xn2, sv['u1'], sv['h1'],
+        ctx.save_for_backward(x2d, mean1, rstd1, xn, qkvA, oA, yA, qkvB, oB, x1, mean2, rstd2, xn2, sv['u1'],
                               sv['u2'], sv['h2'], dp_a, dp_m, n1w, tabA, wqA, wkvA, wpA, tabB, wqB, wkvB, wpB, n2w, w1,
                               wdw, w2)
         return x2.view(LB, H * W, C)
 
     @staticmethod
     def backward(ctx, dx2):
-        (x2d, mean1, rstd1, xn, qkvA, oA, yA, qkvB, oB, x1, mean2, rstd2, xn2, u1, h1, u2, h2, dp_a, dp_m, n1w, tabA,
+        (x2d, mean1, rstd1, xn, qkvA, oA, yA, qkvB, oB, x1, mean2, rstd2, xn2, u1, u2, h2, dp_a, dp_m, n1w, tabA,
          wqA, wkvA, wpA, tabB, wqB, wkvB, wpB, n2w, w1, wdw, w2) = ctx.saved_tensors
         (P_n1w, P_n1b, P_wqA, P_bqA, P_wkvA, P_bkvA, P_wpA, P_bpA, P_wqB, P_bqB, P_wkvB, P_bkvB, P_wpB, P_bpB, P_n2w,
          P_n2b, P_w1, P_b1, P_wdw, P_bdw, P_w2, P_b2) = ctx.params
@@ -286,7 +286,7 @@ class EncoderBlockFn(torch.autograd.Function):
         dev = x2d.device
         g = dx2.reshape(T, C).contiguous()
         gs, dpf = _fold(g, dp_m, H * W)
-        dxn2, (dW1, db1, dwdw, dbdw, dW2, db2) = leff_bwd(gs, dict(u1=u1, h1=h1, u2=u2, h2=h2), xn2, P_w1, P_b1, P_wdw,
+        dxn2, (dW1, db1, dwdw, dbdw, dW2, db2) = leff_bwd(gs, dict(u1=u1, u2=u2, h2=h2), xn2, P_w1, P_b1, P_wdw,
                                                          P_bdw, P_w2, P_b2, LB, H, W, dp=dpf)
         dn2w, dn2wr = _wbuf(P_n2w)
         dn2b, dn2br = _wbuf(P_n2b)

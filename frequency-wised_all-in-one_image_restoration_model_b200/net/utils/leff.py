@@ -20,17 +20,17 @@ class _LeFFFn(torch.autograd.Function):
         y = leff_fwd(x2, w1, b1, wdw, bdw, w2, b2, B, H, W, None, None, sv)
         ctx.geom = (B, H, W)
         ctx.params = (w1, b1, wdw, bdw, w2, b2)
-        ctx.save_for_backward(x2, sv['u1'], sv['h1'], sv['u2'], sv['h2'], w1, wdw, w2)
+        ctx.save_for_backward(x2, sv['u1'], sv['u2'], sv['h2'], w1, wdw, w2)
         return y.view(B, L, -1)
 
     @staticmethod
     def backward(ctx, dy):
         from ..lewin import leff_bwd
-        x2, u1, h1, u2, h2, w1, wdw, w2 = ctx.saved_tensors
+        x2, u1, u2, h2, w1, wdw, w2 = ctx.saved_tensors
         B, H, W = ctx.geom
         g = dy.reshape(-1, w2.shape[0]).contiguous()
         P_w1, P_b1, P_wdw, P_bdw, P_w2, P_b2 = ctx.params
-        dx, (dW1, db1, dwdw, dbdw, dW2, db2) = leff_bwd(g, dict(u1=u1, h1=h1, u2=u2, h2=h2), x2, P_w1, P_b1, P_wdw, P_bdw,
+        dx, (dW1, db1, dwdw, dbdw, dW2, db2) = leff_bwd(g, dict(u1=u1, u2=u2, h2=h2), x2, P_w1, P_b1, P_wdw, P_bdw,
                                                         P_w2, P_b2, B, H, W)
         return dx.view(B, H * W, -1), dW1, db1, dwdw, dbdw, dW2, db2
 

@@ -297,6 +297,7 @@ def dwconv_fwd(h1, w, b, B, H, W, C, want_act=True, u2_mode=0):
 
 
 def dwconv_bwd(du2, h1, u1, w, dw, db, B, H, W, C):
+    """h1=None: the kernel recomputes h1 = gelu(u1) for the weight gradient instead of reading it."""
     _f32(du2, h1, u1, w)
     du1 = torch.empty_like(du2)
     _call('fa_dwconv3x3_bwd', _p(du2), _p(h1), _p(u1), _p(w), _p(du1), _p(dw), _p(db), B, H, W, C, _stream())

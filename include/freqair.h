@@ -170,7 +170,8 @@ int fa_token_mean_bwd(const float* dy, float* dx, int B, int HW, int C, fa_strea
  *   fwd: u2 = dwconv(h1) + b ; h2 = gelu(u2)            (h1 = gelu(u1)).  u2_mode = 1 stores gelu'(u2) in `u2` instead
  *        (the only thing the backward needs u2 for: the dX contraction then multiplies by it with aux_act = 4, no
  *        transcendental in its epilogue); u2 or h2 may be NULL (inference stores h2 only).
- *   bwd: du1 = gelu'(u1) * dwconv^T(du2)  (u1 NULL: plain adjoint) ; dw, db ACCUMULATE (dw NULL: skipped). */
+ *   bwd: du1 = gelu'(u1) * dwconv^T(du2)  (u1 NULL: plain adjoint) ; dw, db ACCUMULATE (dw NULL: skipped).  h1 NULL with u1
+ *        set: h1 = gelu(u1) is recomputed from the u1 values the kernel loads anyway (3.5 instead of 4.5 passes). */
 int fa_dwconv3x3_fwd(const float* h1, const float* w, const float* b, float* u2, float* h2, int u2_mode, int B, int H,
                      int W, int C, fa_stream_t stream);
 int fa_dwconv3x3_bwd(const float* du2, const float* h1, const float* u1, const float* w, float* du1, float* dw,

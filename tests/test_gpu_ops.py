@@ -158,6 +158,10 @@ def test_dwconv(ops, B, H, W, C):
     dw, db = torch.zeros(C, 1, 3, 3, device='cuda'), torch.zeros(C, device='cuda')
     du1 = ops.dwconv_bwd(du2, h1d, dev(u1.detach()), dev(w.detach()), dw, db, B, H, W, C)
     close(du1, u1.grad, 1e-4, 'dw du1'); close(dw, w.grad, 1e-4, 'dw dw'); close(db, b.grad, 1e-4, 'dw db')
+    dw2, db2 = torch.zeros_like(dw), torch.zeros_like(db)                      # h1 recomputed from u1 inside the kernel
+    du1b = ops.dwconv_bwd(du2, None, dev(u1.detach()), dev(w.detach()), dw2, db2, B, H, W, C)
+    close(du1b, u1.grad, 1e-4, 'dw du1 (h1 recomputed)'); close(dw2, w.grad, 1e-4, 'dw dw (h1 recomputed)')
+    close(db2, b.grad, 1e-4, 'dw db (h1 recomputed)')
 
 
 @pytest.mark.parametrize('C,k,s,p', [(8, 4, 2, 1), (12, 3, 1, 1), (3, 3, 1, 1)])
