@@ -173,3 +173,18 @@ def test_gemm_a_kscale_and_bwd_rowscale(ops, backend):
     with pytest.raises(RuntimeError):            # no silent fallback: the SIMT kernel has no a_kscale
         ops.gemm(dY.cuda(), X.cuda(), G, transA=True, transB=False, accumulate=True, a_kscale=dp.cuda(),
                  a_k_rows_per_scale=rps, backend=1)
+
+
+@pytest.mark.parametrize('backend', [2, 3])
+@pytest.mark.parametrize('tA,tB', [(False, True), (False, False), (True, False), (True, True)])
+@pytest.mark.parametrize('M,N,K', [(128 * 151 + 40, 256, 96), (128 * 150, 64, 1056), (128 * 3 + 4, 128 * 60, 72)])
+def test_gemm_tc_many_tiles(ops, M, N, K, tA, tB, backend):
+    """Shapes with several waves of tiles per SM (persistent loop, ring and accumulator phases wrapping many times), odd
+    tile counts, ragged M, both B layouts, split-K; exact on TF32-representable data."""
+    A = quant(gen(K, M) if tA else gen(M, K))
+    B = quant(gen(N, K, seed=1) if tB else gen(K, N, seed=1))
+    C = torch.full((M, N), float('nan'), device='cuda')
+    ops.gemm(A.cuda(), B.cuda(), C, transA=tA, transB=tB, backend=backend)
+    ref = (A.t() if tA else A).double() @ (B.t() if tB else B).double()
+    err = (C.double().cpu() - ref).abs().max().item()
+    assert err == 0.0, f'tc gemm {M}x{N}x{K} tA={tA} tB={tB}: max err {err:.3e}'
