@@ -145,6 +145,26 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem,
       : "memory");
 }
 
+// TS-form MMA with the B descriptor passed as its two 32-bit words (lo carries the 14-bit start-address field, so stepping
+// a descriptor is ONE 32-bit add) and the accumulate flag a compile-time constant: the issuing thread is a single lane
+// whose own address arithmetic, not the tensor pipe, set the pace of the first version (~65 SASS instructions per
+// k-step of 3 MMAs = ~130 cycles per MMA, twice the 64 cycles a 128x128x8 tf32 MMA computes for).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+template <int ACC>
+__device__ __forceinline__ void tc_mma_tf32_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+      "mov.b64 bd, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(ACC)
+      : "memory");
+}
+
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
   asm volatile(
@@ -414,8 +434,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ---------------------------------------------------------------- MMA issuer
+      // The WHOLE warp walks the loops and waits on the barriers; one elected lane issues.  Under `if (lane == 0)` the
+      // compiler cannot keep the descriptors in uniform registers and wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST
+      // waterfall (~12 instructions, ~130 cycles per MMA - twice the 64 cycles a 128x128x8 tf32 MMA computes for).
       // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32, a=b=tf32, majors, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (((A_MN && !A_TMEM) ? 1u : 0u) << 15) |
                              ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -432,9 +455,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + as * BN;
           const int kb1 = min(nkb, kb0 + KC_BLOCKS);
+          if (A_TMEM) {
+            // descriptors stepped with 32-bit adds: the start-address field (smem address >> 4, < 2^14) never carries
+            const uint64_t dz = make_desc(0, B_MN);
+            const uint32_t b_hi = (uint32_t)(dz >> 32), lo_c = (uint32_t)dz;
+            const uint32_t b_lo0 = lo_c | ((smem_u32(sB) >> 4) & 0x3FFFu), bl_lo0 = lo_c | ((smem_u32(sBlo) >> 4) & 0x3FFFu);
+            const uint32_t kinc = bstep >> 4;
+            const uint32_t at_base = tmem_base + TMEM_A_COL0;
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
+              mbar_wait(&ready[s], (it / STAGES) & 1);
+              tc_fence_after();
+              const uint32_t bs = b_lo0 + (uint32_t)s * (B_BYTES >> 4), bls = bl_lo0 + (uint32_t)s * (B_BYTES >> 4);
+              const uint32_t at = at_base + (uint32_t)s * 64;                                // hi at +0, lo at +32
+              if (elect_one()) {
+                if (kb == kb0) tc_mma_tf32_ts2<0>(d_tmem, at + 32, bs, b_hi, idesc);          // small terms first
+                else tc_mma_tf32_ts2<1>(d_tmem, at + 32, bs, b_hi, idesc);
+                tc_mma_tf32_ts2<1>(d_tmem, at, bls, b_hi, idesc);
+                tc_mma_tf32_ts2<1>(d_tmem, at, bs, b_hi, idesc);
+#pragma unroll
+                for (int k = 1; k < BK / UMMA_K; ++k) {
+                  tc_mma_tf32_ts2<1>(d_tmem, at + 32 + k * UMMA_K, bs + k * kinc, b_hi, idesc);
+                  tc_mma_tf32_ts2<1>(d_tmem, at + k * UMMA_K, bls + k * kinc, b_hi, idesc);
+                  tc_mma_tf32_ts2<1>(d_tmem, at + k * UMMA_K, bs + k * kinc, b_hi, idesc);
+                }
+                tc_commit(&empty[s]);                  // frees the smem slot when these MMAs retire
+              }
+              __syncwarp();
+              if (++s == STAGES) s = 0;
+            }
+          } else
           for (int kb = kb0; kb < kb1; ++kb, ++it) {
             mbar_wait(X3 ? &ready[s] : &full[s], (it / STAGES) & 1);
             tc_fence_after();
+            if (lane == 0) {
             const uint32_t a0 = smem_u32(sA + s * A_BYTES), b0 = smem_u32(sB + s * B_BYTES);
             const uint32_t al0 = smem_u32(sAlo + s * A_BYTES), bl0 = smem_u32(sBlo + s * B_BYTES);
 #pragma unroll
@@ -455,9 +508,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
               }
             }
             tc_commit(&empty[s]);                      // frees the smem slot when these MMAs retire
+            }
+            __syncwarp();
             if (++s == STAGES) s = 0;
           }
-          tc_commit(&tmem_full[as]);                   // partial accumulator complete
+          if (lane == 0) tc_commit(&tmem_full[as]);    // partial accumulator complete
+          __syncwarp();
         }
       }
     }
