@@ -404,8 +404,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ---------------------------------------------------------------- TMA producer
+      // (whole warp walks the loop, an elected lane issues: coordinates and addresses stay in uniform registers)
       uint32_t it = 0;
       int s = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -415,6 +416,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
         const int nkb = (min(g.K, kbeg + g.k_chunk) - kbeg + BK - 1) / BK;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+          if (elect_one()) {
           mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
           const int k0 = kbeg + kb * BK;
           if (!A_MN) {
@@ -429,6 +431,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
             for (int j = 0; j < BN / 32; ++j) tma_load_2d(sB + s * B_BYTES + j * 4096, &tmB, &full[s], n0 + 32 * j, k0);
           }
+          }
+          __syncwarp();
           if (++s == STAGES) s = 0;
         }
       }
