@@ -383,7 +383,7 @@ def main():
                                    'the contractions run fp32/tf32, SURVEY.md section 8d)',
                     'note': 'achieved counts ALGORITHMIC flops (2MNK); the product path issues 3 tf32 MMAs per product '
                             '(error-compensated 3xTF32, needed for the 1e-3 parity bar), so the tensor pipe does 3x this '
-                            'work: ncu shows it 47-49 % active on the compute-class shapes (profiles/r1_ncu_gemm_*.txt); '
+                            'work (compute-class shapes run 175-198 TFLOP/s algorithmic = 520-590 TFLOP/s of raw tf32 MMA, DESIGN.md section 3); '
                             'K <= 224 layers at the 128^2 / 64^2 levels are HBM-bound (2.3-3.2 TB/s, tools/bench_kernels.py)'}
     if dist is not None:
         dist.barrier()
