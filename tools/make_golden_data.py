@@ -44,3 +44,51 @@ for mode in range(8):
     out[f'clean{mode}'] = tt(np.ascontiguousarray(c_aug)).numpy()
 np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'datagen.npz'), **out)
 print('wrote tests/golden/datagen.npz', {k: v.shape for k, v in out.items() if k.startswith('deg')})
+
+
+# ----------------------------------------------------------------------------- part 2: the dataset object itself
+def dataset_fixture():
+    """Run the UNMODIFIED TrainDataset (utils/dataset_utils.py:68-143) on a tiny PNG tree with a seeded ``random`` and
+    store what it returns, so that the host-side draw logic of ``datagen.DeviceTrainSet`` (type round-robin, shuffle at
+    wrap-around, two crop + augmentation draws per item) is pinned to the real thing.  Paired types only (the noise
+    synthesis of 'denoising_*' draws np.random.randn, which DeviceTrainSet replaces by its stateless generator)."""
+    import tempfile
+    import types
+    from PIL import Image
+    from utils.dataset_utils import TrainDataset
+    rng2 = np.random.RandomState(21)
+    cwd = os.getcwd()
+    out2 = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            spec = {'deraining': [(40, 52), (37, 45), (33, 64)], 'dehazing': [(48, 48), (36, 70)]}
+            for de, sizes in spec.items():
+                os.makedirs(f'data/{de}_train/GT'); os.makedirs(f'data/{de}_train/Input')
+                for i, (h, w) in enumerate(sizes):
+                    gt_img = rng2.randint(0, 256, size=(h, w, 3)).astype(np.uint8)
+                    in_img = rng2.randint(0, 256, size=(h, w, 3)).astype(np.uint8)
+                    Image.fromarray(gt_img).save(f'data/{de}_train/GT/{de[:3]}{i}.png')
+                    Image.fromarray(in_img).save(f'data/{de}_train/Input/{de[:3]}{i}_x.png')
+                    out2[f'img/{de}/{de[:3]}{i}/gt'] = gt_img
+                    out2[f'img/{de}/{de[:3]}{i}/in'] = in_img
+            args = types.SimpleNamespace(de_type=['deraining', 'dehazing'], patch_size=16)
+            ds = TrainDataset(args)
+            for t, de in enumerate(args.de_type):             # listdir order is file-system dependent: record it
+                out2[f'order/{de}'] = np.array([os.path.basename(p).split('.')[0] for p in ds.gt_ids[t]])
+            random.seed(5)
+            n = 9                                              # wraps both per-type iterators at least once
+            names, des = [], []
+            for k in range(n):
+                (name, de), d1, d2, c1, c2 = ds[k]
+                names.append(name); des.append(de)
+                out2[f'item{k}/d1'], out2[f'item{k}/d2'] = d1.numpy(), d2.numpy()
+                out2[f'item{k}/c1'], out2[f'item{k}/c2'] = c1.numpy(), c2.numpy()
+            out2['names'] = np.array(names); out2['de_ids'] = np.array(des); out2['seed'] = np.array(5); out2['n'] = np.array(n)
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'datagen_dataset.npz'), **out2)
+    print('wrote tests/golden/datagen_dataset.npz', names, des)
+
+
+dataset_fixture()
