@@ -19,7 +19,8 @@ class FaGemmEpilogue(ctypes.Structure):
                 ('aux_param', ctypes.c_float), ('rowscale', ctypes.c_void_p), ('rows_per_scale', ctypes.c_int),
                 ('residual', ctypes.c_void_p), ('ldr', ctypes.c_int64), ('accumulate', ctypes.c_int),
                 ('alpha', ctypes.c_float), ('preact', ctypes.c_void_p), ('ldpre', ctypes.c_int64),
-                ('a_rowsum', ctypes.c_void_p), ('a_kscale', ctypes.c_void_p), ('a_k_rows_per_scale', ctypes.c_int)]
+                ('a_rowsum', ctypes.c_void_p), ('a_kscale', ctypes.c_void_p), ('a_k_rows_per_scale', ctypes.c_int),
+                ('b_is_tf32', ctypes.c_int)]
 
 
 _SCALARS = {'int': ctypes.c_int, 'int64_t': ctypes.c_int64, 'float': ctypes.c_float, 'double': ctypes.c_double,
@@ -70,11 +71,37 @@ _lib = None
 _protos = None
 
 
+def _stale():
+    """True when a source of the library is newer than the built .so (only meaningful where the sources are)."""
+    csrc = os.path.join(HERE, 'csrc')
+    if not os.path.isdir(csrc):
+        return False
+    built = os.path.getmtime(LIB_PATH)
+    srcs = [os.path.join(csrc, f) for f in os.listdir(csrc)] + [HEADER]
+    return any(os.path.getmtime(f) > built for f in srcs)
+
+
+def abi_version_of_header(path=HEADER):
+    m = re.search(r'#define\s+FREQAIR_ABI_VERSION\s+(\d+)', open(path).read())
+    return int(m.group(1)) if m else None
+
+
 def load():
-    """Load the shared library (building it in-tree if the source is newer and nvcc is around)."""
+    """Load libfreqair.so.  If a source file is newer than the .so and nvcc is present the library is rebuilt in-tree
+    first (``build.build()``); without nvcc a stale library is an error, not something to load silently.  After loading,
+    every prototype of ``include/freqair.h`` must resolve and ``fa_abi_version()`` must equal the header's
+    ``FREQAIR_ABI_VERSION`` (a library built from another revision of the header is refused)."""
     global _lib, _protos
     if _lib is not None:
         return _lib
+    if os.path.exists(LIB_PATH) and _stale():
+        from . import build as _build
+        nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+        if os.path.exists(nvcc):
+            _build.build()
+        elif os.environ.get('FREQAIR_ALLOW_STALE') != '1':
+            raise RuntimeError(f'{LIB_PATH} is older than its sources and nvcc ({nvcc}) is not available to rebuild it '
+                               '(set FREQAIR_ALLOW_STALE=1 to load it anyway)')
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(f'{LIB_PATH} is missing: run `python __graft_entry__.py build` (nvcc, sm_100a). '
                            'freqair has no CPU or PyTorch fallback.')
@@ -84,6 +111,9 @@ def load():
         fn = getattr(lib, name)          # AttributeError here == header/library mismatch
         fn.restype = restype
         fn.argtypes = argtypes
+    want, got = abi_version_of_header(), lib.fa_abi_version()
+    if want != got:
+        raise RuntimeError(f'{LIB_PATH} implements ABI version {got}, include/freqair.h declares {want}: rebuild the library')
     _lib = lib
     return lib
 

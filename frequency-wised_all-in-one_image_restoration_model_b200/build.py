@@ -9,7 +9,7 @@ ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, 'libfreqair.so')
 SOURCES = ['api.cu', 'gemm_simt.cu', 'gemm_tc.cu', 'norm.cu', 'conv.cu', 'fft_band.cu', 'win_attn.cu', 'joint_attn.cu',
            'elementwise.cu', 'dcn.cu', 'datagen.cu']
-NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--use_fast_math=false',
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-O2', '-I', os.path.join(ROOT, 'include'), '-I', CSRC]
 
 
@@ -30,7 +30,7 @@ def build(force=False, verbose=False):
         o = os.path.join(objdir, src.replace('.cu', '.o'))
         objs.append(o)
         if force or _newer(s, o) or os.path.getmtime(o) < hdr_time:
-            cmd = [nvcc] + [f for f in NVCC_FLAGS if f != '--use_fast_math=false'] + ['-c', s, '-o', o]
+            cmd = [nvcc] + NVCC_FLAGS + ['-c', s, '-o', o]
             if verbose:
                 cmd.insert(1, '-Xptxas')
                 cmd.insert(2, '-v')

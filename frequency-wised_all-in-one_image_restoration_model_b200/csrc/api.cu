@@ -1,12 +1,16 @@
 // Library-level entry points: version, error string, launch counter, per-class in-stream timing.
 #include <stdarg.h>
+#include <atomic>
+#include <mutex>
 #include <vector>
 #include "freqair_internal.h"
 
 static thread_local char g_err[512] = "";
-static int g_prof_cls = 0;
+// touched from the forward thread and from autograd's backward thread: atomics + one mutex around the event list
+static std::atomic<int> g_prof_cls{0};
+static std::mutex g_prof_mu;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
-static int64_t g_launches = 0;
+static std::atomic<int64_t> g_launches{0};
 
 void fa_set_error(const char* fmt, ...) {
   va_list ap;
@@ -15,11 +19,12 @@ void fa_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-void fa_count_launch(int) { ++g_launches; }
+void fa_count_launch(int) { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 FaProfScope::FaProfScope(int cls_, cudaStream_t st_) : cls(cls_), st(st_), e0(nullptr), on(false) {
-  ++g_launches;
-  if (g_prof_cls != 0 && g_prof_cls == cls) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  const int want = g_prof_cls.load(std::memory_order_relaxed);
+  if (want != 0 && want == cls) {
     on = true;
     cudaEventCreate(&e0);
     cudaEventRecord(e0, st);
@@ -30,13 +35,15 @@ FaProfScope::~FaProfScope() {
     cudaEvent_t e1;
     cudaEventCreate(&e1);
     cudaEventRecord(e1, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof_events.emplace_back(e0, e1);
   }
 }
 
 extern "C" {
 
-const char* fa_version(void) { return "freqair 0.1 (sm_100a)"; }
+const char* fa_version(void) { return "freqair 0.2 (sm_100a)"; }
+int fa_abi_version(void) { return FREQAIR_ABI_VERSION; }
 const char* fa_last_error_string(void) { return g_err; }
 
 int fa_device_info(int* sm_count, int* cc_major, int* cc_minor) {
@@ -51,6 +58,7 @@ int fa_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 }
 
 int fa_prof_begin(int kernel_class) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   for (auto& pr : g_prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   g_prof_events.clear();
   g_prof_cls = kernel_class;
@@ -58,6 +66,7 @@ int fa_prof_begin(int kernel_class) {
 }
 
 int fa_prof_end(double* total_ms, int64_t* launches) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   double tot = 0.0;
   for (auto& pr : g_prof_events) {
     cudaEventSynchronize(pr.second);
@@ -74,18 +83,20 @@ int fa_prof_end(double* total_ms, int64_t* launches) {
   return FA_OK;
 }
 
-int64_t fa_launch_count(void) { return g_launches; }
-void fa_launch_count_reset(void) { g_launches = 0; }
+int64_t fa_launch_count(void) { return g_launches.load(); }
+void fa_launch_count_reset(void) { g_launches.store(0); }
 
 int fa_gemm(const float* A, const float* B, float* C, int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc,
             int transA, int transB, const FaGemmEpilogue* epi, int backend, fa_stream_t stream) {
   FA_REQUIRE(A && B && C, "fa_gemm: null operand");
   FA_REQUIRE(M >= 0 && N >= 0 && K >= 0, "fa_gemm: negative dimension");
-  FA_REQUIRE(backend >= 0 && backend <= 3, "fa_gemm: backend must be 0, 1, 2 or 3");
+  FA_REQUIRE(backend >= 0 && backend <= 5, "fa_gemm: backend must be 0..5");
   cudaStream_t st = (cudaStream_t)stream;
   FaProfScope prof(FA_K_GEMM, st);
   if (backend != 1) {
-    int rc = fa_gemm_tc_launch(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, epi, st, backend == 3);
+    // MMAs per product: 3 (backends 0, 2), 0 = raw truncated operands (3), 2 = A exact / B RN-rounded (4), 1 = RN-TF32 (5)
+    const int passes = backend == 3 ? 0 : (backend == 4 ? 2 : (backend == 5 ? 1 : 3));
+    int rc = fa_gemm_tc_launch(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, epi, st, passes);
     if (rc != FA_ERR_UNSUPPORTED) return rc;
     if (backend >= 2) {
       fa_set_error("fa_gemm: shape M=%d N=%d K=%d tA=%d tB=%d not eligible for the tcgen05 path", M, N, K, transA, transB);

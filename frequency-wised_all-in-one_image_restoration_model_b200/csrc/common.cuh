@@ -38,6 +38,20 @@ void fa_set_error(const char* fmt, ...);
     }                                                                         \
   } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize once per (call site, device): the attribute belongs to the device's copy of
+// the function, so a process-wide flag would leave the kernel un-configured on every GPU but the first one used.
+// Usage: FA_SMEM_ATTR_ONCE(bytes, kernel<template, args>);
+#define FA_SMEM_ATTR_ONCE(bytes, ...)                                                                     \
+  do {                                                                                                    \
+    static bool done__[64] = {};                                                                          \
+    int dev__ = 0;                                                                                        \
+    FA_CUDA(cudaGetDevice(&dev__));                                                                       \
+    if (dev__ < 0 || dev__ >= 64 || !done__[dev__]) {                                                     \
+      FA_CUDA(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      if (dev__ >= 0 && dev__ < 64) done__[dev__] = true;                                                 \
+    }                                                                                                     \
+  } while (0)
+
 // ---- optional in-stream timing of one kernel class (bench.py roofline leg) ----
 // Each public launcher names its class; when profiling of that class is on, the
 // launcher brackets the launch with events on the launching stream.

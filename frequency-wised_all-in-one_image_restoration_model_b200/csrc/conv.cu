@@ -618,11 +618,7 @@ int fa_dwconv3x3_fwd(const float* h1, const float* w, const float* b, float* u2,
   if ((int64_t)B * H * W * C == 0) return FA_OK;
   int nstrips; dim3 grid;
   const StripGeom g = make_strips_persistent(B, H, W, C, DWF_WARPS, nstrips, grid);
-  static bool attr_set = false;
-  if (!attr_set) {
-    FA_CUDA(cudaFuncSetAttribute(dwconv_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DWF_SMEM));
-    attr_set = true;
-  }
+  FA_SMEM_ATTR_ONCE(DWF_SMEM, dwconv_strip_kernel);
   dwconv_strip_kernel<<<grid, dim3(32, DWF_WARPS), DWF_SMEM, st>>>(h1, w, b, u2, h2, g, nstrips, u2_mode);
   FA_LAUNCH_CHECK("fa_dwconv3x3_fwd");
   return FA_OK;
@@ -638,11 +634,7 @@ int fa_dwconv3x3_bwd(const float* du2, const float* h1, const float* u1, const f
   int nstrips; dim3 grid;
   const StripGeom g = make_strips_persistent(B, H, W, C, 8, nstrips, grid);
   FA_REQUIRE(!dw || h1 || u1, "fa_dwconv3x3_bwd: the weight gradient needs h1, or u1 to recompute h1 = gelu(u1)");
-  static bool attr_set = false;
-  if (!attr_set) {
-    FA_CUDA(cudaFuncSetAttribute(dwconv_bwd_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DWB_SMEM));
-    attr_set = true;
-  }
+  FA_SMEM_ATTR_ONCE(DWB_SMEM, dwconv_bwd_strip_kernel);
   dwconv_bwd_strip_kernel<<<grid, dim3(32, 8), DWB_SMEM, st>>>(du2, h1, u1, w, du1, dw, db, g, nstrips);
   FA_LAUNCH_CHECK("fa_dwconv3x3_bwd");
   return FA_OK;

@@ -70,8 +70,20 @@ __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, flo
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n, float b1,
                                                    float b2, float eps, float step_size, float inv_bc2_sqrt,
-                                                   float gscale, int vec, const float* __restrict__ hyper) {
-  if (hyper) { step_size = hyper[0]; inv_bc2_sqrt = hyper[1]; }     // step-dependent scalars read at run time (CUDA graphs)
+                                                   float gscale, int vec, const float* __restrict__ state) {
+  if (state) {
+    // {lr, step count} live in device memory (fa_adam_tick advances the count): the bias corrections of
+    // torch.optim.Adam are derived here, in double like torch's host code, once per block
+    __shared__ float sh[2];
+    if (threadIdx.x == 0) {
+      const double t = (double)reinterpret_cast<const int*>(state)[1];
+      const double bc1 = 1.0 - pow((double)b1, t), bc2 = 1.0 - pow((double)b2, t);
+      sh[0] = (float)((double)state[0] / bc1);
+      sh[1] = (float)(1.0 / sqrt(bc2));
+    }
+    __syncthreads();
+    step_size = sh[0]; inv_bc2_sqrt = sh[1];
+  }
   if (vec) {
     const int64_t n4 = n >> 2;
     float4* p4 = reinterpret_cast<float4*>(p);
@@ -301,15 +313,26 @@ int fa_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float 
   return FA_OK;
 }
 
-int fa_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, float beta1, float beta2,
-                     float eps, float grad_scale, fa_stream_t stream) {
-  FA_REQUIRE(p && g && m && v && hyper, "fa_adam_step_dev: bad argument");
+__global__ void adam_tick_kernel(float* state) { reinterpret_cast<int*>(state)[1] += 1; }
+
+int fa_adam_tick(float* state, fa_stream_t stream) {
+  FA_REQUIRE(state, "fa_adam_tick: null state");
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_OPTIM, st);
+  adam_tick_kernel<<<1, 1, 0, st>>>(state);
+  FA_LAUNCH_CHECK("fa_adam_tick");
+  return FA_OK;
+}
+
+int fa_adam_step_state(float* p, const float* g, float* m, float* v, int64_t n, const float* state, float beta1,
+                       float beta2, float eps, float grad_scale, fa_stream_t stream) {
+  FA_REQUIRE(p && g && m && v && state, "fa_adam_step_state: bad argument");
   if (n == 0) return FA_OK;
   cudaStream_t st = (cudaStream_t)stream;
   FaProfScope prof(FA_K_OPTIM, st);
   const bool al = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16) == 0;
-  adam_kernel<<<ew_grid(n / 4 + 1), 256, 0, st>>>(p, g, m, v, n, beta1, beta2, eps, 0.f, 0.f, grad_scale, al ? 1 : 0, hyper);
-  FA_LAUNCH_CHECK("fa_adam_step_dev");
+  adam_kernel<<<ew_grid(n / 4 + 1), 256, 0, st>>>(p, g, m, v, n, beta1, beta2, eps, 0.f, 0.f, grad_scale, al ? 1 : 0, state);
+  FA_LAUNCH_CHECK("fa_adam_step_state");
   return FA_OK;
 }
 

@@ -194,6 +194,14 @@ __device__ __forceinline__ float lds32(uint32_t saddr) {
   return v;
 }
 
+// round-to-nearest (ties away) to TF32: the result is exactly representable, so the tensor core's operand truncation is
+// the identity on it
+__device__ __forceinline__ float rn1(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float4 rn4(float4 v) { return make_float4(rn1(v.x), rn1(v.y), rn1(v.z), rn1(v.w)); }
 __device__ __forceinline__ float lo1(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __device__ __forceinline__ float4 lo4(float4 v) { return make_float4(lo1(v.x), lo1(v.y), lo1(v.z), lo1(v.w)); }
 
@@ -232,8 +240,11 @@ struct TcGeom {
   int M, N, K;
   int64_t ldc;
   int k_chunk, splits, tiles_m, tiles_n;
-  int a_mn, b_mn, x3, stages;
-  int a_tmem;    // x3 only: A and A_lo are staged in TMEM by the split warps (MMA reads only B from shared memory)
+  int a_mn, b_mn, stages;
+  int passes;    // MMAs per product: 3 = A_lo.B + A.B_lo + A.B (fp32-level), 2 = A_lo.rn(B) + A.rn(B) (A exact, B rounded to
+                 // nearest TF32), 1 = rn(A).rn(B), 0 = raw operands, truncated by the tensor core (measurement only)
+  int a_tmem;    // passes >= 1: A (and A_lo) are staged in TMEM by the split warps (MMA reads only B from shared memory)
+  int b_exact;   // passes 1 / 2: B is already TF32-representable (pre-rounded by its producer): the split warps skip it
 };
 
 // compile-time activation: keeps the unrolled row loop straight-line (a run-time switch per element splits it into
@@ -368,10 +379,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int STAGES = g.stages;
-  const bool X3 = g.x3 != 0, A_MN = g.a_mn != 0, B_MN = g.b_mn != 0, A_TMEM = g.a_tmem != 0;
+  const int PASSES = g.passes;
+  const bool X3 = PASSES == 3, SPLIT = PASSES >= 1, A_MN = g.a_mn != 0, B_MN = g.b_mn != 0, A_TMEM = g.a_tmem != 0;
+  const uint32_t A_TSTRIDE = PASSES == 1 ? 32u : 64u;      // TMEM columns per stage of the A ring ({A} or {A, A_lo})
   unsigned char* sA = smem;
   unsigned char* sB = sA + STAGES * A_BYTES;
-  unsigned char* sAlo = sB + STAGES * B_BYTES;                                // x3 only (absent with a_tmem)
+  unsigned char* sAlo = sB + STAGES * B_BYTES;                                // 3 passes only (absent with a_tmem)
   unsigned char* sBlo = sAlo + ((X3 && !A_TMEM) ? STAGES * A_BYTES : 0);
   float* stg_all = reinterpret_cast<float*>(sBlo + (X3 ? STAGES * B_BYTES : 0));   // [EPI_WARPS][32][32]
   uint64_t* full = reinterpret_cast<uint64_t*>(stg_all + EPI_WARPS * 32 * 32);
@@ -470,17 +483,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
               mbar_wait(&ready[s], (it / STAGES) & 1);
               tc_fence_after();
               const uint32_t bs = b_lo0 + (uint32_t)s * (B_BYTES >> 4), bls = bl_lo0 + (uint32_t)s * (B_BYTES >> 4);
-              const uint32_t at = at_base + (uint32_t)s * 64;                                // hi at +0, lo at +32
+              const uint32_t at = at_base + (uint32_t)s * A_TSTRIDE;                         // hi at +0, lo at +32
               if (elect_one()) {
-                if (kb == kb0) tc_mma_tf32_ts2<0>(d_tmem, at + 32, bs, b_hi, idesc);          // small terms first
-                else tc_mma_tf32_ts2<1>(d_tmem, at + 32, bs, b_hi, idesc);
-                tc_mma_tf32_ts2<1>(d_tmem, at, bls, b_hi, idesc);
-                tc_mma_tf32_ts2<1>(d_tmem, at, bs, b_hi, idesc);
+                if (PASSES == 3) {
+                  if (kb == kb0) tc_mma_tf32_ts2<0>(d_tmem, at + 32, bs, b_hi, idesc);          // small terms first
+                  else tc_mma_tf32_ts2<1>(d_tmem, at + 32, bs, b_hi, idesc);
+                  tc_mma_tf32_ts2<1>(d_tmem, at, bls, b_hi, idesc);
+                  tc_mma_tf32_ts2<1>(d_tmem, at, bs, b_hi, idesc);
 #pragma unroll
-                for (int k = 1; k < BK / UMMA_K; ++k) {
-                  tc_mma_tf32_ts2<1>(d_tmem, at + 32 + k * UMMA_K, bs + k * kinc, b_hi, idesc);
-                  tc_mma_tf32_ts2<1>(d_tmem, at + k * UMMA_K, bls + k * kinc, b_hi, idesc);
-                  tc_mma_tf32_ts2<1>(d_tmem, at + k * UMMA_K, bs + k * kinc, b_hi, idesc);
+                  for (int k = 1; k < BK / UMMA_K; ++k) {
+                    tc_mma_tf32_ts2<1>(d_tmem, at + 32 + k * UMMA_K, bs + k * kinc, b_hi, idesc);
+                    tc_mma_tf32_ts2<1>(d_tmem, at + k * UMMA_K, bls + k * kinc, b_hi, idesc);
+                    tc_mma_tf32_ts2<1>(d_tmem, at + k * UMMA_K, bs + k * kinc, b_hi, idesc);
+                  }
+                } else if (PASSES == 2) {                  // B was rounded to TF32 in place: A_lo.B + A.B
+                  if (kb == kb0) tc_mma_tf32_ts2<0>(d_tmem, at + 32, bs, b_hi, idesc);
+                  else tc_mma_tf32_ts2<1>(d_tmem, at + 32, bs, b_hi, idesc);
+                  tc_mma_tf32_ts2<1>(d_tmem, at, bs, b_hi, idesc);
+#pragma unroll
+                  for (int k = 1; k < BK / UMMA_K; ++k) {
+                    tc_mma_tf32_ts2<1>(d_tmem, at + 32 + k * UMMA_K, bs + k * kinc, b_hi, idesc);
+                    tc_mma_tf32_ts2<1>(d_tmem, at + k * UMMA_K, bs + k * kinc, b_hi, idesc);
+                  }
+                } else {                                   // both operands rounded to TF32: one MMA per k-step
+                  if (kb == kb0) tc_mma_tf32_ts2<0>(d_tmem, at, bs, b_hi, idesc);
+                  else tc_mma_tf32_ts2<1>(d_tmem, at, bs, b_hi, idesc);
+#pragma unroll
+                  for (int k = 1; k < BK / UMMA_K; ++k) tc_mma_tf32_ts2<1>(d_tmem, at + k * UMMA_K, bs + k * kinc, b_hi, idesc);
                 }
                 tc_commit(&empty[s]);                  // frees the smem slot when these MMAs retire
               }
@@ -489,7 +518,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
             }
           } else
           for (int kb = kb0; kb < kb1; ++kb, ++it) {
-            mbar_wait(X3 ? &ready[s] : &full[s], (it / STAGES) & 1);
+            mbar_wait(SPLIT ? &ready[s] : &full[s], (it / STAGES) & 1);
             tc_fence_after();
             if (lane == 0) {
             const uint32_t a0 = smem_u32(sA + s * A_BYTES), b0 = smem_u32(sB + s * B_BYTES);
@@ -522,8 +551,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
       }
     }
   } else if (warp < EPI_WARP0) {
-    // ------------------------------------------------------------------ split warps: lo = x - trunc_tf32(x)
-    if (X3) {
+    // ------------------------------------------------------------------ split warps: lo = x - trunc_tf32(x) / rn_tf32(x)
+    if (SPLIT) {
       const int st = threadIdx.x - 64;        // 0..SPLIT_WARPS*32-1
       float rsum = 0.f;                       // a_rowsum: this thread's A row, summed over the k-blocks of the tile
       uint32_t it = 0;
@@ -556,9 +585,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
               for (int k = 0; k < 32; ++k) av[k] = lds32(base + k * 128 + (((cm ^ k) & 3) << 5));
             }
+            if (PASSES == 3 || !g.b_exact) {
 #pragma unroll
-            for (int i = 0; i < NB; ++i) rb[i] = lds128(b + i * SPLIT_WARPS * 512);
-            const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + TMEM_A_COL0 + s * 64;
+              for (int i = 0; i < NB; ++i) rb[i] = lds128(b + i * SPLIT_WARPS * 512);
+            }
+            const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + TMEM_A_COL0 + s * A_TSTRIDE;
             if (epi.a_kscale) {                         // DropPath scale of the k-block's sample, folded into A
               const float sc = __ldg(epi.a_kscale + (kbeg + kb * BK) / epi.a_krps);
 #pragma unroll
@@ -568,12 +599,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
               for (int k = 0; k < 32; ++k) rsum += av[k];
             }
-            tc_st32(taddr, av);
+            if (PASSES == 1) {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) av[k] = lo1(av[k]);
-            tc_st32(taddr + 32, av);
+              for (int k = 0; k < 32; ++k) av[k] = rn1(av[k]);
+              tc_st32(taddr, av);
+            } else {
+              tc_st32(taddr, av);
 #pragma unroll
-            for (int i = 0; i < NB; ++i) sts128(bl + i * SPLIT_WARPS * 512, lo4(rb[i]));
+              for (int k = 0; k < 32; ++k) av[k] = lo1(av[k]);
+              tc_st32(taddr + 32, av);
+            }
+            if (PASSES == 3) {
+#pragma unroll
+              for (int i = 0; i < NB; ++i) sts128(bl + i * SPLIT_WARPS * 512, lo4(rb[i]));
+            } else if (!g.b_exact) {                    // round B to nearest TF32 where it lies (element-wise: swizzle-agnostic)
+#pragma unroll
+              for (int i = 0; i < NB; ++i) sts128(b + i * SPLIT_WARPS * 512, rn4(rb[i]));
+            }
             tc_wait_st();
             tc_fence_before();
           } else {
@@ -740,20 +782,17 @@ bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int
 template <int BN, int MODE>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, float* C, TcGeom g, const EpiTC& e, cudaStream_t st) {
   // one persistent CTA per SM; the operand ring takes what the 227 KB leave after the 32 KB epilogue transpose tiles
-  const int stage_bytes = g.a_tmem ? (A_BYTES + 2 * BN * BK * 4) : (A_BYTES + BN * BK * 4) * (g.x3 ? 2 : 1);
+  const int stage_bytes = g.a_tmem ? (A_BYTES + (g.passes == 3 ? 2 : 1) * BN * BK * 4) : (A_BYTES + BN * BK * 4) * (g.passes == 3 ? 2 : 1);
   const int tail_bytes = EPI_WARPS * 32 * 32 * 4 + (3 * MAX_STAGES + 4) * 8 + 16;
   const int budget = 227 * 1024 - 1024 - tail_bytes;
   int stages = budget / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (g.a_tmem && stages > MAX_TMEM_A_STAGES) stages = MAX_TMEM_A_STAGES;
+  const int tmem_a_stages = g.passes == 1 ? 2 * MAX_TMEM_A_STAGES : MAX_TMEM_A_STAGES;    // 256 TMEM columns / {32, 64} per stage
+  if (g.a_tmem && stages > tmem_a_stages) stages = tmem_a_stages;
   g.stages = stages;
   const size_t smem = 1024 + (size_t)stages * stage_bytes + tail_bytes;
   auto kern = gemm_tc_kernel<BN, MODE>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    FA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done = true;
-  }
+  FA_SMEM_ATTR_ONCE(227 * 1024, kern);
   const int64_t total = (int64_t)g.tiles_m * g.tiles_n * g.splits;
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
   kern<<<grid, NTHREADS, smem, st>>>(ta, tb, C, g, e);
@@ -775,7 +814,7 @@ int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, float* C, 
 }  // namespace
 
 int fa_gemm_tc_launch(const float* A, const float* B, float* C, int M, int N, int K, int64_t lda, int64_t ldb,
-                      int64_t ldc, int transA, int transB, const FaGemmEpilogue* ep, cudaStream_t st, bool single_pass) {
+                      int64_t ldc, int transA, int transB, const FaGemmEpilogue* ep, cudaStream_t st, int passes) {
   // eligibility: 16-byte aligned bases and row pitches (TMA), a tile-sized problem, driver entry point present
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (!al16(A) || !al16(B) || (lda % 4) || (ldb % 4)) return FA_ERR_UNSUPPORTED;
@@ -817,9 +856,10 @@ int fa_gemm_tc_launch(const float* A, const float* B, float* C, int M, int N, in
   TcGeom g;
   memset(&g, 0, sizeof(g));
   g.M = M; g.N = N; g.K = K; g.ldc = ldc;
-  g.a_mn = a_mn; g.b_mn = b_mn; g.x3 = single_pass ? 0 : 1;
+  g.a_mn = a_mn; g.b_mn = b_mn; g.passes = passes;
   static const bool atmem_env = [] { const char* e = getenv("FREQAIR_GEMM_ATMEM"); return !(e && e[0] == '0'); }();
-  g.a_tmem = (g.x3 && atmem_env) ? 1 : 0;
+  g.a_tmem = (passes >= 1 && (atmem_env || passes != 3)) ? 1 : 0;
+  g.b_exact = (ep && ep->b_is_tf32 && passes >= 1 && passes <= 2) ? 1 : 0;
   if ((e.a_rowsum || e.a_kscale) && !g.a_tmem) return FA_ERR_UNSUPPORTED;      // both ride the TMEM staging of A
   g.tiles_m = (M + BM - 1) / BM;
   int bn = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 96 ? 96 : 128));

@@ -259,11 +259,7 @@ template <int HD, int NKB>
 int launch_jfwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, float* o, const JGeom& g, float scale,
                 const float* tables, cudaStream_t st) {
   const size_t smem = sizeof(JSmemF<HD, NKB>);
-  static bool done = false;
-  if (!done) {
-    FA_CUDA(cudaFuncSetAttribute(joint_fwd_kernel<HD, NKB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    done = true;
-  }
+  FA_SMEM_ATTR_ONCE(smem, joint_fwd_kernel<HD, NKB>);
   dim3 grid((unsigned)(g.B * g.nWy * g.nWx * g.heads), (unsigned)g.L);
   joint_fwd_kernel<HD, NKB><<<grid, 256, smem, st>>>(q, ldq, kv, ldkv, o, g, scale, tables);
   FA_LAUNCH_CHECK("fa_joint_attn_fwd");
@@ -274,11 +270,7 @@ template <int HD, int NKB, bool ATOMIC>
 int launch_jbwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, const float* dout, float* dq, float* dkv,
                 const JGeom& g, float scale, const float* tables, float* dtables, cudaStream_t st) {
   const size_t smem = sizeof(JSmemB<HD, NKB>);
-  static bool done = false;
-  if (!done) {
-    FA_CUDA(cudaFuncSetAttribute(joint_bwd_kernel<HD, NKB, ATOMIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    done = true;
-  }
+  FA_SMEM_ATTR_ONCE(smem, joint_bwd_kernel<HD, NKB, ATOMIC>);
   const int items = g.B * g.nWy * g.nWx * g.heads;
   // persistent: exactly one resident wave (a 4-per-SM guess on a 3-per-SM kernel ran 1.33 waves = 2 rounds)
   static int per_sm = 0;

@@ -16,19 +16,22 @@ def _z(t):
     return torch.zeros_like(t)
 
 
-# Direct gradient sinks.  trainer.TrainStep makes every parameter's .grad a view of one flat, per-step-zeroed buffer; the
-# block-level backward then ACCUMULATES weight / bias / norm gradients straight into those views (GEMM epilogue
-# accumulate, atomics) and hands autograd ``None``, which removes ~2 000 AccumulateGrad add kernels and as many
-# zero-filled temporaries per step.  GRAD_READY(param) tells the bucketed all-reduce that a gradient is complete
-# (the post-accumulate hooks no longer fire for these parameters).  With DIRECT_GRAD off, or for a parameter without
-# a .grad buffer, gradients are returned to autograd as usual (what the parity tests exercise).
-DIRECT_GRAD = False
+# Direct gradient sinks.  trainer.TrainStep makes every parameter's .grad a view of one flat, per-step-zeroed buffer and
+# marks the parameter (``p._fa_direct = True``); the block-level backward then ACCUMULATES weight / bias / norm gradients
+# straight into those views (GEMM epilogue accumulate, atomics) and hands autograd ``None``, which removes ~2 000
+# AccumulateGrad add kernels and as many zero-filled temporaries per step.  ``p._fa_ready(p)`` (set by TrainStep when it
+# runs data-parallel) tells the bucketed all-reduce that a gradient is complete: the post-accumulate hooks no longer fire
+# for these parameters.  Both switches live on the PARAMETER, not in this module, so two TrainSteps - or a TrainStep
+# beside a plain optim.Adam loop on another net - do not rewire each other.  A parameter without the mark gets its
+# gradient through autograd as usual (what the parity tests exercise).  DIRECT_GRAD = False switches the sinks off
+# process-wide (tests only: direct vs autograd-routed gradients).
+DIRECT_GRAD = True
 FOLD_DROPPATH = True          # fold the DropPath backward scale into the consuming contractions (see _fold)
-GRAD_READY = None
 
 
 def _sink(p):
-    if DIRECT_GRAD and p is not None and p.requires_grad and p.grad is not None and p.grad.is_contiguous():
+    if (DIRECT_GRAD and p is not None and getattr(p, '_fa_direct', False) and p.requires_grad and p.grad is not None
+            and p.grad.is_contiguous()):
         return p.grad
     return None
 
@@ -56,10 +59,11 @@ def _bias_grad(g, p):
 
 
 def _ready(*ps):
-    if GRAD_READY is not None:
-        for p in ps:
-            if p is not None and _sink(p) is not None:
-                GRAD_READY(p)
+    for p in ps:
+        if p is not None:
+            cb = getattr(p, '_fa_ready', None)
+            if cb is not None and _sink(p) is not None:
+                cb(p)
 
 
 def linear_grads(g, x, W, dW, db, want_dx=True, dx=None, accumulate_dx=False):

@@ -18,6 +18,7 @@ FLOP_COUNTER = [None]          # bench.py roofline leg: set to 0 to accumulate 2
 # fa_gemm backend used when a call does not name one: 0 = auto (tcgen05 3xTF32 where eligible, else fp32 SIMT).
 # FREQAIR_GEMM_BACKEND=1 forces the fp32 SIMT kernel everywhere (A/B accuracy and speed comparisons).
 DEFAULT_GEMM_BACKEND = int(os.environ.get('FREQAIR_GEMM_BACKEND', '0'))
+GEMM_3X, GEMM_SIMT, GEMM_2X, GEMM_1X = 0, 1, 4, 5     # fa_gemm backend ids (include/freqair.h)
 K_GEMM, K_WIN_ATTN, K_JOINT_ATTN, K_BAND, K_LN, K_DWCONV, K_IM2COL, K_BN, K_OPTIM, K_DCN, K_ELEM = range(1, 12)
 
 
@@ -82,7 +83,7 @@ def _rows2d(t):
 
 def gemm(A, B, C, transA=False, transB=True, bias=None, act=ACT_NONE, act_param=0.0, aux=None, aux_act=ACT_NONE,
          aux_param=0.0, rowscale=None, rows_per_scale=1, residual=None, accumulate=False, alpha=1.0, preact=None,
-         backend=None, a_rowsum=None, a_kscale=None, a_k_rows_per_scale=1):
+         backend=None, a_rowsum=None, a_kscale=None, a_k_rows_per_scale=1, b_is_tf32=False):
     """C = epi(alpha * op(A) @ op(B)); see fa_gemm in include/freqair.h.  A, B, C, aux, residual, preact are 2-D
     row-major views (row stride may exceed the width).  transB=True means B is an nn.Linear weight [N, K]."""
     ar, ac, lda = _rows2d(A)
@@ -127,6 +128,7 @@ def gemm(A, B, C, transA=False, transB=True, bias=None, act=ACT_NONE, act_param=
             raise RuntimeError(f'freqair.gemm: a_kscale covers {a_kscale.numel() * a_k_rows_per_scale} of K={K}')
         e.a_kscale = a_kscale.data_ptr()
         e.a_k_rows_per_scale = a_k_rows_per_scale
+    e.b_is_tf32 = 1 if b_is_tf32 else 0
     _call('fa_gemm', _p(A), _p(B), _p(C), M, N, K, lda, ldb, ldc, int(transA), int(transB), ctypes.byref(e), backend,
           _stream())
     return C
@@ -469,10 +471,17 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
     _call('fa_adam_step', _p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, step, grad_scale, _stream())
 
 
-def adam_step_dev(p, g, m, v, hyper, beta1, beta2, eps, grad_scale=1.0):
-    """Adam with {lr/(1-b1^t), 1/sqrt(1-b2^t)} read from the 2-float device tensor ``hyper`` (graph-replay safe)."""
-    _f32(p, g, m, v, hyper)
-    _call('fa_adam_step_dev', _p(p), _p(g), _p(m), _p(v), p.numel(), _p(hyper), beta1, beta2, eps, grad_scale, _stream())
+def adam_tick(state):
+    """state = {lr (fp32), step count (int32)} in device memory: count += 1 (fa_adam_tick; graph-replay safe)."""
+    _f32(state)
+    _call('fa_adam_tick', _p(state), _stream())
+
+
+def adam_step_state(p, g, m, v, state, beta1, beta2, eps, grad_scale=1.0):
+    """Adam with lr and the step count read from the 2-word device tensor ``state``; the bias corrections are derived
+    inside the kernel, so a captured graph of the step never reads host memory."""
+    _f32(p, g, m, v, state)
+    _call('fa_adam_step_state', _p(p), _p(g), _p(m), _p(v), p.numel(), _p(state), beta1, beta2, eps, grad_scale, _stream())
 
 
 def _ptr_array(tensors):

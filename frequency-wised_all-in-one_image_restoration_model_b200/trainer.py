@@ -11,7 +11,6 @@ import torch.nn.functional as F
 
 from . import ops
 from .losses import l1_loss, spectral_l1_loss
-from .net import lewin
 
 
 def _offsets(params):
@@ -77,27 +76,38 @@ class BucketedAllReduce:
             counts = [0] * nb
             owners = []
             for p, o in zip(seg.params, seg.offs):
-                b = min(nb - 1, (o + p.numel() - 1) // per)      # bucket of the parameter's last element
-                counts[b] += 1
-                owners.append(base + b)
+                # a parameter that straddles a bucket boundary has elements in BOTH slices: neither may be reduced
+                # before its gradient is complete, so it counts in every bucket it overlaps
+                b0, b1 = min(nb - 1, o // per), min(nb - 1, (o + max(p.numel(), 1) - 1) // per)
+                for b in range(b0, b1 + 1):
+                    counts[b] += 1
+                owners.append(tuple(range(base + b0, base + b1 + 1)))
             for i in range(nb):
                 self.buckets.append((seg.grad[bounds[i]:bounds[i + 1]], counts[i]))
-            for p, b in zip(seg.params, owners):
-                p.register_post_accumulate_grad_hook(self._make_hook(b))
-                self.bucket_of[id(p)] = b
+            for p, bs in zip(seg.params, owners):
+                p.register_post_accumulate_grad_hook(self._make_hook(bs))
+                self.bucket_of[id(p)] = bs
         self.reset()
 
     def param_ready(self, p):
         """A block-level backward accumulated this parameter's gradient straight into the flat buffer (no
-        AccumulateGrad, so no hook): same bookkeeping as the hook, once per parameter per step."""
+        AccumulateGrad, so no hook): same bookkeeping as the hook.  Exactly once per parameter per step: a weight
+        shared by two direct-sink nodes would be announced by the first while the second still has to add to it."""
         k = id(p)
-        b = self.bucket_of.get(k)
-        if b is None or k in self.seen:
+        bs = self.bucket_of.get(k)
+        if bs is None:
             return
+        if k in self.seen:
+            raise RuntimeError('BucketedAllReduce: a parameter was reported complete twice in one step (a weight shared '
+                               'by several direct-gradient nodes is not supported under data parallelism)')
         self.seen.add(k)
-        self.pending[b] -= 1
-        if self.pending[b] == 0:
-            self._launch(b)
+        self._dec(bs)
+
+    def _dec(self, bs):
+        for b in bs:
+            self.pending[b] -= 1
+            if self.pending[b] == 0:
+                self._launch(b)
 
     def reset(self):
         self.seen = set()
@@ -105,11 +115,9 @@ class BucketedAllReduce:
         self.handles = []
         self.launched = [False] * len(self.buckets)
 
-    def _make_hook(self, b):
+    def _make_hook(self, bs):
         def hook(_param):
-            self.pending[b] -= 1
-            if self.pending[b] == 0:
-                self._launch(b)
+            self._dec(bs)
         return hook
 
     def _launch(self, b):
@@ -159,7 +167,7 @@ class TrainStep:
             from .net.utils.frequency_decompose import FrequencyDecompose
             self.decompose = FrequencyDecompose('frequency_decompose', 1. / num_frequency_bands_l1, patch_size, patch_size,
                                                 inverse=False)                       # train.py:70
-        self.ts = [0, 0]                # Adam step count of the encoder / decoder segment
+        self.ts = [0, 0]                # Adam step count of the encoder / decoder segment (host mirror)
         moco = net.E.E
         fq, _ = moco._ensure_flat()
         enc_params = [p for p in moco.encoder_q.parameters()]
@@ -167,18 +175,42 @@ class TrainStep:
         self.segments = [Segment(enc_params, fq), Segment(dec_params)]
         moco._flat_q = self.segments[0].flat
         self.ddp = BucketedAllReduce(self.segments, bucket_mb) if distributed else None
-        # parameters now own .grad views of per-step-zeroed flat buffers: let the block backwards accumulate into them
-        lewin.DIRECT_GRAD = True
-        lewin.GRAD_READY = self.ddp.param_ready if self.ddp is not None else None
+        # Parameters now own .grad views of per-step-zeroed flat buffers: let the block backwards accumulate into them.
+        # The switch is a per-PARAMETER attribute (net/lewin._sink), so a second TrainStep, or a plain optim.Adam loop
+        # on another net in the same process, is not rewired by this constructor.
+        ready = self.ddp.param_ready if self.ddp is not None else None
+        for seg in self.segments:
+            for p in seg.params:
+                p._fa_direct = True
+                p._fa_ready = ready
         self.last = {}
-        # CUDA-graph state (capture()): static inputs / loss, and the two step-dependent Adam scalars in device memory
+        # CUDA-graph state (capture()): static inputs / loss
         self.graph = None
         self.graph_launches = 0
+        self.graph_cfg = None
         self.static_in = None
         self.static_out = None
         dev = self.segments[0].flat.device
-        self.hyper = torch.zeros(4, device=dev, dtype=torch.float32)
-        self.hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory() if dev.type == 'cuda' else torch.zeros(4)
+        # Optimiser state that changes from step to step lives ON THE DEVICE: per segment {lr (fp32), step count (int32)}.
+        # fa_adam_tick increments the count and fa_adam_step_state derives the bias corrections from it inside the
+        # kernel, so neither the eager step nor a graph replay reads host memory that a later step may already have
+        # overwritten (the host runs many replays ahead of the GPU).
+        self.opt_state = torch.zeros(2 * len(self.segments), device=dev, dtype=torch.float32)
+        self.set_lr(lr)
+
+    def set_lr(self, lr):
+        """Learning rate of every segment (train.py's StepLR): a stream-ordered device write, valid under graph replay."""
+        self.lr = lr
+        self.opt_state[0::2].fill_(lr)
+
+    def _state(self, i):
+        return self.opt_state[2 * i:2 * i + 2]
+
+    def _sync_counts(self):
+        """Push the host mirror of the step counts to the device (after `ts.t = n`, checkpoint restore)."""
+        cnt = self.opt_state.view(torch.int32)
+        for i, t in enumerate(self.ts):
+            cnt[2 * i + 1].fill_(int(t))
 
     @property
     def t(self):
@@ -187,6 +219,7 @@ class TrainStep:
     @t.setter
     def t(self, v):
         self.ts = [v, v]
+        self._sync_counts()
 
     def zero_grad(self):
         for s in self.segments:
@@ -203,7 +236,7 @@ class TrainStep:
     def _active(self):
         return self.segments[:1] if self.encoder_only else self.segments
 
-    def _body(self, x_query, x_key, clean, use_hyper):
+    def _body(self, x_query, x_key, clean):
         self.zero_grad()
         if self.encoder_only:                                                        # train.py:84-87
             _, logits, labels, _ = self.net.E(x_query, x_key)
@@ -218,62 +251,61 @@ class TrainStep:
             self.ddp.finish()
         gscale = 1.0 / self.ddp.world if self.ddp is not None else 1.0       # mean over ranks, fused into Adam
         for i, s in enumerate(self._active()):
-            if use_hyper:
-                ops.adam_step_dev(s.flat, s.grad, s.m, s.v, self.hyper[2 * i:2 * i + 2], self.betas[0], self.betas[1],
-                                  self.eps, gscale)
-            else:
-                ops.adam_step(s.flat, s.grad, s.m, s.v, self.lr, self.betas[0], self.betas[1], self.eps, self.ts[i], gscale)
+            ops.adam_tick(self._state(i))
+            ops.adam_step_state(s.flat, s.grad, s.m, s.v, self._state(i), self.betas[0], self.betas[1], self.eps, gscale)
         return dict(loss=loss.detach(), l1=l1.detach(), ce=ce.detach())
 
     def _tick(self, d=1):
         for i in range(len(self._active())):
             self.ts[i] += d
 
-    def _advance(self):
-        """step counts += 1 and the step-dependent Adam scalars {lr/(1-b1^t), 1/sqrt(1-b2^t)} of each segment pushed to
-        the device."""
-        self._tick()
-        for i, t in enumerate(self.ts):
-            if t >= 1:
-                self.hyper_host[2 * i] = self.lr / (1.0 - self.betas[0] ** t)
-                self.hyper_host[2 * i + 1] = 1.0 / (1.0 - self.betas[1] ** t) ** 0.5
-        self.hyper.copy_(self.hyper_host, non_blocking=True)
+    def _cfg(self, x_query):
+        return (self.encoder_only, tuple(x_query.shape), self.net.training, self.decompose is not None)
 
     def step(self, x_query, x_key, clean):
         """One optimisation step; returns the (device) loss tensor.  Replays the captured graph when there is one."""
         if self.graph is not None:
+            if self._cfg(x_query) != self.graph_cfg:
+                raise RuntimeError(f'TrainStep.step: the captured graph was recorded for (encoder_only, input shape, '
+                                   f'training, spectral_l1) = {self.graph_cfg} but the step is now {self._cfg(x_query)}; '
+                                   'call capture() again (e.g. at the epochs_encoder phase switch, train.py:82)')
             for dst, src in zip(self.static_in, (x_query, x_key, clean)):
                 if dst.data_ptr() != src.data_ptr():
                     dst.copy_(src, non_blocking=True)
-            self._advance()
+            self._tick()
             self.graph.replay()
             self.last = self.static_out
             return self.last['loss']
         self._tick()
-        self.last = self._body(x_query, x_key, clean, False)
+        self.last = self._body(x_query, x_key, clean)
         return self.last['loss']
 
     def capture(self, x_query, x_key, clean, warmup=2):
-        """Capture the whole step (zero_grad, forward, losses, backward, gradient all-reduce, Adam, momentum and queue
-        updates: ~7 500 kernel launches) into ONE CUDA graph; later ``step`` calls copy the crops into the static input
+        """Capture the whole step (zero_grad, forward, losses, backward, gradient all-reduce, step-count tick, Adam,
+        momentum and queue updates) into ONE CUDA graph; later ``step`` calls copy the crops into the static input
         buffers and replay it.  ``warmup`` eager steps run first on a side stream (allocator warm-up, one-time
-        cudaFuncSetAttribute calls); they are real optimisation steps."""
+        cudaFuncSetAttribute calls); they are real optimisation steps.  The graph is valid for the configuration it was
+        captured with (phase, shapes, train mode): ``step`` refuses to replay it under another one.
+
+        Adam step counts: one count per SEGMENT (query encoder, restorer).  torch.optim.Adam keeps one per parameter
+        and starts it at the first step in which the parameter receives a gradient; the two agree because every
+        parameter of a segment receives a gradient in every step in which its segment is active (encoder-only phase:
+        the restorer segment is skipped as a whole, exactly like parameters without .grad in torch)."""
         self.static_in = [t.clone() for t in (x_query, x_key, clean)]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self._advance()
-                self._body(*self.static_in, True)
+                self._tick()
+                self._body(*self.static_in)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        self._advance()
         n0 = ops.launch_count()
         with torch.cuda.graph(graph):
-            self.static_out = self._body(*self.static_in, True)
+            self.static_out = self._body(*self.static_in)
         self.graph_launches = ops.launch_count() - n0        # libfreqair kernels recorded in the graph (per replay)
-        self._tick(-1)                  # capture records the step without executing it
-        self.graph = graph
+        self.graph = graph                                    # capture records the step without executing it
+        self.graph_cfg = self._cfg(x_query)
         self.last = self.static_out
         return self.static_out['loss']

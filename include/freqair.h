@@ -25,7 +25,9 @@ extern "C" {
 typedef void* fa_stream_t; /* cudaStream_t */
 
 /* ------------------------------------------------------------------ library */
+#define FREQAIR_ABI_VERSION 2      /* bumped whenever a prototype or struct in this header changes */
 const char* fa_version(void);
+int fa_abi_version(void);          /* the FREQAIR_ABI_VERSION the library was compiled against (checked at load time) */
 const char* fa_last_error_string(void);
 int fa_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* in-stream timing of one kernel class (bench.py roofline leg): cls = FA_K_* id, 0 = off */
@@ -47,7 +49,11 @@ enum { FA_ACT_NONE = 0, FA_ACT_GELU = 1, FA_ACT_LRELU = 2, FA_ACT_SIGMOID = 3 };
  *      autograd backward of each (cuBLAS sgemm in the reference).
  * backend: 0 = auto (tcgen05 error-compensated 3xTF32 - fp32-level accuracy - when the shape is eligible, else fp32
  *          SIMT), 1 = force fp32 SIMT, 2 = force tcgen05 3xTF32 (error if not eligible), 3 = force tcgen05 single-pass
- *          TF32 (operands truncated to 10 mantissa bits; measurement / comparison only). */
+ *          TF32 on the raw operands (truncated to 10 mantissa bits by the tensor core; measurement / comparison only),
+ *          4 = tcgen05 2xTF32: op(A) exact (hi + lo split), op(B) rounded to the nearest TF32 inside the kernel
+ *          (relative operand error <= 2^-12, unbiased), 5 = tcgen05 1xTF32 with BOTH operands rounded to nearest.
+ *          4 and 5 fall back to the SIMT kernel for ineligible shapes like 0 does.  Which layer classes may use them is
+ *          a parity decision made by the caller (the LeFF contractions; everything else stays 3x). */
 typedef struct FaGemmEpilogue {
   const float* bias;
   int act; float act_param;
@@ -66,6 +72,8 @@ typedef struct FaGemmEpilogue {
      tcgen05 path only (an ineligible shape is an error, not a fallback). */
   const float* a_kscale;
   int a_k_rows_per_scale;
+  int b_is_tf32;                  /* backends 4 / 5: op(B) is already TF32-representable (e.g. weights rounded once per
+                                     optimiser step by fa_round_tf32): the kernel skips its in-place rounding of B */
 } FaGemmEpilogue;
 int fa_gemm(const float* A, const float* B, float* C, int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc,
             int transA, int transB, const FaGemmEpilogue* epi, int backend, fa_stream_t stream);
@@ -254,10 +262,14 @@ int fa_momentum_update(float* k, const float* q, int64_t n, float m, fa_stream_t
 /* torch.optim.Adam step over a flat buffer (train.py:63,96); step >= 1 */
 int fa_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                  int step, float grad_scale, fa_stream_t stream);
-/* the same update with the two step-dependent scalars read from DEVICE memory at run time, hyper = {lr / (1 - beta1^t),
- * 1 / sqrt(1 - beta2^t)}: a captured CUDA graph of the train step stays valid as t (and a scheduled lr) advance */
-int fa_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, float beta1, float beta2,
-                     float eps, float grad_scale, fa_stream_t stream);
+/* the same update with the step-dependent quantities held in DEVICE memory: state = {float lr, int32 step count}.
+ * fa_adam_tick does count += 1 (one thread); fa_adam_step_state reads lr and the count at run time and derives
+ * lr / (1 - beta1^t) and 1 / sqrt(1 - beta2^t) inside the kernel (double precision, as torch's host code).  A captured
+ * CUDA graph of the train step is therefore self-contained: replays never read host memory, however far the host runs
+ * ahead of the device, and a scheduled lr is one stream-ordered device write. */
+int fa_adam_tick(float* state, fa_stream_t stream);
+int fa_adam_step_state(float* p, const float* g, float* m, float* v, int64_t n, const float* state, float beta1,
+                       float beta2, float eps, float grad_scale, fa_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -4,6 +4,7 @@ import importlib
 import os
 import socket
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -18,21 +19,39 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _model():
+class _Reversed(nn.Module):
+    """Parameters REGISTERED as [out, inp] but USED inp -> out: backward completes `out`'s gradient first, so with small
+    buckets a parameter that straddles a bucket boundary has its head in a bucket whose other parameters finish earlier.
+    (The round-1 bookkeeping counted a parameter only in the bucket of its last element and reduced such a bucket
+    before the straddling gradient was written - found by the advisor; nn.Sequential's forward-order registration hid it.)"""
+
+    def __init__(self):
+        super().__init__()
+        self.out = nn.Linear(5, 3)
+        self.mid = nn.Linear(13, 5)
+        self.inp = nn.Linear(7, 13)
+
+    def forward(self, x):
+        return self.out(torch.tanh(self.mid(torch.tanh(self.inp(x)))))
+
+
+def _model(variant='seq'):
     torch.manual_seed(0)
+    if variant == 'reversed':
+        return _Reversed()
     return nn.Sequential(nn.Linear(7, 13), nn.Tanh(), nn.Linear(13, 5), nn.Tanh(), nn.Linear(5, 3))
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, variant='seq', bucket_floats=16):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
         trainer = importlib.import_module(PKG_NAME + '.trainer')
-        net = _model()
+        net = _model(variant)
         params = list(net.parameters())
         seg_a, seg_b = trainer.Segment(params[:2]), trainer.Segment(params[2:])
-        # 64-byte buckets: several buckets per segment, parameters straddling bucket boundaries
-        ddp = trainer.BucketedAllReduce([seg_a, seg_b], bucket_mb=64 / (1 << 20))
+        # 64-byte (or 96-byte) buckets: several buckets per segment, parameters straddling bucket boundaries
+        ddp = trainer.BucketedAllReduce([seg_a, seg_b], bucket_mb=4 * bucket_floats / (1 << 20))
         assert len(ddp.buckets) > 4
         res = []
         for step in range(2):                          # two steps: reset() must re-arm the hooks
@@ -48,18 +67,19 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_bucketed_allreduce_world2():
+@pytest.mark.parametrize('variant,bucket_floats', [('seq', 16), ('reversed', 24), ('reversed', 16)])
+def test_bucketed_allreduce_world2(variant, bucket_floats):
     world = 2
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out, variant, bucket_floats), nprocs=world, join=True)
     assert torch.equal(out[0], out[1])                  # both ranks hold the same reduced gradients
     # expected: sum over ranks of the single-process gradients, in flat-segment order
     trainer = importlib.import_module(PKG_NAME + '.trainer')
     for step in range(2):
         tot = None
         for rank in range(world):
-            net = _model()
+            net = _model(variant)
             x = torch.randn(4, 7, generator=torch.Generator().manual_seed(10 * step + rank))
             net(x).square().sum().backward()
             params = list(net.parameters())

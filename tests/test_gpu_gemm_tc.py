@@ -44,7 +44,7 @@ SHAPES = [(128, 32, 32), (256, 56, 56), (4096, 224, 56), (1000, 112, 28), (2048,
           (40, 12, 520), (8, 8, 8)]
 
 
-@pytest.mark.parametrize('backend', [2, 3])
+@pytest.mark.parametrize('backend', [2, 3, 4, 5])
 @pytest.mark.parametrize('M,N,K', SHAPES)
 @pytest.mark.parametrize('tA,tB', [(False, True), (False, False), (True, False), (True, True)])
 def test_gemm_tc_plain(ops, M, N, K, tA, tB, backend):
@@ -78,6 +78,23 @@ def test_gemm_tc_fp32_inputs(ops, M, N, K, tA, tB):
     e1 = (C1.double().cpu() - ref).abs().max().item()
     assert e3 <= 3 * e1 + 1e-6, f'3xTF32 {M}x{N}x{K}: max err {e3:.3e} (fp32 SIMT {e1:.3e})'
     print(f'3xTF32 err {e3:.3e}, fp32 SIMT err {e1:.3e}')
+    # reduced-pass modes against their DEFINITION (same operand treatment in fp64): 2x = A exact, B rounded to nearest
+    # TF32; 1x = both rounded to nearest.  What is left is accumulation round-off, i.e. the 3x-level bound.
+    def rn(x):
+        return ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    opA, opB = (A.t() if tA else A), (B.t() if tB else B)
+    for backend, ra, rb in ((4, opA, rn(opB)), (5, rn(opA), rn(opB))):
+        Cx = torch.full((M, N), float('nan'), device='cuda')
+        ops.gemm(A.cuda(), B.cuda(), Cx, transA=tA, transB=tB, backend=backend)
+        refx = ra.double() @ rb.double()
+        ex = (Cx.double().cpu() - refx).abs().max().item()
+        assert ex <= 3 * e1 + 1e-6, f'backend {backend} {M}x{N}x{K}: {ex:.3e} away from its own definition (fp32 SIMT {e1:.3e})'
+        # and the operand rounding itself stays inside the TF32 bound (unbiased: ~2^-12 per operand, sqrt(K) growth)
+        tf32_close(Cx, ref, K, f'backend {backend} vs fp64', ascale=0.5)
+        # pre-rounded B + b_is_tf32: the kernel skips B and must give the same result bit for bit
+        Cy = torch.full((M, N), float('nan'), device='cuda')
+        ops.gemm(A.cuda(), rn(B).cuda(), Cy, transA=tA, transB=tB, backend=backend, b_is_tf32=True)
+        assert torch.equal(Cx, Cy), f'backend {backend}: b_is_tf32 path differs from in-kernel rounding'
 
 
 def test_gemm_tc_epilogues(ops):

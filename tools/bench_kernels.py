@@ -53,7 +53,7 @@ def gemm_cases():
     return cases
 
 
-def bench_gemm(backend, only=None, layouts='NT,NN,TN'):
+def bench_gemm(backend, only=None, layouts='NT,NN,TN', bexact=False):
     print(f'{"case":24s} {"layout":3s} {"M":>8s} {"N":>6s} {"K":>6s} {"ms":>8s} {"TFLOP/s":>8s} {"GB/s":>8s}')
     for name, M, N, K in gemm_cases():
         if only and only not in name:
@@ -64,8 +64,8 @@ def bench_gemm(backend, only=None, layouts='NT,NN,TN'):
         dX = torch.empty(M, K, device='cuda')
         dW = torch.zeros(N, K, device='cuda')
         for lay, fn, flops, byts in [
-            ('NT', lambda: ops.gemm(X, W, Y, backend=backend), 2 * M * N * K, 4 * (M * K + N * K + M * N)),
-            ('NN', lambda: ops.gemm(Y, W, dX, transB=False, backend=backend), 2 * M * N * K, 4 * (M * N + N * K + M * K)),
+            ('NT', lambda: ops.gemm(X, W, Y, backend=backend, b_is_tf32=bexact), 2 * M * N * K, 4 * (M * K + N * K + M * N)),
+            ('NN', lambda: ops.gemm(Y, W, dX, transB=False, backend=backend, b_is_tf32=bexact), 2 * M * N * K, 4 * (M * N + N * K + M * K)),
             ('TN', lambda: ops.gemm(Y, X, dW, transA=True, transB=False, accumulate=True, backend=backend), 2 * M * N * K,
              4 * (M * N + M * K + N * K)),
         ]:
@@ -180,9 +180,10 @@ if __name__ == '__main__':
     ap.add_argument('--backend', type=int, default=0)
     ap.add_argument('--only', default=None)
     ap.add_argument('--layouts', default='NT,NN,TN')
+    ap.add_argument('--bexact', action='store_true', help='backends 4/5: declare the weight operand pre-rounded (b_is_tf32)')
     a = ap.parse_args()
     if a.what == 'gemm':
-        bench_gemm(a.backend, a.only, a.layouts)
+        bench_gemm(a.backend, a.only, a.layouts, a.bexact)
     if a.what == 'epi':
         bench_epi(a.backend)
     if a.what == 'misc':
