@@ -34,7 +34,13 @@ constexpr int BK = 32;              // floats per k-block = one 128-byte swizzle
 constexpr int UMMA_K = 8;           // tf32
 constexpr int KC_BLOCKS = 8;        // k-blocks accumulated inside TMEM before promotion to registers (KC = 256)
 constexpr int MAX_STAGES = 8;
-constexpr int SPLIT_WARPS = 4;      // 14 warps: 4 on one SM sub-partition -> 128 registers per thread
+// 16 warps = 4 per SM sub-partition (128 registers per thread; a 5th warp on a sub-partition would cap everyone at 96):
+// warp 0 TMA producer, warp 1 MMA issuer, warps 2-3 B-operand split / rounding, warps 4-7 A-operand staging into TMEM
+// (thread = tile row = TMEM lane, quarter = warp % 4), warps 8-15 epilogue.
+constexpr int BSPLIT_WARPS = 2;
+constexpr int ASPLIT_WARPS = 4;
+constexpr int ASPLIT_WARP0 = 2 + BSPLIT_WARPS;
+constexpr int SPLIT_WARPS = BSPLIT_WARPS + ASPLIT_WARPS;
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_WARP0 = 2 + SPLIT_WARPS;     // first epilogue warp (TMEM lane quarter = warp % 4)
 constexpr int NTHREADS = 32 * (2 + SPLIT_WARPS + EPI_WARPS);
@@ -134,6 +140,14 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const float (&v)[32]) {
         "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
       : "memory");
 }
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]),
+        "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+      : "memory");
+}
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem: lane = row, column = k] . B[smem descriptor]
 __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -162,6 +176,20 @@ __device__ __forceinline__ void tc_mma_tf32_ts2(uint32_t d_tmem, uint32_t a_tmem
       "setp.ne.b32 p, %5, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(ACC)
+      : "memory");
+}
+
+// SS form (both operands from shared memory), descriptors as 32-bit word pairs like tc_mma_tf32_ts2
+template <int ACC>
+__device__ __forceinline__ void tc_mma_tf32_ss2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\t"
+      "mov.b64 ad, {%1, %2};\n\t"
+      "mov.b64 bd, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], ad, bd, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(ACC)
       : "memory");
 }
 
@@ -194,13 +222,11 @@ __device__ __forceinline__ float lds32(uint32_t saddr) {
   return v;
 }
 
-// round-to-nearest (ties away) to TF32: the result is exactly representable, so the tensor core's operand truncation is
-// the identity on it
-__device__ __forceinline__ float rn1(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+// round-to-nearest (ties away) to TF32 as the tensor core will see it
+// ONE integer add: half an ulp(TF32) is added to the magnitude and the low 13 bits are left for the tensor core to
+// truncate (cvt.rna.tf32.f32 compiles to add + inf/nan select + mask: 4 instructions per element on the warps that
+// pace the pipeline; the mask is redundant in front of a truncating consumer, the select only matters for inf / nan)
+__device__ __forceinline__ float rn1(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 __device__ __forceinline__ float4 rn4(float4 v) { return make_float4(rn1(v.x), rn1(v.y), rn1(v.z), rn1(v.w)); }
 __device__ __forceinline__ float lo1(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __device__ __forceinline__ float4 lo4(float4 v) { return make_float4(lo1(v.x), lo1(v.y), lo1(v.z), lo1(v.w)); }
@@ -369,6 +395,30 @@ __device__ __forceinline__ void epi_rows(uint32_t stg_s, const EpiTC& e, float4 
   }
 }
 
+// Lean store path for a 32 x 32 chunk that lies completely inside C and whose epilogue only STORES (bias, activation,
+// optional pre-activation copy; or the plain alpha * acc): no per-row bound checks, no 64-bit multiplies and no flag tests
+// inside the row loop - the pointers advance by one add per row quad and the two swizzled shared-memory offsets (rows
+// r = 4*it + rsub alternate between r % 8 = rsub and rsub + 4) are computed once.  ncu on the K = 112, N = 448 contraction
+// of the 128 x 128 level: the generic loop executed ~470 instructions per chunk and kept the eight epilogue warps busy
+// 90 % of the time while every other role waited; this one is ~4x shorter.
+template <int ACT, bool PRE>
+__device__ __forceinline__ void epi_chunk_store(uint32_t stg_s, float alpha, float act_p, float4 b4, int rsub, int c4,
+                                                float* __restrict__ cp, int64_t ldc, float* __restrict__ pp, int64_t ldpre) {
+  const uint32_t a0 = stg_s + 4 * (rsub * 32 + ((((c4 >> 2) ^ rsub) & 7) << 2));
+  const uint32_t a1 = stg_s + 4 * ((rsub + 4) * 32 + ((((c4 >> 2) ^ (rsub + 4)) & 7) << 2));
+  const int64_t dc = 4 * ldc, dp = 4 * ldpre;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    float4 x = lds128(((it & 1) ? a1 : a0) + (it >> 1) * (8 * 32 * 4));
+    x.x = fmaf(x.x, alpha, b4.x); x.y = fmaf(x.y, alpha, b4.y);
+    x.z = fmaf(x.z, alpha, b4.z); x.w = fmaf(x.w, alpha, b4.w);
+    if (PRE) { *reinterpret_cast<float4*>(pp) = x; pp += dp; }
+    if (ACT != ACT_NONE) x = make_float4(act_c<ACT>(x.x, act_p), act_c<ACT>(x.y, act_p), act_c<ACT>(x.z, act_p), act_c<ACT>(x.w, act_p));
+    *reinterpret_cast<float4*>(cp) = x;
+    cp += dc;
+  }
+}
+
 template <int BN, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
@@ -397,8 +447,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = g.tiles_m * g.tiles_n * g.splits;
 
+  // who publishes a stage: the A warps always; the B warps when they have work (B_lo, or rounding B in place)
+  const bool need_b = PASSES == 3 || (SPLIT && !g.b_exact);
+  const uint32_t ready_count = A_TMEM ? (ASPLIT_WARPS + (need_b ? BSPLIT_WARPS : 0)) * 32 : SPLIT_WARPS * 32;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], SPLIT_WARPS * 32); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], ready_count); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -420,15 +473,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     {
       // ---------------------------------------------------------------- TMA producer
       // (whole warp walks the loop, an elected lane issues: coordinates and addresses stay in uniform registers)
-      uint32_t it = 0;
+      uint32_t ph = 1;               // parity to wait for on empty[s]: flips every time the ring wraps (no division per k-block)
       int s = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int sp = t % g.splits, rest = t / g.splits;
         const int m0 = (rest / g.tiles_n) * BM, n0 = (rest % g.tiles_n) * BN;
         const int kbeg = sp * g.k_chunk;
         const int nkb = (min(g.K, kbeg + g.k_chunk) - kbeg + BK - 1) / BK;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty[s], ph);
           if (elect_one()) {
           mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
           const int k0 = kbeg + kb * BK;
@@ -446,7 +499,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
           }
           }
           __syncwarp();
-          if (++s == STAGES) s = 0;
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -460,7 +513,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (((A_MN && !A_TMEM) ? 1u : 0u) << 15) |
                              ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t astep = A_MN ? 1024u : 32u, bstep = B_MN ? 1024u : 32u;
-      uint32_t it = 0, lu = 0;           // lu = accumulation units issued (a unit = up to KC_BLOCKS k-blocks of one tile)
+      uint32_t ph = 0, lu = 0;           // lu = accumulation units issued (a unit = up to KC_BLOCKS k-blocks of one tile)
       int s = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int sp = t % g.splits;
@@ -479,8 +532,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
             const uint32_t b_lo0 = lo_c | ((smem_u32(sB) >> 4) & 0x3FFFu), bl_lo0 = lo_c | ((smem_u32(sBlo) >> 4) & 0x3FFFu);
             const uint32_t kinc = bstep >> 4;
             const uint32_t at_base = tmem_base + TMEM_A_COL0;
-            for (int kb = kb0; kb < kb1; ++kb, ++it) {
-              mbar_wait(&ready[s], (it / STAGES) & 1);
+            for (int kb = kb0; kb < kb1; ++kb) {
+              mbar_wait(&ready[s], ph);
               tc_fence_after();
               const uint32_t bs = b_lo0 + (uint32_t)s * (B_BYTES >> 4), bls = bl_lo0 + (uint32_t)s * (B_BYTES >> 4);
               const uint32_t at = at_base + (uint32_t)s * A_TSTRIDE;                         // hi at +0, lo at +32
@@ -514,11 +567,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
                 tc_commit(&empty[s]);                  // frees the smem slot when these MMAs retire
               }
               __syncwarp();
-              if (++s == STAGES) s = 0;
+              if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+          } else if (!SPLIT) {
+            // raw operands straight from the TMA tiles (SS form), one MMA per k-step: the operands are either
+            // TF32-representable already (pre-rounded by their producers) or get truncated by the tensor core
+            const uint64_t dza = make_desc(0, A_MN), dzb = make_desc(0, B_MN);
+            const uint32_t a_hi = (uint32_t)(dza >> 32), b_hi = (uint32_t)(dzb >> 32);
+            const uint32_t a_lo0 = (uint32_t)dza | ((smem_u32(sA) >> 4) & 0x3FFFu), b_lo0 = (uint32_t)dzb | ((smem_u32(sB) >> 4) & 0x3FFFu);
+            const uint32_t ainc = astep >> 4, binc = bstep >> 4;
+            for (int kb = kb0; kb < kb1; ++kb) {
+              mbar_wait(&full[s], ph);
+              tc_fence_after();
+              const uint32_t as_ = a_lo0 + (uint32_t)s * (A_BYTES >> 4), bs = b_lo0 + (uint32_t)s * (B_BYTES >> 4);
+              if (elect_one()) {
+                if (kb == kb0) tc_mma_tf32_ss2<0>(d_tmem, as_, a_hi, bs, b_hi, idesc);
+                else tc_mma_tf32_ss2<1>(d_tmem, as_, a_hi, bs, b_hi, idesc);
+#pragma unroll
+                for (int k = 1; k < BK / UMMA_K; ++k) tc_mma_tf32_ss2<1>(d_tmem, as_ + k * ainc, a_hi, bs + k * binc, b_hi, idesc);
+                tc_commit(&empty[s]);
+              }
+              __syncwarp();
+              if (++s == STAGES) { s = 0; ph ^= 1; }
             }
           } else
-          for (int kb = kb0; kb < kb1; ++kb, ++it) {
-            mbar_wait(SPLIT ? &ready[s] : &full[s], (it / STAGES) & 1);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(SPLIT ? &ready[s] : &full[s], ph);
             tc_fence_after();
             if (lane == 0) {
             const uint32_t a0 = smem_u32(sA + s * A_BYTES), b0 = smem_u32(sB + s * B_BYTES);
@@ -543,7 +617,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
             tc_commit(&empty[s]);                      // frees the smem slot when these MMAs retire
             }
             __syncwarp();
-            if (++s == STAGES) s = 0;
+            if (++s == STAGES) { s = 0; ph ^= 1; }
           }
           if (lane == 0) tc_commit(&tmem_full[as]);    // partial accumulator complete
           __syncwarp();
@@ -552,96 +626,121 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     }
   } else if (warp < EPI_WARP0) {
     // ------------------------------------------------------------------ split warps: lo = x - trunc_tf32(x) / rn_tf32(x)
-    if (SPLIT) {
-      const int st = threadIdx.x - 64;        // 0..SPLIT_WARPS*32-1
+    // These warps pace the kernel (ncu: the only role that never waits), so their loops hold nothing but the loads, one or
+    // two ALU ops per element and the TMEM / smem stores.
+    if (SPLIT && A_TMEM && warp >= ASPLIT_WARP0) {
+      // ---- A warps: thread = A-tile row (= TMEM lane): gather the row's 32 k-values from the swizzled tile TMA wrote,
+      // store them (and their lo parts, or their TF32 rounding) into this stage's TMEM columns; the MMA then reads A
+      // without touching shared memory
+      const int q4 = warp & 3, r = q4 * 32 + lane;
+      const bool has_ks = epi.a_kscale != nullptr, has_rs = epi.a_rowsum != nullptr;
       float rsum = 0.f;                       // a_rowsum: this thread's A row, summed over the k-blocks of the tile
-      uint32_t it = 0;
+      uint32_t ph = 0;
+      int s = 0;
+      const uint32_t tbase = tmem_base + ((uint32_t)(q4 * 32) << 16) + TMEM_A_COL0;
+      const uint32_t abase = smem_u32(sA) + (A_MN ? (r >> 5) * 4096 + (r & 7) * 4 : r * 128);
+      const int cm = (r & 31) >> 3;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int sp = t % g.splits;
+        const int kbeg = sp * g.k_chunk;
+        const int nkb = (min(g.K, kbeg + g.k_chunk) - kbeg + BK - 1) / BK;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[s], ph);
+          const uint32_t a0 = abase + s * A_BYTES;
+          float av[32];
+          if (!A_MN) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 v = lds128(a0 + (((c ^ r) & 7) << 4));
+              av[4 * c] = v.x; av[4 * c + 1] = v.y; av[4 * c + 2] = v.z; av[4 * c + 3] = v.w;
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) av[k] = lds32(a0 + k * 128 + (((cm ^ k) & 3) << 5));
+          }
+          const uint32_t taddr = tbase + s * A_TSTRIDE;
+          if (has_ks) {                               // DropPath scale of the k-block's sample, folded into A
+            const float sc = __ldg(epi.a_kscale + (kbeg + kb * BK) / epi.a_krps);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) av[k] *= sc;
+          }
+          if (has_rs) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) rsum += av[k];
+          }
+          if (PASSES == 1) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) av[k] = rn1(av[k]);
+            tc_st32(taddr, av);
+          } else {
+            tc_st32(taddr, av);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) av[k] = lo1(av[k]);
+            tc_st32(taddr + 32, av);
+          }
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(&ready[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        if (has_rs) {
+          const int rest = t / g.splits;
+          const int row = (rest / g.tiles_n) * BM + r;
+          if (rest % g.tiles_n == 0 && row < g.M) atomicAdd(epi.a_rowsum + row, rsum);     // each A tile counted once
+          rsum = 0.f;
+        }
+      }
+    } else if (SPLIT && A_TMEM) {
+      // ---- B warps: lo = x - trunc(x) into the B_lo tile (3 passes), or x rounded to nearest TF32 in place (1 / 2 passes
+      // on a B that its producer did not pre-round).  Element-wise, so swizzle-agnostic.
+      if (need_b) {
+        const int st = threadIdx.x - 64;        // 0..BSPLIT_WARPS*32-1
+        constexpr int NB = B_BYTES / 16 / (BSPLIT_WARPS * 32);
+        uint32_t ph = 0;
+        int s = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+          const int sp = t % g.splits;
+          const int kbeg = sp * g.k_chunk;
+          const int nkb = (min(g.K, kbeg + g.k_chunk) - kbeg + BK - 1) / BK;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&full[s], ph);
+            const uint32_t b = smem_u32(sB + s * B_BYTES) + st * 16, bl = smem_u32(sBlo + s * B_BYTES) + st * 16;
+            float4 rb[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) rb[i] = lds128(b + i * BSPLIT_WARPS * 512);
+            if (PASSES == 3) {
+#pragma unroll
+              for (int i = 0; i < NB; ++i) sts128(bl + i * BSPLIT_WARPS * 512, lo4(rb[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < NB; ++i) sts128(b + i * BSPLIT_WARPS * 512, rn4(rb[i]));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy smem writes -> visible to UMMA
+            mbar_arrive(&ready[s]);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    } else if (SPLIT) {
+      // ---- legacy 3-pass form with A and A_lo in shared memory (FREQAIR_GEMM_ATMEM=0; kept for A/B measurements):
+      // all 6 warps split both tiles.  All loads first, then all stores: a load-convert-store chain per element would
+      // serialise ~32 shared-memory round trips per stage.
+      const int st = threadIdx.x - 64;        // 0..SPLIT_WARPS*32-1
+      uint32_t ph = 0;
       int s = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int sp = t % g.splits;
         const int kbeg = sp * g.k_chunk;
         const int nkb = (min(g.K, kbeg + g.k_chunk) - kbeg + BK - 1) / BK;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          mbar_wait(&full[s], (it / STAGES) & 1);
-          constexpr int NB = B_BYTES / 16 / (SPLIT_WARPS * 32);
-          const uint32_t b = smem_u32(sB + s * B_BYTES) + st * 16, bl = smem_u32(sBlo + s * B_BYTES) + st * 16;
-          float4 rb[NB];
-          if (A_TMEM) {
-            // thread = A-tile row (= TMEM lane): gather the row's 32 k-values from the swizzled tile TMA wrote, store
-            // them and their lo parts into this stage's TMEM columns; the MMA then reads A without touching smem
-            const int q4 = warp & 3, r = q4 * 32 + lane;
-            const uint32_t a0 = smem_u32(sA + s * A_BYTES);
-            float av[32];
-            if (!A_MN) {
-              const uint32_t base = a0 + r * 128;
-#pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const float4 v = lds128(base + (((c ^ r) & 7) << 4));
-                av[4 * c] = v.x; av[4 * c + 1] = v.y; av[4 * c + 2] = v.z; av[4 * c + 3] = v.w;
-              }
-            } else {
-              const uint32_t base = a0 + (r >> 5) * 4096 + (r & 7) * 4;
-              const int cm = (r & 31) >> 3;
-#pragma unroll
-              for (int k = 0; k < 32; ++k) av[k] = lds32(base + k * 128 + (((cm ^ k) & 3) << 5));
-            }
-            if (PASSES == 3 || !g.b_exact) {
-#pragma unroll
-              for (int i = 0; i < NB; ++i) rb[i] = lds128(b + i * SPLIT_WARPS * 512);
-            }
-            const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + TMEM_A_COL0 + s * A_TSTRIDE;
-            if (epi.a_kscale) {                         // DropPath scale of the k-block's sample, folded into A
-              const float sc = __ldg(epi.a_kscale + (kbeg + kb * BK) / epi.a_krps);
-#pragma unroll
-              for (int k = 0; k < 32; ++k) av[k] *= sc;
-            }
-            if (epi.a_rowsum) {
-#pragma unroll
-              for (int k = 0; k < 32; ++k) rsum += av[k];
-            }
-            if (PASSES == 1) {
-#pragma unroll
-              for (int k = 0; k < 32; ++k) av[k] = rn1(av[k]);
-              tc_st32(taddr, av);
-            } else {
-              tc_st32(taddr, av);
-#pragma unroll
-              for (int k = 0; k < 32; ++k) av[k] = lo1(av[k]);
-              tc_st32(taddr + 32, av);
-            }
-            if (PASSES == 3) {
-#pragma unroll
-              for (int i = 0; i < NB; ++i) sts128(bl + i * SPLIT_WARPS * 512, lo4(rb[i]));
-            } else if (!g.b_exact) {                    // round B to nearest TF32 where it lies (element-wise: swizzle-agnostic)
-#pragma unroll
-              for (int i = 0; i < NB; ++i) sts128(b + i * SPLIT_WARPS * 512, rn4(rb[i]));
-            }
-            tc_wait_st();
-            tc_fence_before();
-          } else {
-            // all loads first, then all stores: a load-convert-store chain per element would serialise ~32 shared-memory
-            // round trips per stage (measured: the split stage, not the tensor pipe, then paces the whole kernel)
-            constexpr int NA = A_BYTES / 16 / (SPLIT_WARPS * 32);
-            const uint32_t a = smem_u32(sA + s * A_BYTES) + st * 16, al = smem_u32(sAlo + s * A_BYTES) + st * 16;
-            float4 ra[NA];
-#pragma unroll
-            for (int i = 0; i < NA; ++i) ra[i] = lds128(a + i * SPLIT_WARPS * 512);
-#pragma unroll
-            for (int i = 0; i < NB; ++i) rb[i] = lds128(b + i * SPLIT_WARPS * 512);
-#pragma unroll
-            for (int i = 0; i < NA; ++i) sts128(al + i * SPLIT_WARPS * 512, lo4(ra[i]));
-#pragma unroll
-            for (int i = 0; i < NB; ++i) sts128(bl + i * SPLIT_WARPS * 512, lo4(rb[i]));
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to UMMA
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[s], ph);
+          const uint32_t a = smem_u32(sA + s * A_BYTES), al = smem_u32(sAlo + s * A_BYTES);
+          const uint32_t b = smem_u32(sB + s * B_BYTES), bl = smem_u32(sBlo + s * B_BYTES);
+          for (int i = st; i < A_BYTES / 16; i += SPLIT_WARPS * 32) sts128(al + i * 16, lo4(lds128(a + i * 16)));
+          for (int i = st; i < B_BYTES / 16; i += SPLIT_WARPS * 32) sts128(bl + i * 16, lo4(lds128(b + i * 16)));
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           mbar_arrive(&ready[s]);
-          if (++s == STAGES) s = 0;
-        }
-        if (A_TMEM && epi.a_rowsum) {
-          const int rest = t / g.splits;
-          const int row = (rest / g.tiles_n) * BM + (warp & 3) * 32 + lane;
-          if (rest % g.tiles_n == 0 && row < g.M) atomicAdd(epi.a_rowsum + row, rsum);     // each A tile counted once
-          rsum = 0.f;
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -653,6 +752,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     float* stg = stg_all + ew * (32 * 32);
     const uint32_t stg_s = smem_u32(stg);
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;        // vector path: a warp instruction covers 4 rows x 32 columns
+    // epilogues that read nothing from global memory and write every element exactly once take the lean store path
+    const bool store_only = (MODE == EPI_PLAIN && !epi.atomic && !epi.accumulate) ||
+                            (MODE == EPI_FWD && !epi.residual && !epi.rowscale);
     uint32_t lu = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int sp = t % g.splits, rest = t / g.splits;
@@ -703,6 +805,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
                 if (epi.bias) b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
               float* cp0 = C + (int64_t)(row0 + rsub) * g.ldc + col;
               const int act = (MODE == EPI_FWD) ? epi.act : (MODE == EPI_BWD ? epi.aux_act : ACT_NONE);
+              bool done = false;
+              if (store_only && row0 + 32 <= g.M) {
+                if (MODE == EPI_PLAIN) {
+                  epi_chunk_store<ACT_NONE, false>(stg_s, epi.alpha, 0.f, b4, rsub, c4, cp0, g.ldc, nullptr, 0);
+                  done = true;
+                } else if (MODE == EPI_FWD) {
+                  float* pp0 = epi.preact ? epi.preact + (int64_t)(row0 + rsub) * epi.ldpre + col : nullptr;
+                  done = true;
+                  if (pp0 && act == ACT_GELU) epi_chunk_store<ACT_GELU, true>(stg_s, epi.alpha, epi.act_p, b4, rsub, c4, cp0, g.ldc, pp0, epi.ldpre);
+                  else if (!pp0 && act == ACT_GELU) epi_chunk_store<ACT_GELU, false>(stg_s, epi.alpha, epi.act_p, b4, rsub, c4, cp0, g.ldc, nullptr, 0);
+                  else if (!pp0 && act == ACT_LRELU) epi_chunk_store<ACT_LRELU, false>(stg_s, epi.alpha, epi.act_p, b4, rsub, c4, cp0, g.ldc, nullptr, 0);
+                  else if (!pp0 && act == ACT_NONE) epi_chunk_store<ACT_NONE, false>(stg_s, epi.alpha, epi.act_p, b4, rsub, c4, cp0, g.ldc, nullptr, 0);
+                  else done = false;                      // rarer combinations: generic loop below
+                }
+              }
+              if (done) {
+              } else
               if (act == ACT_GELU) epi_rows<MODE, ACT_GELU>(stg_s, epi, b4, row0, rsub, c4, col, g.M, cp0, g.ldc);
               else if (act == ACT_LRELU) epi_rows<MODE, ACT_LRELU>(stg_s, epi, b4, row0, rsub, c4, col, g.M, cp0, g.ldc);
               else if (act == ACT_SIGMOID) epi_rows<MODE, ACT_SIGMOID>(stg_s, epi, b4, row0, rsub, c4, col, g.M, cp0, g.ldc);

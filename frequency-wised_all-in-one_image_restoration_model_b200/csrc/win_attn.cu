@@ -34,6 +34,23 @@ __device__ __forceinline__ void token_of(const WinGeom& g, int b, int wy, int wx
   label = g.shift > 0 ? ry * 3 + rx : 0;
 }
 
+// Dropout on the attention map (nn.Dropout after the band re-weighting, encoder_ViT.py:94): keep-mask from a stateless
+// hash of (seed, item, i, j) so that the backward kernel regenerates exactly the mask the forward applied.  The seed is
+// read from DEVICE memory (one int64 drawn by torch's generator per call), so a captured CUDA graph draws a new mask at
+// every replay.  Returns 0 or 1/keep.
+__device__ __forceinline__ float drop_scale(uint64_t seed, uint32_t item, uint32_t ij, float p, float inv_keep) {
+  uint64_t x = seed ^ (((uint64_t)item << 12) | ij) * 0x9E3779B97F4A7C15ull;       // splitmix64 finaliser
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27; x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  const float u = (float)(uint32_t)(x >> 40) * (1.0f / 16777216.0f);               // 24 uniform bits in [0, 1)
+  return u < p ? 0.f : inv_keep;
+}
+__device__ __forceinline__ void drop_map(float* P, uint64_t seed, uint32_t item, float p, int tid) {
+  const float inv_keep = 1.0f / (1.0f - p);
+  for (int e = tid; e < NTOK * NTOK; e += NTHR) P[(e >> 6) * fft64::PSTR + (e & 63)] *= drop_scale(seed, item, e, p, inv_keep);
+}
+
 template <int HD>
 struct Smem {
   static constexpr int HS = Pitch<HD>::HS;
@@ -76,7 +93,8 @@ __global__ void __launch_bounds__(NTHR) win_attn_fwd_kernel(const float* __restr
                                                             float* __restrict__ o, WinGeom g, float scale,
                                                             const float* __restrict__ table,
                                                             const float* __restrict__ coef, int coef_bstride,
-                                                            const uint8_t* __restrict__ band_of_bin, int nbands) {
+                                                            const uint8_t* __restrict__ band_of_bin, int nbands,
+                                                            float drop_p, const int64_t* __restrict__ drop_seed) {
   extern __shared__ __align__(16) unsigned char smraw[];
   Smem<HD>& s = *reinterpret_cast<Smem<HD>*>(smraw);
   const int tid = threadIdx.x;
@@ -105,6 +123,10 @@ __global__ void __launch_bounds__(NTHR) win_attn_fwd_kernel(const float* __restr
   softmax_rows(s.p, tid);
   __syncthreads();
   if (coef) fft64::filter_map(s.p, s.sp(), s.band, s.coef, 1.0f, tid);
+  if (drop_seed) {
+    drop_map(s.p, (uint64_t)__ldg(drop_seed), blockIdx.x, drop_p, tid);
+    __syncthreads();
+  }
   tile_pv<HD, false>(s.p, s.v, HSV, o, C, h * HD, s.row, 1.0f, tid);
 }
 
@@ -144,7 +166,8 @@ __global__ void __launch_bounds__(NTHR) win_attn_bwd_kernel(const float* __restr
                                                             const float* __restrict__ coef, int coef_bstride,
                                                             float* __restrict__ dcoef,
                                                             const uint8_t* __restrict__ band_of_bin, int nbands,
-                                                            int total_items) {
+                                                            int total_items, float drop_p,
+                                                            const int64_t* __restrict__ drop_seed) {
   extern __shared__ __align__(16) unsigned char smraw[];
   SmemB<HD>& s = *reinterpret_cast<SmemB<HD>*>(smraw);
   const int tid = threadIdx.x;
@@ -177,6 +200,7 @@ __global__ void __launch_bounds__(NTHR) win_attn_bwd_kernel(const float* __restr
     tile_abt<HD, false>(s.dO, HS, s.v, HS, s.x, 1.0f, nullptr, nullptr, tid);   // dP' = dO.V^T
     __syncthreads();
     softmax_rows(s.p, tid);                                             // P
+    if (drop_seed) drop_map(s.x, (uint64_t)__ldg(drop_seed), item, drop_p, tid);    // dropout backward: dP' o mask / keep
     __syncthreads();
     if (coef) {
       // F(dP') -> spB
@@ -226,6 +250,10 @@ __global__ void __launch_bounds__(NTHR) win_attn_bwd_kernel(const float* __restr
       __syncthreads();
       fft64::rows_inverse(s.spA(), s.x, 1.0f / 4096.0f, tid);             // x = P'
       __syncthreads();
+      if (drop_seed) {                                                  // the forward multiplied P' by the same mask
+        drop_map(s.x, (uint64_t)__ldg(drop_seed), item, drop_p, tid);
+        __syncthreads();
+      }
       tile_pv<HD, true>(s.x, s.dO, HS, dkv, 2 * C, C + h * HD, s.row, 1.0f, tid);   // dV = P'^T.dO
       {
         // dP = filter(dP'): gain on F(dP'), inverse columns
@@ -284,11 +312,12 @@ __global__ void __launch_bounds__(NTHR) win_attn_bwd_kernel(const float* __restr
 
 template <int HD>
 int launch_fwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, float* o, const WinGeom& g, float scale,
-               const float* table, const float* coef, int cbs, const uint8_t* bob, int nbands, cudaStream_t st) {
+               const float* table, const float* coef, int cbs, const uint8_t* bob, int nbands, float drop_p,
+               const int64_t* drop_seed, cudaStream_t st) {
   const size_t smem = sizeof(Smem<HD>);
   FA_CUDA(cudaFuncSetAttribute(win_attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int items = g.B * g.nWy * g.nWx * g.heads;
-  win_attn_fwd_kernel<HD><<<items, NTHR, smem, st>>>(q, ldq, kv, ldkv, o, g, scale, table, coef, cbs, bob, nbands);
+  win_attn_fwd_kernel<HD><<<items, NTHR, smem, st>>>(q, ldq, kv, ldkv, o, g, scale, table, coef, cbs, bob, nbands, drop_p, drop_seed);
   FA_LAUNCH_CHECK("fa_win_attn_fwd");
   return FA_OK;
 }
@@ -296,7 +325,7 @@ int launch_fwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, float
 template <int HD>
 int launch_bwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, const float* dout, float* dq, float* dkv,
                const WinGeom& g, float scale, const float* table, float* dtable, const float* coef, int cbs,
-               float* dcoef, const uint8_t* bob, int nbands, cudaStream_t st) {
+               float* dcoef, const uint8_t* bob, int nbands, float drop_p, const int64_t* drop_seed, cudaStream_t st) {
   const size_t smem = sizeof(SmemB<HD>);
   FA_CUDA(cudaFuncSetAttribute(win_attn_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int items = g.B * g.nWy * g.nWx * g.heads;
@@ -309,7 +338,7 @@ int launch_bwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, const
   if (grid < g.heads) grid = g.heads;
   if (grid > items) grid = items;          // items is a multiple of heads
   win_attn_bwd_kernel<HD><<<grid, NTHR, smem, st>>>(q, ldq, kv, ldkv, dout, dq, dkv, g, scale, table, dtable, coef, cbs,
-                                                   dcoef, bob, nbands, items);
+                                                   dcoef, bob, nbands, items, drop_p, drop_seed);
   FA_LAUNCH_CHECK("fa_win_attn_bwd");
   return FA_OK;
 }
@@ -334,33 +363,35 @@ extern "C" {
 
 int fa_win_attn_fwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, float* o, int B, int H, int W, int heads,
                     int hd, int shift, float scale, const float* table, const float* coef, int coef_bstride,
-                    const uint8_t* band_of_bin, int nbands, fa_stream_t stream) {
+                    const uint8_t* band_of_bin, int nbands, float drop_p, const int64_t* drop_seed, fa_stream_t stream) {
   FA_REQUIRE(q && kv && o, "fa_win_attn_fwd: null pointer");
+  FA_REQUIRE(!drop_seed || (drop_p > 0.f && drop_p < 1.f && coef), "fa_win_attn_fwd: dropout needs 0 < p < 1 and the coef path");
   FA_REQUIRE(((uintptr_t)q | (uintptr_t)kv | (uintptr_t)o) % 16 == 0, "fa_win_attn_fwd: pointers must be 16-byte aligned");
   WinGeom g;
   int rc = check_geom("fa_win_attn_fwd", B, H, W, heads, hd, shift, ldq, ldkv, coef, band_of_bin, nbands, g);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   FaProfScope prof(FA_K_WIN_ATTN, st);
-  if (hd == 56) return launch_fwd<56>(q, ldq, kv, ldkv, o, g, scale, table, coef, coef_bstride, band_of_bin, nbands, st);
-  if (hd == 28) return launch_fwd<28>(q, ldq, kv, ldkv, o, g, scale, table, coef, coef_bstride, band_of_bin, nbands, st);
-  return launch_fwd<64>(q, ldq, kv, ldkv, o, g, scale, table, coef, coef_bstride, band_of_bin, nbands, st);
+  if (hd == 56) return launch_fwd<56>(q, ldq, kv, ldkv, o, g, scale, table, coef, coef_bstride, band_of_bin, nbands, drop_p, drop_seed, st);
+  if (hd == 28) return launch_fwd<28>(q, ldq, kv, ldkv, o, g, scale, table, coef, coef_bstride, band_of_bin, nbands, drop_p, drop_seed, st);
+  return launch_fwd<64>(q, ldq, kv, ldkv, o, g, scale, table, coef, coef_bstride, band_of_bin, nbands, drop_p, drop_seed, st);
 }
 
 int fa_win_attn_bwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, const float* dout, float* dq, float* dkv,
                     int B, int H, int W, int heads, int hd, int shift, float scale, const float* table, float* dtable,
                     const float* coef, int coef_bstride, float* dcoef, const uint8_t* band_of_bin, int nbands,
-                    fa_stream_t stream) {
+                    float drop_p, const int64_t* drop_seed, fa_stream_t stream) {
   FA_REQUIRE(q && kv && dout && dq && dkv, "fa_win_attn_bwd: null pointer");
+  FA_REQUIRE(!drop_seed || (drop_p > 0.f && drop_p < 1.f && coef), "fa_win_attn_bwd: dropout needs 0 < p < 1 and the coef path");
   FA_REQUIRE(((uintptr_t)q | (uintptr_t)kv | (uintptr_t)dout) % 16 == 0, "fa_win_attn_bwd: pointers must be 16-byte aligned");
   WinGeom g;
   int rc = check_geom("fa_win_attn_bwd", B, H, W, heads, hd, shift, ldq, ldkv, coef, band_of_bin, nbands, g);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   FaProfScope prof(FA_K_WIN_ATTN, st);
-  if (hd == 56) return launch_bwd<56>(q, ldq, kv, ldkv, dout, dq, dkv, g, scale, table, dtable, coef, coef_bstride, dcoef, band_of_bin, nbands, st);
-  if (hd == 28) return launch_bwd<28>(q, ldq, kv, ldkv, dout, dq, dkv, g, scale, table, dtable, coef, coef_bstride, dcoef, band_of_bin, nbands, st);
-  return launch_bwd<64>(q, ldq, kv, ldkv, dout, dq, dkv, g, scale, table, dtable, coef, coef_bstride, dcoef, band_of_bin, nbands, st);
+  if (hd == 56) return launch_bwd<56>(q, ldq, kv, ldkv, dout, dq, dkv, g, scale, table, dtable, coef, coef_bstride, dcoef, band_of_bin, nbands, drop_p, drop_seed, st);
+  if (hd == 28) return launch_bwd<28>(q, ldq, kv, ldkv, dout, dq, dkv, g, scale, table, dtable, coef, coef_bstride, dcoef, band_of_bin, nbands, drop_p, drop_seed, st);
+  return launch_bwd<64>(q, ldq, kv, ldkv, dout, dq, dkv, g, scale, table, dtable, coef, coef_bstride, dcoef, band_of_bin, nbands, drop_p, drop_seed, st);
 }
 
 }  // extern "C"

@@ -5,8 +5,11 @@ Each attention layer is the K2 window-attention kernel run on the single 8x8 gri
 head_dim 64, no bias table, no shift) with the band re-weighting ``attn + sum_i lamb_i * band_i(attn)``
 (encoder_ViT.py:85-92) fused as one real filter in shared memory; ``lamb`` [nb, 1|B, heads] is the learned part.
 Linear / LayerNorm / FFN run on the GEMM + LN kernels with residual adds in the GEMM epilogue.
-Dropout (p=0.1, encoder_ViT.py:128-129) is an RNG-dependent elementwise mask kept on the host side of the ABI
-in train mode; parity and throughput runs use eval mode or p=0.
+Dropout (p=0.1, encoder_ViT.py:128-129) in train mode: the mask on the attention MAP (encoder_ViT.py:94) is applied
+inside the attention kernel (the map never leaves shared memory) from a stateless hash of a per-call seed that torch's
+generator draws on the device; the masks on token tensors (embedding, to_out, FeedForward) are torch dropouts on the
+host side of the ABI.  Same distribution as the reference, not the same stream (no CUDA kernel can replay torch's
+CPU / Philox stream), so parity runs use eval mode or p=0 and check the dropout path statistically.
 """
 import torch
 import torch.nn.functional as F
@@ -25,11 +28,12 @@ def pair(t):
 class _AttnCoreFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, coef, cfg):
-        B, heads, hd, bob, nb, bstride = cfg
+        B, heads, hd, bob, nb, bstride, drop_p, seed = cfg
         C = heads * hd
         q2 = qkv.reshape(-1, 3 * C)
         o = torch.empty(q2.shape[0], C, device=qkv.device, dtype=torch.float32)
-        ops.win_attn_fwd(q2[:, :C], q2[:, C:], o, B, 8, 8, heads, hd, 0, hd ** -0.5, None, coef, bstride, bob, nb)
+        ops.win_attn_fwd(q2[:, :C], q2[:, C:], o, B, 8, 8, heads, hd, 0, hd ** -0.5, None, coef, bstride, bob, nb,
+                         drop_p, seed)
         ctx.cfg = cfg
         ctx.save_for_backward(q2, coef)
         return o.view(B, 64, C)
@@ -37,14 +41,14 @@ class _AttnCoreFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, do):
         q2, coef = ctx.saved_tensors
-        B, heads, hd, bob, nb, bstride = ctx.cfg
+        B, heads, hd, bob, nb, bstride, drop_p, seed = ctx.cfg
         C = heads * hd
         T = q2.shape[0]
         dq = torch.empty(T, C, device=q2.device)
         dkv = torch.empty(T, 2 * C, device=q2.device)
         dcoef = torch.zeros_like(coef) if coef is not None else None
         ops.win_attn_bwd(q2[:, :C], q2[:, C:], do.reshape(T, C).contiguous(), dq, dkv, B, 8, 8, heads, hd, 0, hd ** -0.5,
-                         None, None, coef, bstride, dcoef, bob, nb)
+                         None, None, coef, bstride, dcoef, bob, nb, drop_p, seed)
         dqkv = torch.empty(T, 3 * C, device=q2.device)
         ops.copy2d(dq, dqkv[:, :C])
         ops.copy2d(dkv, dqkv[:, C:])
@@ -111,10 +115,21 @@ class Attention(nn.Module):
             bob, nb = self._bob, self.num_bands
             coef = self.lamb.permute(1, 2, 0).contiguous()             # [1|B, heads, nb]
             bstride = self.heads if coef.shape[0] > 1 else 0
+        drop_p, seed = 0.0, None
         if self.training and self.p > 0:
-            raise NotImplementedError('freqair: attention-map dropout (encoder_ViT.py:94) is not fused; run the ViT '
-                                      'encoder with dropout=0 or in eval mode')
-        o = _AttnCoreFn.apply(qkv, coef, (B, self.heads, self.dim_head, bob, nb, bstride))
+            # attention-map dropout (encoder_ViT.py:94) inside the kernel; it rides the filter stage, so without bands the
+            # map passes through the identity filter (one band, coefficient 0)
+            if coef is None:
+                if self._bob is None or self._bob.device != x.device:
+                    self._bob = torch.zeros(64, 33, dtype=torch.uint8, device=x.device)
+                bob, nb, bstride = self._bob, 1, 0
+                coef = torch.zeros(1, self.heads, 1, device=x.device)
+            drop_p = float(self.p)
+            seed = torch.randint(0, 1 << 62, (1,), device=x.device, dtype=torch.int64)
+        o = _AttnCoreFn.apply(qkv, coef, (B, self.heads, self.dim_head, bob, nb, bstride, drop_p, seed))
+        if drop_p > 0:                               # to_out's nn.Dropout sits between the projection and the residual add
+            y = F.dropout(linear(o, self.to_out[0].weight, self.to_out[0].bias), drop_p, True)
+            return y + residual if residual is not None else y
         return linear(o, self.to_out[0].weight, self.to_out[0].bias, residual=residual)
 
 

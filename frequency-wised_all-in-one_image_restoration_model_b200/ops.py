@@ -179,16 +179,19 @@ def dc_split(x):
 
 
 # ----------------------------------------------------------------------------- attention (K2)
-def win_attn_fwd(q, kv, o, B, H, W, heads, hd, shift, scale, table, coef, coef_bstride, band_of_bin, nbands):
+def win_attn_fwd(q, kv, o, B, H, W, heads, hd, shift, scale, table, coef, coef_bstride, band_of_bin, nbands, drop_p=0.0,
+                 drop_seed=None):
+    """drop_seed: int64 CUDA tensor [1] (attention-map dropout with probability drop_p, mask = hash of the seed)."""
     _call('fa_win_attn_fwd', _p(q), q.stride(0), _p(kv), kv.stride(0), _p(o), B, H, W, heads, hd, shift, scale,
-          _p(table), _p(coef), coef_bstride, _p(band_of_bin), nbands, _stream())
+          _p(table), _p(coef), coef_bstride, _p(band_of_bin), nbands, drop_p, _p(drop_seed), _stream())
 
 
 def win_attn_bwd(q, kv, dout, dq, dkv, B, H, W, heads, hd, shift, scale, table, dtable, coef, coef_bstride, dcoef,
-                 band_of_bin, nbands):
+                 band_of_bin, nbands, drop_p=0.0, drop_seed=None):
     _f32(dout, dq, dkv)
     _call('fa_win_attn_bwd', _p(q), q.stride(0), _p(kv), kv.stride(0), _p(dout), _p(dq), _p(dkv), B, H, W, heads, hd,
-          shift, scale, _p(table), _p(dtable), _p(coef), coef_bstride, _p(dcoef), _p(band_of_bin), nbands, _stream())
+          shift, scale, _p(table), _p(dtable), _p(coef), coef_bstride, _p(dcoef), _p(band_of_bin), nbands, drop_p,
+          _p(drop_seed), _stream())
 
 
 def joint_attn_fwd(q, kv, o, L, B, H, W, heads, hd, shift, scale, tables, kind):

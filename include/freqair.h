@@ -25,7 +25,7 @@ extern "C" {
 typedef void* fa_stream_t; /* cudaStream_t */
 
 /* ------------------------------------------------------------------ library */
-#define FREQAIR_ABI_VERSION 2      /* bumped whenever a prototype or struct in this header changes */
+#define FREQAIR_ABI_VERSION 3      /* bumped whenever a prototype or struct in this header changes */
 const char* fa_version(void);
 int fa_abi_version(void);          /* the FREQAIR_ABI_VERSION the library was compiled against (checked at load time) */
 const char* fa_last_error_string(void);
@@ -117,14 +117,17 @@ int fa_dc_split(const float* x, float* y, int64_t nmaps, int n, fa_stream_t stre
  * hd in {28, 56, 64}; table [225][heads] or NULL; coef [B][heads][nbands] or NULL.
  * ref: WindowAttention.forward decoder_Uformer.py:235-299, encoder_Uformer.py:152-183 ('origin' MSA),
  *      Attention.forward encoder_ViT.py:76-98 (H=W=8, table=NULL, shift=0, coef [B or 1][heads][nb]).
- * bwd recomputes P; dtable / dcoef are ACCUMULATED (caller zero-fills). coef_bstride = 0 shares coef over b. */
+ * bwd recomputes P; dtable / dcoef are ACCUMULATED (caller zero-fills). coef_bstride = 0 shares coef over b.
+ * drop_seed != NULL (a DEVICE pointer to one int64): nn.Dropout(drop_p) on P' before P'.v (encoder_ViT.py:94, train
+ * mode): element (item, i, j) is kept with probability 1 - drop_p and scaled by 1 / (1 - drop_p), the mask being a
+ * stateless hash of (*drop_seed, item, i, j) that the backward regenerates from the same seed.  Needs coef != NULL. */
 int fa_win_attn_fwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, float* o, int B, int H, int W, int heads,
                     int hd, int shift, float scale, const float* table, const float* coef, int coef_bstride,
-                    const uint8_t* band_of_bin, int nbands, fa_stream_t stream);
+                    const uint8_t* band_of_bin, int nbands, float drop_p, const int64_t* drop_seed, fa_stream_t stream);
 int fa_win_attn_bwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, const float* dout, float* dq, float* dkv,
                     int B, int H, int W, int heads, int hd, int shift, float scale, const float* table, float* dtable,
                     const float* coef, int coef_bstride, float* dcoef, const uint8_t* band_of_bin, int nbands,
-                    fa_stream_t stream);
+                    float drop_p, const int64_t* drop_seed, fa_stream_t stream);
 /* joint attention over the L band copies of a window (192 tokens for L=3), images ordered (l, b):
  * S = scale*q.k^T + tables[l1*L+l2][rel_index] + (0/-100 intra|inter band mask) + shift mask; softmax; .v
  * ref: FrequencyWindowAttention.forward encoder_Uformer.py:256-310; kind 0 = intra, 1 = inter. hd = 28. */

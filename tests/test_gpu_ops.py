@@ -319,7 +319,7 @@ def test_dc_split(ops):
 
 
 # ----------------------------------------------------------------------------- K2 attention
-def ref_win_attn(q, kv, B, H, W, heads, hd, shift, scale, table, coef, nW_img):
+def ref_win_attn(q, kv, B, H, W, heads, hd, shift, scale, table, coef, nW_img, drop=None):
     C = heads * hd
 
     def win(t):
@@ -341,6 +341,8 @@ def ref_win_attn(q, kv, B, H, W, heads, hd, shift, scale, table, coef, nW_img):
     if coef is not None:
         cf = coef.permute(2, 0, 1).repeat_interleave(nW_img, 1)
         attn = freq.band_filter(attn, 'frequency_decompose_1', 0.5, cf)
+    if drop is not None:                     # [windows, heads, 64, 64] of 0 or 1/keep
+        attn = attn * drop
     o = (attn @ vh).transpose(1, 2).reshape(-1, 8, 8, C)
     o = uformer.reverse(o, H, W)
     if shift:
@@ -383,6 +385,62 @@ def test_win_attn(ops, H, heads, hd, shift, use_coef):
         close(dtab, tb.grad, 2e-4, 'win_attn dtable')
     if coef is not None:
         close(dcf[..., 1:], cf.grad[..., 1:], 5e-4, 'win_attn dcoef')
+
+
+def drop_mask_host(seed, n_items, p):
+    """The kernel's attention-dropout mask (win_attn.cu drop_scale: splitmix64 of seed ^ ((item << 12 | ij) * golden))."""
+    import numpy as np
+    with np.errstate(over='ignore'):
+        idx = (np.arange(n_items, dtype=np.uint64)[:, None] << np.uint64(12)) | np.arange(4096, dtype=np.uint64)[None, :]
+        x = np.uint64(seed) ^ (idx * np.uint64(0x9E3779B97F4A7C15))
+        x ^= x >> np.uint64(30); x *= np.uint64(0xBF58476D1CE4E5B9)
+        x ^= x >> np.uint64(27); x *= np.uint64(0x94D049BB133111EB)
+        x ^= x >> np.uint64(31)
+    u = (x >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    keep = torch.from_numpy((u >= np.float32(p)).astype(np.float32))
+    return keep / (1.0 - p)
+
+
+@pytest.mark.parametrize('H,heads,hd,shift', [(8, 12, 64, 0), (16, 2, 56, 4)])
+def test_win_attn_dropout(ops, H, heads, hd, shift):
+    """nn.Dropout on the attention map (encoder_ViT.py:94) inside the kernel: the mask is a stateless hash of a device
+    seed, so the test rebuilds it on the host and checks forward and backward against the dense oracle with the SAME mask;
+    keep-rate within sampling error of 1 - p."""
+    B, W, C, nb, p = 2, H, heads * hd, 3, 0.1
+    nW = (H // 8) * (W // 8)
+    T = B * H * W
+    qkv = gen(T, 3 * C, scale=0.5)
+    table = gen(225, heads, seed=1, scale=0.3) if hd != 64 else None
+    coef = torch.cat([torch.zeros(B, heads, 1), gen(B, heads, nb - 1, seed=2) * 0.5], -1)
+    dO = gen(T, C, seed=3)
+    scale = hd ** -0.5
+    seed = 0x1234567890ABCDE
+    mask = drop_mask_host(seed, B * nW * heads, p).view(B * nW, heads, 64, 64)
+    assert abs((mask > 0).float().mean().item() - (1 - p)) < 0.01
+    leaf = qkv.clone().requires_grad_(True)
+    tb = table.clone().requires_grad_(True) if table is not None else None
+    cf = coef.clone().requires_grad_(True)
+    ref = ref_win_attn(leaf[:, :C], leaf[:, C:], B, H, W, heads, hd, shift, scale, tb, cf, nW, drop=mask)
+    ref.backward(dO)
+    qkvd = dev(qkv)
+    bob = dev(_bob('frequency_decompose_1', 0.5, 64))
+    sd = torch.tensor([seed], dtype=torch.int64, device='cuda')
+    o = torch.empty(T, C, device='cuda')
+    args = (B, H, W, heads, hd, shift, scale)
+    tbd = dev(table) if table is not None else None
+    ops.win_attn_fwd(qkvd[:, :C], qkvd[:, C:], o, *args, tbd, dev(coef), heads, bob, nb, p, sd)
+    close(o, ref, 5e-5, 'win_attn dropout fwd')
+    dq = torch.empty(T, C, device='cuda'); dkv = torch.empty(T, 2 * C, device='cuda')
+    dtab = torch.zeros(225, heads, device='cuda') if table is not None else None
+    dcf = torch.zeros(B, heads, nb, device='cuda')
+    ops.win_attn_bwd(qkvd[:, :C], qkvd[:, C:], dev(dO), dq, dkv, *args, tbd, dtab, dev(coef), heads, dcf, bob, nb, p, sd)
+    g = leaf.grad
+    close(dq, g[:, :C], 2e-4, 'win_attn dropout dq'); close(dkv, g[:, C:], 2e-4, 'win_attn dropout dkv')
+    close(dcf[..., 1:], cf.grad[..., 1:], 5e-4, 'win_attn dropout dcoef')
+    # another seed gives another mask
+    o2 = torch.empty_like(o)
+    ops.win_attn_fwd(qkvd[:, :C], qkvd[:, C:], o2, *args, tbd, dev(coef), heads, bob, nb, p, sd + 1)
+    assert (o2 - o).abs().max().item() > 1e-3
 
 
 @pytest.mark.parametrize('H,heads,shift,kind,L', [(16, 2, 0, 'intra', 3), (16, 1, 4, 'inter', 3), (8, 2, 0, 'inter', 2)])

@@ -31,16 +31,29 @@ def spec_of(module):
     return {k: [list(v.shape), str(v.dtype).replace('torch.', '')] for k, v in module.state_dict().items()}
 
 
-def grad_digest(named_params, every=53):
-    """Per selected parameter: full grad if small, else head slice + sums."""
+def strided_sample(t, n):
+    """Up to n elements of t.flatten() at a fixed stride (a pure function of numel and n: tests recompute the indices)."""
+    f = t.flatten()
+    step = max(1, -(-f.numel() // n))
+    return f[::step]
+
+
+def grad_digest(named_params, every=53, n_all=256, n_big=4096):
+    """For EVERY parameter with a gradient: gstat = [sum, abs-sum, l2 norm, max-abs] and gsamp = a strided sample of up to
+    ``n_all`` elements (``n_big`` for every ``every``-th parameter, the relative-position tables and the lambda MLPs), so
+    the GPU test can bound the max-abs gradient error per parameter over the whole model.  grad_head / grad_sum are the
+    round-1 keys (first 256 entries of every ``every``-th parameter), kept for the CPU oracle test."""
     out = {}
+    byname = dict(named_params)
     names = sorted(n for n, p in named_params if p.grad is not None)
     for j, n in enumerate(names):
-        if j % every and 'relative_position_bias_table' not in n and '.mlp.1.0.' not in n:
-            continue
-        g = dict(named_params)[n].grad.detach().float().flatten()
-        out['grad_sum/' + n] = np.array([g.sum().item(), g.abs().sum().item()], np.float64)
-        out['grad_head/' + n] = g[:256].numpy().copy()
+        g = byname[n].grad.detach().float().flatten()
+        big = not (j % every and 'relative_position_bias_table' not in n and '.mlp.1.0.' not in n)
+        out['gstat/' + n] = np.array([g.sum().item(), g.abs().sum().item(), g.norm().item(), g.abs().max().item()], np.float64)
+        out['gsamp/' + n] = strided_sample(g, n_big if big else n_all).numpy().copy()
+        if big:
+            out['grad_sum/' + n] = np.array([g.sum().item(), g.abs().sum().item()], np.float64)
+            out['grad_head/' + n] = g[:256].numpy().copy()
     return out
 
 
