@@ -98,7 +98,7 @@ int fa_gemm(const float* A, const float* B, float* C, int M, int N, int K, int64
     const int passes = backend == 3 ? 0 : (backend == 4 ? 2 : (backend == 5 ? 1 : 3));
     int rc = fa_gemm_tc_launch(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, epi, st, passes);
     if (rc != FA_ERR_UNSUPPORTED) return rc;
-    if (backend >= 2) {
+    if (backend == 2 || backend == 3) {
       fa_set_error("fa_gemm: shape M=%d N=%d K=%d tA=%d tB=%d not eligible for the tcgen05 path", M, N, K, transA, transB);
       return FA_ERR_UNSUPPORTED;
     }

@@ -313,7 +313,35 @@ int fa_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float 
   return FA_OK;
 }
 
+// dst = x rounded to the nearest TF32 (ties away), low 13 mantissa bits cleared: exactly what a 1xTF32 / 2xTF32 contraction
+// wants as its weight operand (FaGemmEpilogue::b_is_tf32)
+__device__ __forceinline__ float round_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+__global__ void __launch_bounds__(256) round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n,
+                                                         int vec) {
+  if (vec) {
+    const int64_t n4 = n >> 2;
+    FA_GRID_STRIDE(i, n4) {
+      const float4 v = reinterpret_cast<const float4*>(src)[i];
+      reinterpret_cast<float4*>(dst)[i] = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+    }
+    FA_GRID_STRIDE(j, n - (n4 << 2)) dst[(n4 << 2) + j] = round_tf32(src[(n4 << 2) + j]);
+  } else {
+    FA_GRID_STRIDE(i, n) dst[i] = round_tf32(src[i]);
+  }
+}
+
 __global__ void adam_tick_kernel(float* state) { reinterpret_cast<int*>(state)[1] += 1; }
+
+int fa_round_tf32(const float* src, float* dst, int64_t n, fa_stream_t stream) {
+  FA_REQUIRE(src && dst && n >= 0, "fa_round_tf32: bad argument");
+  if (n == 0) return FA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_ELEMWISE, st);
+  const bool al = (((uintptr_t)src | (uintptr_t)dst) % 16) == 0;
+  round_tf32_kernel<<<ew_grid(n / 4 + 1), 256, 0, st>>>(src, dst, n, al ? 1 : 0);
+  FA_LAUNCH_CHECK("fa_round_tf32");
+  return FA_OK;
+}
 
 int fa_adam_tick(float* state, fa_stream_t stream) {
   FA_REQUIRE(state, "fa_adam_tick: null state");

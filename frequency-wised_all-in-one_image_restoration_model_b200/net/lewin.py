@@ -102,53 +102,78 @@ def _fold(g, dp, rps):
     return ops.scale_rows(g, dp, rps), None
 
 
-def linear_param_grads(g, x, W, b, want_dx=True, dx=None, accumulate_dx=False, dp=None, rps=1):
+def linear_param_grads(g, x, W, b, want_dx=True, dx=None, accumulate_dx=False, dp=None, rps=1, backend=None):
     """linear_grads with the parameter gradients routed through the sinks: returns (dx, dW_ret, db_ret).
-    dp / rps: per-sample scale of g (DropPath backward) folded into both contractions."""
+    dp / rps: per-sample scale of g (DropPath backward) folded into both contractions.
+    backend: fa_gemm backend of both contractions (the LeFF class passes ops.LEFF_BACKEND)."""
     dW, dW_ret = _wbuf(W)
     db, db_ret = _wbuf(b) if b is not None else (None, None)
     # dW += g^T x, and the bias gradient (column sums of g) taken from the same pass over g (FaGemmEpilogue.a_rowsum)
-    ops.gemm(g, x, dW, transA=True, transB=False, accumulate=True, a_rowsum=db, a_kscale=dp, a_k_rows_per_scale=rps)
+    ops.gemm(g, x, dW, transA=True, transB=False, accumulate=True, a_rowsum=db, a_kscale=dp, a_k_rows_per_scale=rps,
+             backend=backend)
     _ready(W, b)
     if not want_dx:
         return None, dW_ret, db_ret
     if dx is None:
         dx = torch.empty_like(x)
-    ops.gemm(g, W, dx, transB=False, accumulate=accumulate_dx, rowscale=dp, rows_per_scale=rps)
+    Wr, bx = rn_weight(W, backend)
+    ops.gemm(g, Wr, dx, transB=False, accumulate=accumulate_dx, rowscale=dp, rows_per_scale=rps, backend=backend, b_is_tf32=bx)
     return dx, dW_ret, db_ret
 
 
 # ----------------------------------------------------------------------------- LeFF
-def leff_fwd(xn2, w1, b1, wdw, bdw, w2, b2, B, H, W, residual, dp_scale, save):
+# Rounded weight copies.  The LeFF contractions run 1xTF32 (ops.LEFF_BACKEND) and want their weight operand already
+# rounded to TF32 (the kernel then skips its in-place rounding pass over the B tile).  trainer.TrainStep keeps ONE rounded
+# copy of each flat parameter buffer, refreshed at the start of every step, and marks the parameters with views of it
+# (``p._fa_rn``); the views are only trusted while that TrainStep's step is running (RN_OWNER), because nothing else
+# (load_state_dict, an external optimiser) keeps them in sync.  Anywhere else the copy is made on the fly.
+RN_OWNER = [None]
+
+
+def rn_weight(W, backend=None):
+    """(weight operand for a contraction on fa_gemm backend `backend`, b_is_tf32)"""
+    if backend not in (ops.GEMM_1X, ops.GEMM_2X):
+        return W, False
+    r = getattr(W, '_fa_rn', None)
+    if r is not None and RN_OWNER[0] is not None and getattr(W, '_fa_rn_owner', None) == RN_OWNER[0]:
+        return r, True
+    return ops.round_tf32(W.detach().contiguous()), True
+
+
+def leff_fwd(xn2, w1, b1, wdw, bdw, w2, b2, B, H, W, residual, dp_scale, save, be=0):
     T, C = xn2.shape
     Ch = w1.shape[0]
     h1 = torch.empty(T, Ch, device=xn2.device, dtype=torch.float32)
     u1 = torch.empty_like(h1) if save is not None else None          # pre-activation: only the backward reads it
-    ops.gemm(xn2, w1, h1, bias=b1, act=ops.ACT_GELU, preact=u1)
+    w1r, x1 = rn_weight(w1, be)
+    w2r, x2 = rn_weight(w2, be)
+    ops.gemm(xn2, w1r, h1, bias=b1, act=ops.ACT_GELU, preact=u1, backend=be, b_is_tf32=x1)
     # saved for the backward: gelu'(u2), not u2 - it only ever multiplies dh2 (leff_bwd); nothing in inference
     u2, h2 = ops.dwconv_fwd(h1, wdw, bdw, B, H, W, Ch, u2_mode=1 if save is not None else None)
     out = torch.empty(T, w2.shape[0], device=xn2.device, dtype=torch.float32)
-    ops.gemm(h2, w2, out, bias=b2, rowscale=dp_scale, rows_per_scale=H * W, residual=residual)
+    ops.gemm(h2, w2r, out, bias=b2, rowscale=dp_scale, rows_per_scale=H * W, residual=residual, backend=be, b_is_tf32=x2)
     if save is not None:
         save.update(u1=u1, u2=u2, h2=h2)          # h1 = gelu(u1) is recomputed by the depthwise-conv backward
     return out
 
 
-def leff_bwd(gs, sv, xn2, w1, b1, wdw, bdw, w2, b2, B, H, W, dp=None):
+def leff_bwd(gs, sv, xn2, w1, b1, wdw, bdw, w2, b2, B, H, W, dp=None, be=0):
     """gs: gradient wrt the LeFF output; dp: its per-sample DropPath scale when it is folded into the two contractions
     that consume gs (None: already applied). Returns dxn2 and the parameter gradients (None where they were
     accumulated straight into the parameters' .grad buffers)."""
     dW2, dW2r = _wbuf(w2)
     db2b, db2 = _wbuf(b2)
     ops.gemm(gs, sv['h2'], dW2, transA=True, transB=False, accumulate=True, a_rowsum=db2b, a_kscale=dp,
-             a_k_rows_per_scale=H * W)
+             a_k_rows_per_scale=H * W, backend=be)
     du2 = torch.empty_like(sv['u2'])
-    ops.gemm(gs, w2, du2, transB=False, aux=sv['u2'], aux_act=ops.ACT_MUL, rowscale=dp, rows_per_scale=H * W)   # u2 = gelu'
+    w2r, x2 = rn_weight(w2, be)
+    ops.gemm(gs, w2r, du2, transB=False, aux=sv['u2'], aux_act=ops.ACT_MUL, rowscale=dp, rows_per_scale=H * W,
+             backend=be, b_is_tf32=x2)                                                                          # u2 = gelu'
     dwdw, dwdwr = _wbuf(wdw)
     dbdw, dbdwr = _wbuf(bdw)
     du1 = ops.dwconv_bwd(du2, None, sv['u1'], wdw, dwdw, dbdw, B, H, W, wdw.shape[0])      # h1 = gelu(u1) recomputed
     _ready(w2, b2, wdw, bdw)
-    dxn2, dW1r, db1r = linear_param_grads(du1, xn2, w1, b1)
+    dxn2, dW1r, db1r = linear_param_grads(du1, xn2, w1, b1, backend=be)
     return dxn2, (dW1r, db1r, dwdwr, dbdwr, dW2r, db2)
 
 
@@ -177,7 +202,7 @@ class DecoderBlockFn(torch.autograd.Function):
         xn2, mean2, rstd2 = ops.layernorm_fwd(x1, n2w, n2b)
         need_bwd = any(ctx.needs_input_grad)
         sv = {} if need_bwd else None                 # inference: the LeFF intermediates u1, u2 are never stored
-        x2 = leff_fwd(xn2, w1, b1, wdw, bdw, w2, b2, B, H, W, x1, dp_m, sv)
+        x2 = leff_fwd(xn2, w1, b1, wdw, bdw, w2, b2, B, H, W, x1, dp_m, sv, ops.LEFF_BACKEND)
         if not need_bwd:
             return x2.view(B, H * W, C)
         ctx.cfg = cfg
@@ -199,7 +224,7 @@ class DecoderBlockFn(torch.autograd.Function):
         g = dx2.reshape(T, C).contiguous()
         gs, dpf = _fold(g, dp_m, H * W)
         dxn2, (dW1, db1, dwdw, dbdw, dW2, db2) = leff_bwd(gs, dict(u1=u1, u2=u2, h2=h2), xn2, P_w1, P_b1, P_wdw,
-                                                         P_bdw, P_w2, P_b2, B, H, W, dp=dpf)
+                                                         P_bdw, P_w2, P_b2, B, H, W, dp=dpf, be=ops.LEFF_BACKEND)
         dn2w, dn2wr = _wbuf(P_n2w)
         dn2b, dn2br = _wbuf(P_n2b)
         g1 = ops.layernorm_bwd(dxn2, x1, mean2, rstd2, n2w, g, dn2w, dn2b)
@@ -265,7 +290,7 @@ class EncoderBlockFn(torch.autograd.Function):
         xn2, mean2, rstd2 = ops.layernorm_fwd(x1, n2w, n2b)
         need_bwd = any(ctx.needs_input_grad)
         sv = {} if need_bwd else None
-        x2 = leff_fwd(xn2, w1, b1, wdw, bdw, w2, b2, LB, H, W, x1, dp_m, sv)
+        x2 = leff_fwd(xn2, w1, b1, wdw, bdw, w2, b2, LB, H, W, x1, dp_m, sv, ops.LEFF_ENC_BACKEND)
         if not need_bwd:
             return x2.view(LB, H * W, C)
         ctx.cfg = cfg
@@ -291,7 +316,7 @@ class EncoderBlockFn(torch.autograd.Function):
         g = dx2.reshape(T, C).contiguous()
         gs, dpf = _fold(g, dp_m, H * W)
         dxn2, (dW1, db1, dwdw, dbdw, dW2, db2) = leff_bwd(gs, dict(u1=u1, u2=u2, h2=h2), xn2, P_w1, P_b1, P_wdw,
-                                                         P_bdw, P_w2, P_b2, LB, H, W, dp=dpf)
+                                                         P_bdw, P_w2, P_b2, LB, H, W, dp=dpf, be=ops.LEFF_ENC_BACKEND)
         dn2w, dn2wr = _wbuf(P_n2w)
         dn2b, dn2br = _wbuf(P_n2b)
         g1 = ops.layernorm_bwd(dxn2, x1, mean2, rstd2, n2w, g, dn2w, dn2b)

@@ -47,6 +47,7 @@ class MoCo(nn.Module):
             self.queue[i] = nn.functional.normalize(self.queue[i], dim=0)
         self.register_buffer('queue_ptr', torch.zeros(1, dtype=torch.long))
         self._flat_q = self._flat_k = None
+        self._flat_k_rn = None          # TF32-rounded copy of the key encoder's weights (see rounded_key_weights)
         # the key encoder (no gradient) is independent of the query encoder: run it on a side stream so that its
         # latency-bound kernels (small grids at the 16x16 / 8x8 levels) fill the gaps of the query branch
         self.key_stream = None
@@ -61,10 +62,24 @@ class MoCo(nn.Module):
             self._flat_k = flatten_parameters(list(self.encoder_k.parameters()))
         return self._flat_q, self._flat_k
 
+    def rounded_key_weights(self, owner):
+        """Keep a TF32-rounded copy of the key encoder's flat buffer, refreshed right after every momentum update, and
+        mark the key parameters with views of it (net/lewin.rn_weight): the 1xTF32 LeFF contractions of the key branch
+        then read pre-rounded weights like those of the query branch and the restorer (trainer.TrainStep)."""
+        _, fk = self._ensure_flat()
+        self._flat_k_rn = torch.empty_like(fk)
+        off = 0
+        for p in self.encoder_k.parameters():
+            p._fa_rn = self._flat_k_rn[off:off + p.numel()].view(p.shape)
+            p._fa_rn_owner = owner
+            off += (p.numel() + 3) // 4 * 4
+
     @torch.no_grad()
     def _momentum_update_key_encoder(self):
         fq, fk = self._ensure_flat()
         ops.momentum_update(fk, fq, self.m)
+        if self._flat_k_rn is not None and self._flat_k_rn.numel() == fk.numel():
+            ops.round_tf32(fk, self._flat_k_rn)
 
     @torch.no_grad()
     def _dequeue_and_enqueue(self, keys):

@@ -19,6 +19,15 @@ FLOP_COUNTER = [None]          # bench.py roofline leg: set to 0 to accumulate 2
 # FREQAIR_GEMM_BACKEND=1 forces the fp32 SIMT kernel everywhere (A/B accuracy and speed comparisons).
 DEFAULT_GEMM_BACKEND = int(os.environ.get('FREQAIR_GEMM_BACKEND', '0'))
 GEMM_3X, GEMM_SIMT, GEMM_2X, GEMM_1X = 0, 1, 4, 5     # fa_gemm backend ids (include/freqair.h)
+# Contractions of the restorer's LeFF class (linear1, linear2 and their backward contractions: 62 % of the decoder's
+# flops) run 1xTF32 with both operands rounded to nearest: measured on the golden train step (tools/precision_probe.py
+# on the CPU, tests/test_gpu_golden.py on the GPU; table in DESIGN.md section 3) this moves the restored image by <= 5e-4
+# and no gradient by more than 1.5e-4 - inside the 1e-3 bar.  Every other layer class (attention projections,
+# convolutions, encoder heads) exceeds or touches the bar under TF32 rounding and stays on the error-compensated 3xTF32
+# path, and so does the ENCODER's LeFF: its bottleneck tokens (`inter`) moved by 1.14e-3 under 1xTF32.
+# FREQAIR_LEFF_BACKEND / FREQAIR_LEFF_ENC_BACKEND select the fa_gemm backend of the two (0 = 3xTF32, 4 = 2x, 5 = 1x).
+LEFF_BACKEND = int(os.environ.get('FREQAIR_LEFF_BACKEND', str(GEMM_1X)))
+LEFF_ENC_BACKEND = int(os.environ.get('FREQAIR_LEFF_ENC_BACKEND', str(GEMM_3X)))
 K_GEMM, K_WIN_ATTN, K_JOINT_ATTN, K_BAND, K_LN, K_DWCONV, K_IM2COL, K_BN, K_OPTIM, K_DCN, K_ELEM = range(1, 12)
 
 
@@ -485,6 +494,14 @@ def adam_step_state(p, g, m, v, state, beta1, beta2, eps, grad_scale=1.0):
     inside the kernel, so a captured graph of the step never reads host memory."""
     _f32(p, g, m, v, state)
     _call('fa_adam_step_state', _p(p), _p(g), _p(m), _p(v), p.numel(), _p(state), beta1, beta2, eps, grad_scale, _stream())
+
+
+def round_tf32(src, dst=None):
+    """src rounded to the nearest TF32 (a new tensor unless dst is given)."""
+    _f32(src)
+    dst = torch.empty_like(src) if dst is None else dst
+    _call('fa_round_tf32', _p(src), _p(dst), src.numel(), _stream())
+    return dst
 
 
 def _ptr_array(tensors):

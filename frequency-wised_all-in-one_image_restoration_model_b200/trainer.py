@@ -45,8 +45,15 @@ class Segment:
         self.grad = torch.zeros_like(flat)
         self.m = torch.zeros_like(flat)
         self.v = torch.zeros_like(flat)
+        self.flat_rn = None             # TF32-rounded copy of `flat` (TrainStep: weight operand of the 1xTF32 contractions)
         for p, o in zip(self.params, offs):
             p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+    def make_rounded_copy(self, owner):
+        self.flat_rn = torch.empty_like(self.flat)
+        for p, o in zip(self.params, self.offs):
+            p._fa_rn = self.flat_rn[o:o + p.numel()].view(p.shape)
+            p._fa_rn_owner = owner
 
 
 class BucketedAllReduce:
@@ -183,6 +190,11 @@ class TrainStep:
             for p in seg.params:
                 p._fa_direct = True
                 p._fa_ready = ready
+        # one TF32-rounded copy of each flat parameter buffer, refreshed at the start of every step (net/lewin.rn_weight)
+        if self.segments[0].flat.is_cuda and any(b in (ops.GEMM_1X, ops.GEMM_2X) for b in (ops.LEFF_BACKEND, ops.LEFF_ENC_BACKEND)):
+            for seg in self.segments:
+                seg.make_rounded_copy(id(self))
+            moco.rounded_key_weights(id(self))
         self.last = {}
         # CUDA-graph state (capture()): static inputs / loss
         self.graph = None
@@ -237,7 +249,18 @@ class TrainStep:
         return self.segments[:1] if self.encoder_only else self.segments
 
     def _body(self, x_query, x_key, clean):
+        from .net import lewin
+        lewin.RN_OWNER[0] = id(self)
+        try:
+            return self._body_inner(x_query, x_key, clean)
+        finally:
+            lewin.RN_OWNER[0] = None
+
+    def _body_inner(self, x_query, x_key, clean):
         self.zero_grad()
+        for s in self._active():
+            if s.flat_rn is not None:
+                ops.round_tf32(s.flat, s.flat_rn)
         if self.encoder_only:                                                        # train.py:84-87
             _, logits, labels, _ = self.net.E(x_query, x_key)
             n = len(logits)

@@ -25,7 +25,7 @@ extern "C" {
 typedef void* fa_stream_t; /* cudaStream_t */
 
 /* ------------------------------------------------------------------ library */
-#define FREQAIR_ABI_VERSION 3      /* bumped whenever a prototype or struct in this header changes */
+#define FREQAIR_ABI_VERSION 4      /* bumped whenever a prototype or struct in this header changes */
 const char* fa_version(void);
 int fa_abi_version(void);          /* the FREQAIR_ABI_VERSION the library was compiled against (checked at load time) */
 const char* fa_last_error_string(void);
@@ -273,6 +273,10 @@ int fa_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float 
 int fa_adam_tick(float* state, fa_stream_t stream);
 int fa_adam_step_state(float* p, const float* g, float* m, float* v, int64_t n, const float* state, float beta1,
                        float beta2, float eps, float grad_scale, fa_stream_t stream);
+/* dst[i] = src[i] rounded to the nearest TF32 (ties away from zero; low 13 mantissa bits zero): the pre-rounded weight
+ * operand of the 1xTF32 / 2xTF32 contractions (FaGemmEpilogue.b_is_tf32); the train step refreshes one rounded copy of
+ * each flat parameter buffer per step */
+int fa_round_tf32(const float* src, float* dst, int64_t n, fa_stream_t stream);
 
 #ifdef __cplusplus
 }
