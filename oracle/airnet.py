@@ -204,3 +204,29 @@ def airnet_uformer_forward(sd, xq, xk, training, method='all_3_bands', L=3, msa=
     logits = moco_logits(q, k, sd['E.E.queue'])
     restored = U.decoder_forward(sd, 'R.R.', xq, inter, method, dp)
     return restored, logits, k
+
+
+def airnet_dgrn_forward(sd, xq, xk, training, encoder='ResNet', encoder_dim=256, decompose_type='none', bn_stats=None,
+                        param_names=None):
+    """AirNet.forward for the ResNet or ViT encoder + DGRN (net/model.py:59-71 over moco.py:115-170).
+
+    The reference's MoCo loops ``range(opt.L)`` over the 1-element ``[out]`` these encoders return and dies with
+    IndexError (moco.py:127-128 vs encoder_ResNet.py:47, encoder_ViT.py:203); the one deviation, shared by the product
+    and by the golden generator (tools/make_golden_dgrn.py), is ``num_losses = len(out)``.  Dropout is off (p = 0).
+    training: returns (restored, logits, k_out) after the in-place momentum update of the ``E.E.encoder_k.*`` entries.
+    """
+    q_pre, k_pre = 'E.E.encoder_q.', 'E.E.encoder_k.'
+
+    def enc(p, x, train):
+        if encoder == 'ResNet':
+            return resnet_encoder_forward(sd, p, x, train, bn_stats)
+        return vit_encoder_forward(sd, p, x, encoder_dim, decompose_type=decompose_type, training=train, bn_stats=bn_stats)
+    _, q, inter = enc(q_pre, xq, training)
+    if not training:
+        return dgrn_forward(sd, 'R.R.', xq, inter)
+    with torch.no_grad():
+        momentum_update(sd, q_pre, k_pre, param_names)
+        _, k, _ = enc(k_pre, xk, True)
+    logits = moco_logits(q, k, sd['E.E.queue'])
+    restored = dgrn_forward(sd, 'R.R.', xq, inter)
+    return restored, logits, k

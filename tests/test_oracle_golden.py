@@ -147,6 +147,43 @@ def test_resnet_encoder_and_dgrn():
     assert (y - t(g['restored'])).abs().max() < 5e-4
 
 
+def test_resnet_dgrn_cfg0_first_image():
+    """BASELINE configs[0] (ResNet encoder + DGRN eval forward, sigma = 25, batch 4, 128 x 128): the oracle against the
+    reference's own output (tests/golden/resnet_dgrn_cfg0.npz, tools/make_golden_dgrn.py).  Eval-mode BatchNorm makes the
+    images independent, so the CPU suite checks the first image only; the GPU test covers all four."""
+    g = load_golden('resnet_dgrn_cfg0.npz')
+    se, sdg = _state('spec_resnet_encoder.json'), _state('spec_dgrn64.json')
+    xq, _, _ = synth.noisy_batch(4, 25)
+    with torch.no_grad():
+        fea, out, inter = airnet.resnet_encoder_forward(se, '', xq[:1])
+        y = airnet.dgrn_forward(sdg, '', xq[:1], inter)
+    assert (fea - t(g['fea'])[:1]).abs().max() < 1e-4 and (out[0] - t(g['out'])[:1]).abs().max() < 1e-4
+    assert (y - t(g['restored'])[:1]).abs().max() < 5e-4
+
+
+def test_vit_dgrn_train_encoder_side():
+    """configs[2] (ViT 4_bands, encoder_dim 64 + DGRN, mixed degradations): the contrastive side of the reference's train
+    step (MoCo with num_losses = len(out)) - logits, momentum-updated key encoder, BatchNorm running statistics.  The
+    restorer side of this golden (two DGRN forward + backward passes at 128 x 128) is checked on the GPU only."""
+    g = load_golden('airnet_vit_dgrn_train.npz')
+    sd = detfill.make_state(load_spec('spec_airnet_vit_dgrn.json'))
+    pnames = [k[len('E.E.encoder_q.'):] for k in sd if k.startswith('E.E.encoder_q.') and 'running_' not in k and 'num_batches' not in k]
+    xq, xk, clean = synth.mixed_batch(2)
+    bn = {}
+    with torch.no_grad():
+        _, q, inter = airnet.vit_encoder_forward(sd, 'E.E.encoder_q.', xq, 64, decompose_type='4_bands', training=True, bn_stats=bn)
+        airnet.momentum_update(sd, 'E.E.encoder_q.', 'E.E.encoder_k.', pnames)
+        _, k, _ = airnet.vit_encoder_forward(sd, 'E.E.encoder_k.', xk, 64, decompose_type='4_bands', training=True)
+        logits = airnet.moco_logits(q, k, sd['E.E.queue'])
+    assert len(logits) == 1 and (logits[0] - t(g['logits'])[0]).abs().max() < 5e-3
+    for kk in g:
+        if kk.startswith('kparam/'):
+            name = kk[len('kparam/'):]
+            f = sd[name].flatten()
+            step = max(1, -(-f.numel() // 4096))
+            assert (f[::step] - t(g[kk])).abs().max() < 1e-6, name
+
+
 def test_vit_encoder():
     g = load_golden('vit_encoder.npz')
     sd = _state('spec_vit_encoder_ed64.json')
