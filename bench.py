@@ -34,12 +34,17 @@ BATCH = 16
 STEP_GFLOP_PER_CROP = 555.0
 
 
-def make_opt(batch):
-    return types.SimpleNamespace(encoder_type='Uformer', decoder_type='Uformer', encoder_dim=256, L=3,
-                                 encoder_msa_type='freq', encoder_embed_dim=28, embed_dim=56,
-                                 degradation_embedding_method=['all_3_bands'], frequency_decompose_type='none',
-                                 learnable_modulator=False, debug_mode=False, batch_size=batch, out_channels=3,
-                                 batch_wise_decompose=False)
+def make_opt(batch, workload='train'):
+    o = types.SimpleNamespace(encoder_type='Uformer', decoder_type='Uformer', encoder_dim=256, L=3,
+                              encoder_msa_type='freq', encoder_embed_dim=28, embed_dim=56,
+                              degradation_embedding_method=['all_3_bands'], frequency_decompose_type='none',
+                              learnable_modulator=False, debug_mode=False, batch_size=batch, out_channels=3,
+                              batch_wise_decompose=False)
+    if workload == 'vit_dgrn_train':        # the authors' own ViT runs: --encoder_dim 64 (plot_LFS_distribution.py:26)
+        o.encoder_type, o.decoder_type, o.encoder_dim, o.frequency_decompose_type = 'ViT', 'ResNet', 64, '4_bands'
+    elif workload == 'resnet_dgrn_fwd':
+        o.encoder_type, o.decoder_type, o.encoder_dim = 'ResNet', 'ResNet', 256
+    return o
 
 
 class ClockSampler(threading.Thread):
@@ -113,20 +118,38 @@ def measure_tf32_peak():
     return 2 * n ** 3 / (best * 1e-3) / 1e12
 
 
-def oracle_train_step_time(batch, threads, steps=1, device='cpu'):
-    """Seconds per train step of the oracle (reference algorithm in plain torch ops) at ``batch`` crops: forward
-    q/k/decoder, loss, backward, Adam update.  device='cpu' is the contract's reference arm; device='cuda' runs the very
-    same torch program on the GPU through stock cuBLAS / cuFFT / ATen kernels ("the reference on
-    the same B200 via stock torch CUDA - the real bar the kernels must beat")."""
+def _load_by_path(name, relpath):
+    """A host-side helper module of the package loaded by FILE PATH (no package import, no libfreqair): the reference arm
+    must not import the product."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, PKG, relpath))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _oracle_state(spec_name, batch, device):
+    """Name-keyed deterministic weights (oracle/detfill.py) for the parameter names / shapes of the reference's own
+    modules (tests/golden/spec_*.json, written by tools/make_golden*.py from the unmodified reference); the MoCo queue is
+    re-shaped to K = 3 * batch (net/model.py:35)."""
+    from oracle import detfill
+    spec = json.load(open(os.path.join(ROOT, 'tests', 'golden', spec_name)))
+    if 'E.E.queue' in spec:
+        spec['E.E.queue'][0][2] = 3 * batch
+    return {k: v.to(device) for k, v in detfill.make_state(spec).items()}
+
+
+def oracle_train_step_time(batch, threads, steps=1, device='cpu', warmup=0, workload='train'):
+    """Seconds per train step (best of `steps` after `warmup`) of the oracle (the reference algorithm in plain torch ops) at
+    ``batch`` crops: forward q/k/decoder, loss, backward, Adam update.  device='cpu' is the contract's reference arm;
+    device='cuda' runs the very same torch program on the GPU through stock cuBLAS / cuFFT / ATen kernels (SURVEY section
+    8d: "the reference on the same B200 via stock torch CUDA - the real bar the kernels must beat")."""
     from oracle import airnet as oa
-    synth = importlib.import_module(PKG + '.synth')
-    model = importlib.import_module(PKG + '.net.model')
+    synth = _load_by_path('freqair_synth', 'synth.py')
     torch.set_num_threads(threads)
-    torch.manual_seed(0)
-    net = model.AirNet(make_opt(batch))               # parameter container only (CPU); the math below is oracle/
-    sd = {k: v.detach().clone().to(device) for k, v in net.state_dict().items()}
-    del net
     cuda = device != 'cpu'
+    vit = workload == 'vit_dgrn_train'
+    sd = _oracle_state('spec_airnet_vit_dgrn.json' if vit else 'spec_airnet_uformer_uformer_L3.json', batch, device)
     if cuda:
         torch.set_default_device(device)              # the oracle builds its constant tables with bare factories
     pnames = [k[len('E.E.encoder_q.'):] for k in sd if k.startswith('E.E.encoder_q.')
@@ -137,17 +160,21 @@ def oracle_train_step_time(batch, threads, steps=1, device='cpu'):
         sd[k].requires_grad_(True)
     opt = torch.optim.Adam([sd[k] for k in train_keys], lr=2e-4)
     torch.set_default_device('cpu')
-    xq, xk, clean = (t.to(device) for t in synth.noisy_batch(batch, 25))
+    xq, xk, clean = (t.to(device) for t in (synth.mixed_batch(batch) if vit else synth.noisy_batch(batch, 25)))
     if cuda:
         torch.set_default_device(device)
     times = []
     try:
-        for _ in range(steps):
+        for i in range(warmup + steps):
             if cuda:
                 torch.cuda.synchronize()
             t0 = time.perf_counter()
             opt.zero_grad()
-            restored, logits, _ = oa.airnet_uformer_forward(sd, xq, xk, True, param_names=pnames)
+            if vit:
+                restored, logits, _ = oa.airnet_dgrn_forward(sd, xq, xk, True, encoder='ViT', encoder_dim=64,
+                                                             decompose_type='4_bands', param_names=pnames)
+            else:
+                restored, logits, _ = oa.airnet_uformer_forward(sd, xq, xk, True, param_names=pnames)
             labels = torch.zeros(batch, dtype=torch.long, device=device)
             ce = sum(torch.nn.functional.cross_entropy(l, labels) for l in logits) / len(logits)
             loss = (restored - clean).abs().mean() + 0.6 * ce
@@ -156,9 +183,28 @@ def oracle_train_step_time(batch, threads, steps=1, device='cpu'):
             if cuda:
                 loss.item()
                 torch.cuda.synchronize()
-            times.append(time.perf_counter() - t0)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
     finally:
         torch.set_default_device('cpu')
+    return min(times)
+
+
+def oracle_dgrn_forward_time(batch, threads, steps=1, warmup=0):
+    """Seconds per ResNet-encoder + DGRN eval forward (configs[0]) of the oracle at ``batch`` images on the CPU."""
+    from oracle import airnet as oa
+    synth = _load_by_path('freqair_synth', 'synth.py')
+    torch.set_num_threads(threads)
+    se, sdg = _oracle_state('spec_resnet_encoder.json', batch, 'cpu'), _oracle_state('spec_dgrn64.json', batch, 'cpu')
+    xq, _, _ = synth.noisy_batch(batch, 25)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            _, _, inter = oa.resnet_encoder_forward(se, '', xq)
+            oa.dgrn_forward(sdg, '', xq, inter)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
     return min(times)
 
 
@@ -172,8 +218,7 @@ def run_reference_cuda(args):
     for name, tf32 in (('fp32', False), ('tf32', True)):
         torch.backends.cuda.matmul.allow_tf32 = tf32
         torch.backends.cudnn.allow_tf32 = tf32
-        oracle_train_step_time(args.batch, os.cpu_count() or 1, 2, 'cuda')
-        t = oracle_train_step_time(args.batch, os.cpu_count() or 1, k, 'cuda')
+        t = oracle_train_step_time(args.batch, os.cpu_count() or 1, k, 'cuda', 2)
         out[name] = {'value': args.batch / t, 'ms_per_step': t * 1e3}
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
@@ -182,24 +227,42 @@ def run_reference_cuda(args):
     emit(out)
 
 
+WORKLOADS = {
+    'train': dict(metric=METRIC, unit=UNIT,
+                  name='configs[1]: Uformer+Uformer all_3_bands train step, 128x128, sigma=25'),
+    'vit_dgrn_train': dict(metric='train crops/sec (128x128, ViT 4_bands + DGRN train step, mixed degradations)', unit=UNIT,
+                           name='configs[2]: ViT encoder (4_bands, encoder_dim 64) + DGRN train step, 128x128, '
+                                'sigma 15/25/50 + rain + haze'),
+    'resnet_dgrn_fwd': dict(metric='eval forward images/sec (128x128, ResNet encoder + DGRN)', unit='img/s',
+                            name='configs[0]: ResNet encoder + DGRN eval forward, 128x128, sigma=25, batch 4'),
+}
+
+
 def run_reference(args, rank, world):
+    """The contract's reference arm: the reference algorithm's CPU restatement (oracle/) on the host cores, on a bounded
+    sample of the arm's workload (batch 2 of the batch-16 train steps; batch 1 of the batch-4 DGRN forward - CPU time is
+    linear in batch), --warmup untimed and --steps timed steps (capped so the run ends within minutes)."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample_b = 2
-    for _ in range(max(0, min(args.warmup, 1))):
-        oracle_train_step_time(sample_b, cores, 1)
-    k = max(1, min(args.steps, 3))
-    t = oracle_train_step_time(sample_b, cores, k)
+    wl = WORKLOADS.get(args.workload, WORKLOADS['train'])
+    fwd = args.workload == 'resnet_dgrn_fwd'
+    sample_b = 1 if fwd else 2
+    w, k = max(0, min(args.warmup, 2)), max(1, min(args.steps, 5))
+    if fwd:
+        t = oracle_dgrn_forward_time(sample_b, cores, k, w)
+        what = f'oracle/ CPU restatement of the ResNet+DGRN forward, batch {sample_b}'
+    else:
+        t = oracle_train_step_time(sample_b, cores, k, 'cpu', w, args.workload if args.workload in WORKLOADS else 'train')
+        what = f'oracle/ CPU restatement of the reference train step, batch {sample_b}'
     v = sample_b / t
-    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': world, 'steps': k,
-            'warmup': min(args.warmup, 1), 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+    line = {'impl': 'reference', 'metric': wl['metric'], 'value': v, 'unit': wl['unit'], 'n_gpus': world, 'steps': k,
+            'warmup': w, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'configs[1]: Uformer+Uformer all_3_bands train step, 128x128, sigma=25',
-                       'sample': f'batch {sample_b} of the batch-{BATCH} step (CPU step time is linear in batch)'},
-            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                             'sample': f'oracle/ CPU restatement of the reference train step, batch {sample_b}, {k} step(s)'},
-            'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+            'config': {'workload': wl['name'],
+                       'sample': f'batch {sample_b} (CPU time is linear in batch); best of {k} step(s) after {w} warm-up'},
+            'cpu_baseline': {'value': v, 'unit': wl['unit'], 'cores': cores, 'kind': 'port', 'sample': f'{what}, {k} step(s)'},
+            'e2e': {'value': v, 'unit': wl['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     emit(line)
 
 
@@ -253,6 +316,90 @@ def run_inference(args):
                       'gpu_launches': launches, 'tiles_per_s': ntiles / (ms * 1e-3)})
 
 
+def run_dgrn_forward(args):
+    """configs[0]: ResNet encoder + DGRN (AirNet eval forward, test.py:59) on the sigma = 25 batch of 4 at 128 x 128.
+    value = images / s with the batch resident in HBM (CUDA-graph replay); e2e = pinned host batch -> device -> forward ->
+    restored batch back to the host.  cpu_baseline = the oracle's forward on the host cores (batch 1, scaled)."""
+    ops = importlib.import_module(PKG + '.ops')
+    synth = importlib.import_module(PKG + '.synth')
+    model = importlib.import_module(PKG + '.net.model')
+    B = 4 if args.batch == BATCH else args.batch
+    torch.manual_seed(0)
+    net = model.AirNet(make_opt(B, 'resnet_dgrn_fwd')).cuda().eval()
+    xq, _, _ = synth.noisy_batch(B, 25)
+    host = xq.pin_memory()
+    static_in = host.cuda()
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+    with torch.no_grad():
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                net(static_in, static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        n0 = ops.launch_count()
+        with torch.cuda.graph(graph):
+            static_out = net(static_in, static_in)
+        per_replay = ops.launch_count() - n0
+    for _ in range(W):
+        graph.replay()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    clocks = sampler.summary()
+    out_host = torch.empty_like(host).pin_memory()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(K):
+        static_in.copy_(host, non_blocking=True)
+        graph.replay()
+        out_host.copy_(static_out, non_blocking=True)
+        torch.cuda.synchronize()
+    f1.record()
+    torch.cuda.synchronize()
+    ms_e2e = f0.elapsed_time(f1) / K
+    roofline = None
+    if not args.no_roofline:
+        ops.FLOP_COUNTER[0] = 0
+        ops.prof_begin(ops.K_GEMM)
+        with torch.no_grad():
+            net(static_in, static_in)
+        torch.cuda.synchronize()
+        gemm_ms, gemm_n = ops.prof_end()
+        flops, ops.FLOP_COUNTER[0] = ops.FLOP_COUNTER[0], None
+        peak = measure_tf32_peak()
+        ach = flops / (gemm_ms * 1e-3) / 1e12
+        roofline = {'bound': 'tensor', 'kernel': 'fa_gemm (3x3 / 1x1 / DCN contractions of the forward)', 'achieved': ach,
+                    'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': None, 'launches_per_step': gemm_n,
+                    'avg_launch_ms': gemm_ms / max(gemm_n, 1), 'algorithmic_gflop_per_step': flops / 1e9,
+                    'share_of_step': gemm_ms / ms, 'peak_source': 'dense TF32 cuBLAS 8192^3 measured in this run'}
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        t = oracle_dgrn_forward_time(1, cores, 1, 0)
+        cpu_baseline = {'value': 1 / t, 'unit': 'img/s', 'cores': cores, 'kind': 'port',
+                        'sample': f'oracle/ CPU restatement of the same forward at batch 1 ({t:.1f} s; CPU time is linear in batch)'}
+    wl = WORKLOADS['resnet_dgrn_fwd']
+    emit({'metric': wl['metric'], 'value': B / (ms * 1e-3), 'unit': 'img/s', 'n_gpus': 1, 'steps': K, 'warmup': W,
+          'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+          'data': 'synthetic', 'config': {'workload': wl['name'] + ', random init', 'batch': B, 'launch': 'cuda_graph',
+                                          'l2': 'one forward streams ~6 GB of activations, far beyond the 126 MB L2'},
+          'clocks': clocks,
+          'e2e': {'value': B / (ms_e2e * 1e-3), 'unit': 'img/s', 'h2d_bytes_per_step': host.numel() * 4,
+                  'd2h_bytes_per_step': host.numel() * 4, 'ms_per_step': ms_e2e},
+          'gpu_launches': per_replay * K, 'gpu_launches_per_step': per_replay, 'roofline': roofline,
+          'cpu_baseline': cpu_baseline})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -266,8 +413,11 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-roofline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch the step kernel by kernel instead of replaying its CUDA graph')
-    ap.add_argument('--workload', default='train', choices=['train', 'infer512', 'infer1024'],
-                    help='train = the headline configs[1] step (default); infer512 / infer1024 = configs[3]-style tiled '
+    ap.add_argument('--workload', default='train',
+                    choices=['train', 'infer512', 'infer1024', 'vit_dgrn_train', 'resnet_dgrn_fwd'],
+                    help='train = the headline configs[1] step (default); vit_dgrn_train = configs[2] (ViT 4_bands + DGRN '
+                         'train step on the mixed-degradation batch, batch-sharded over --gpus); resnet_dgrn_fwd = configs[0] '
+                         '(ResNet encoder + DGRN eval forward, batch 4); infer512 / infer1024 = configs[3]-style tiled '
                          'full-resolution inference latency (Uformer encoder + Uformer decoder), ms per image, 1 GPU')
     args = ap.parse_args()
     claim_stdout()
@@ -286,9 +436,14 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device - the freqair path has no CPU fallback (use --impl reference for the CPU baseline)')
-    if args.workload != 'train':
+    if args.workload in ('infer512', 'infer1024'):
         run_inference(args)
         return
+    if args.workload == 'resnet_dgrn_fwd':
+        run_dgrn_forward(args)
+        return
+    vit = args.workload == 'vit_dgrn_train'
+    wl = WORKLOADS[args.workload]
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
     torch.cuda.set_device(local)
@@ -302,9 +457,12 @@ def main():
     trainer = importlib.import_module(PKG + '.trainer')
     B = args.batch
     torch.manual_seed(0)                                   # identical replicas on every rank
-    net = model.AirNet(make_opt(B)).cuda().train()
-    ts = trainer.TrainStep(net, lr=2e-4, contrast_loss_weight=0.6, distributed=world > 1)
-    xq, xk, clean = synth.noisy_batch(B, 25, seed=1234 + 97 * rank)       # different crops per rank
+    net = model.AirNet(make_opt(B, args.workload)).cuda().train()
+    ts = trainer.TrainStep(net, lr=3e-4 if vit else 2e-4, contrast_loss_weight=0.6, distributed=world > 1)   # option.py:80-103
+    if vit:                                                                # sample i cycles sigma15/25/50, rain, haze
+        xq, xk, clean = synth.mixed_batch(B, seed=1234 + 97 * rank)
+    else:
+        xq, xk, clean = synth.noisy_batch(B, 25, seed=1234 + 97 * rank)   # different crops per rank
     host = [t.pin_memory() for t in (xq, xk, clean, clean.clone())]       # train.py:77-78 copies four tensors
     dev_in = [t.cuda(non_blocking=True) for t in host[:3]]
     h2d_bytes = sum(t.numel() * 4 for t in host)
@@ -390,17 +548,15 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         sb = 2
-        oracle_train_step_time(sb, cores, 1)                 # warm-up (allocator, thread pool)
-        t = oracle_train_step_time(sb, cores, 3)
+        t = oracle_train_step_time(sb, cores, 3, 'cpu', 1, args.workload)   # 1 warm-up (allocator, thread pool), best of 3
         cpu_baseline = {'value': sb / t, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                         'sample': f'oracle/ CPU restatement of the same train step at batch {sb} (best of 3 steps after 1 '
                                   f'warm-up, {t:.1f} s/step; CPU step time is linear in batch)'}
     if rank == 0:
-        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+        line = {'metric': wl['metric'], 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
                 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'f32', 'data': 'synthetic',
-                'config': {'workload': 'configs[1]: Uformer encoder + Uformer decoder (all_3_bands, L=3, freq MSA) full '
-                                       'train step incl. Adam, 128x128 crops, sigma=25 synthetic noise, random init',
+                'config': {'workload': wl['name'] + '; full train step incl. Adam, random init',
                            'batch_per_gpu': B, 'global_batch': B * world, 'parallelism': f'dp{world}',
                            'launch': 'eager' if args.no_graph else 'cuda_graph',
                            'l2': 'no explicit flush: one step streams >20 GB of activations + 4.5 GB of weights/optimizer '
@@ -409,7 +565,7 @@ def main():
                 'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
                         'ms_per_step': ms_e2e / K, 'last_loss': last},
                 'gpu_launches': launches, 'gpu_launches_per_step': launches / K,
-                'step_tflop': STEP_GFLOP_PER_CROP * B / 1e3,
+                'step_tflop': (STEP_GFLOP_PER_CROP * B / 1e3) if not vit else None,
                 'roofline': roofline, 'cpu_baseline': cpu_baseline}
         emit(line)
     if dist is not None:
