@@ -120,4 +120,43 @@ int fa_gemm(const float* A, const float* B, float* C, int M, int N, int K, int64
   return fa_gemm_simt_launch(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, epi, st);
 }
 
+static int conv_passes(int backend) { return backend == 4 ? 2 : (backend == 5 ? 1 : 3); }
+
+int fa_conv3x3_gemm(const float* x, const float* wk, float* y, int B, int H, int W, int Cin, int Cout, int64_t ldy,
+                    const FaGemmEpilogue* epi, int backend, fa_stream_t stream) {
+  FA_REQUIRE(x && wk && y, "fa_conv3x3_gemm: null operand");
+  FA_REQUIRE(backend == 0 || backend == 2 || backend == 4 || backend == 5, "fa_conv3x3_gemm: backend must be 0, 2, 4 or 5");
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_GEMM, st);
+  FaConvOperand cv{1, B, H, W, Cin};
+  const int64_t T = (int64_t)B * H * W;
+  FA_REQUIRE(T < (1ll << 31), "fa_conv3x3_gemm: too many tokens");
+  int rc = fa_gemm_tc_launch(x, wk, y, (int)T, Cout, 9 * Cin, Cin, 9 * Cin, ldy, 0, 1, epi, st, conv_passes(backend), &cv);
+  if (rc == FA_ERR_UNSUPPORTED)
+    fa_set_error("fa_conv3x3_gemm: geometry B=%d H=%d W=%d Cin=%d Cout=%d not eligible (Cin %% 32, H*W %% 128, W | 128 or 128 | W)",
+                 B, H, W, Cin, Cout);
+  return rc;
+}
+
+int fa_conv3x3_wgrad(const float* g, int64_t ldg, const float* x, float* dwk, int B, int H, int W, int Cin, int Cout,
+                     int accumulate, float* dbias, int backend, fa_stream_t stream) {
+  FA_REQUIRE(g && x && dwk, "fa_conv3x3_wgrad: null operand");
+  FA_REQUIRE(backend == 0 || backend == 2 || backend == 4 || backend == 5, "fa_conv3x3_wgrad: backend must be 0, 2, 4 or 5");
+  cudaStream_t st = (cudaStream_t)stream;
+  FaProfScope prof(FA_K_GEMM, st);
+  FaConvOperand cv{2, B, H, W, Cin};
+  const int64_t T = (int64_t)B * H * W;
+  FA_REQUIRE(T < (1ll << 31), "fa_conv3x3_wgrad: too many tokens");
+  FaGemmEpilogue e;
+  memset(&e, 0, sizeof(e));
+  e.alpha = 1.0f;
+  e.accumulate = accumulate;
+  e.a_rowsum = dbias;                    // column sums of g = the bias gradient, from the same pass over g
+  int rc = fa_gemm_tc_launch(g, x, dwk, Cout, 9 * Cin, (int)T, ldg, Cin, 9 * Cin, 1, 0, &e, st, conv_passes(backend), &cv);
+  if (rc == FA_ERR_UNSUPPORTED)
+    fa_set_error("fa_conv3x3_wgrad: geometry B=%d H=%d W=%d Cin=%d Cout=%d not eligible (Cin %% 32, W %% 32, H*W %% 128)", B, H, W,
+                 Cin, Cout);
+  return rc;
+}
+
 }  // extern "C"

@@ -28,7 +28,7 @@ __device__ __forceinline__ Tap make_tap(const float* omr, int k, int y, int x, i
   return t;
 }
 
-__global__ void __launch_bounds__(256) dcn_im2col_kernel(const float* __restrict__ x, const float* __restrict__ om,
+__global__ void __launch_bounds__(256) dcn_im2col_kernel(const float* __restrict__ x, const float* __restrict__ om, int ldom,
                                                          float* __restrict__ col, int B, int H, int W, int C) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) dcn_im2col_kernel(const float* __restrict
     const int64_t p = it / 9;
     const int xx = (int)(p % W), yy = (int)((p / W) % H);
     const int b = (int)(p / ((int64_t)H * W));
-    const Tap t = make_tap(om + p * 27, k, yy, xx, H, W);
+    const Tap t = make_tap(om + p * ldom, k, yy, xx, H, W);
     const float* xb = x + (int64_t)b * H * W * C;
     float* dst = col + p * 9 * C + (int64_t)k * C;
     for (int c = lane; c < C4; c += 32) {
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) dcn_im2col_kernel(const float* __restrict
 }
 
 // adjoint: dx (atomic scatter), d(offset y/x), d(mask logit)
-__global__ void __launch_bounds__(256) dcn_col2im_kernel(const float* __restrict__ x, const float* __restrict__ om,
+__global__ void __launch_bounds__(256) dcn_col2im_kernel(const float* __restrict__ x, const float* __restrict__ om, int ldom,
                                                          const float* __restrict__ dcol, float* __restrict__ dx,
                                                          float* __restrict__ dom, int B, int H, int W, int C) {
   const int lane = threadIdx.x & 31;
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) dcn_col2im_kernel(const float* __restrict
     const int64_t p = it / 9;
     const int xx = (int)(p % W), yy = (int)((p / W) % H);
     const int b = (int)(p / ((int64_t)H * W));
-    const Tap t = make_tap(om + p * 27, k, yy, xx, H, W);
+    const Tap t = make_tap(om + p * ldom, k, yy, xx, H, W);
     const float* xb = x + (int64_t)b * H * W * C;
     float* dxb = dx + (int64_t)b * H * W * C;
     const float* g = dcol + p * 9 * C + (int64_t)k * C;
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256) dcn_col2im_kernel(const float* __restrict
     }
     gy = warp_sum(gy); gx = warp_sum(gx); gm = warp_sum(gm);
     if (lane == 0) {
-      float* d = dom + p * 27;
+      float* d = dom + p * ldom;
       d[2 * k] = gy;
       d[2 * k + 1] = gx;
       d[18 + k] = gm * t.m * (1.0f - t.m);
@@ -108,8 +108,8 @@ __global__ void __launch_bounds__(256) dcn_col2im_kernel(const float* __restrict
 
 extern "C" {
 
-int fa_dcn_im2col(const float* x, const float* om, float* col, int B, int H, int W, int C, fa_stream_t stream) {
-  FA_REQUIRE(x && om && col, "fa_dcn_im2col: null pointer");
+int fa_dcn_im2col(const float* x, const float* om, int ldom, float* col, int B, int H, int W, int C, fa_stream_t stream) {
+  FA_REQUIRE(x && om && col && ldom >= 27, "fa_dcn_im2col: null pointer or ldom < 27");
   FA_REQUIRE(C % 4 == 0, "fa_dcn_im2col: C=%d must be a multiple of 4", C);
   cudaStream_t st = (cudaStream_t)stream;
   FaProfScope prof(FA_K_DCN, st);
@@ -117,21 +117,21 @@ int fa_dcn_im2col(const float* x, const float* om, float* col, int B, int H, int
   if (items == 0) return FA_OK;
   int64_t blocks = (items + 7) / 8;
   if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;
-  dcn_im2col_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, om, col, B, H, W, C);
+  dcn_im2col_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, om, ldom, col, B, H, W, C);
   FA_LAUNCH_CHECK("fa_dcn_im2col");
   return FA_OK;
 }
 
-int fa_dcn_col2im(const float* x, const float* om, const float* dcol, float* dx, float* dom, int B, int H, int W, int C,
-                  fa_stream_t stream) {
-  FA_REQUIRE(x && om && dcol && dx && dom, "fa_dcn_col2im: null pointer");
+int fa_dcn_col2im(const float* x, const float* om, int ldom, const float* dcol, float* dx, float* dom, int B, int H, int W,
+                  int C, fa_stream_t stream) {
+  FA_REQUIRE(x && om && dcol && dx && dom && ldom >= 27, "fa_dcn_col2im: null pointer or ldom < 27");
   cudaStream_t st = (cudaStream_t)stream;
   FaProfScope prof(FA_K_DCN, st);
   const int64_t items = (int64_t)B * H * W * 9;
   if (items == 0) return FA_OK;
   int64_t blocks = (items + 7) / 8;
   if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;
-  dcn_col2im_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, om, dcol, dx, dom, B, H, W, C);
+  dcn_col2im_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, om, ldom, dcol, dx, dom, B, H, W, C);
   FA_LAUNCH_CHECK("fa_dcn_col2im");
   return FA_OK;
 }

@@ -98,6 +98,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -271,6 +277,12 @@ struct TcGeom {
                  // nearest TF32), 1 = rn(A).rn(B), 0 = raw operands, truncated by the tensor core (measurement only)
   int a_tmem;    // passes >= 1: A (and A_lo) are staged in TMEM by the split warps (MMA reads only B from shared memory)
   int b_exact;   // passes 1 / 2: B is already TF32-representable (pre-rounded by its producer): the split warps skip it
+  // Implicit 3x3 (stride 1, pad 1) patch operand over NHWC tokens x [cB, cH, cW, cC]: the patch matrix
+  // col[(b,y,x)][(ky,kx,ci)] = x[b, y+ky-1, x+kx-1, ci] (0 outside the image) is never materialised - the producer
+  // addresses x through a 4-D tensor map {C, W, H, B} and lets TMA's out-of-bounds zero fill do the padding.
+  //   conv = 1: op(A) = col (K-major; a 128-row M tile is 128/cW image rows of one sample, or a 128-pixel row segment)
+  //   conv = 2: op(B) = col (MN-major; N = 9*cC, a 32-wide slab lies inside one tap, a 32-token k-block inside one row)
+  int conv, cH, cW, cC;
 };
 
 // compile-time activation: keeps the unrolled row loop straight-line (a run-time switch per element splits it into
@@ -485,13 +497,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
           if (elect_one()) {
           mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
           const int k0 = kbeg + kb * BK;
-          if (!A_MN) {
+          if (g.conv == 1) {
+            const int hw = g.cH * g.cW, bi = m0 / hw, rem = m0 - bi * hw, y0 = rem / g.cW, x0 = rem - y0 * g.cW;
+            const int tap = k0 / g.cC, c0 = k0 - tap * g.cC;
+            tma_load_4d(sA + s * A_BYTES, &tmA, &full[s], c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, bi);
+          } else if (!A_MN) {
             tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], k0, m0);
           } else {
 #pragma unroll
             for (int j = 0; j < BM / 32; ++j) tma_load_2d(sA + s * A_BYTES + j * 4096, &tmA, &full[s], m0 + 32 * j, k0);
           }
-          if (!B_MN) {
+          if (g.conv == 2) {
+            const int hw = g.cH * g.cW, bi = k0 / hw, rem = k0 - bi * hw, y0 = rem / g.cW, x0 = rem - y0 * g.cW;
+#pragma unroll
+            for (int j = 0; j < BN / 32; ++j) {
+              const int n = n0 + 32 * j, tap = n / g.cC, c0 = tap < 9 ? n - tap * g.cC : g.cC;     // past N: channel OOB -> zeros
+              tma_load_4d(sB + s * B_BYTES + j * 4096, &tmB, &full[s], c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, bi);
+            }
+          } else if (!B_MN) {
             tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], k0, n0);
           } else {
 #pragma unroll
@@ -898,6 +921,20 @@ bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int
   return r == CUDA_SUCCESS;
 }
 
+// NHWC tokens x [B, H, W, C] as a 4-D tensor {C, W, H, B}; box = {32 channels, box_w pixels, box_h rows, 1 sample}
+bool make_map_nhwc(CUtensorMap* m, const float* base, int B, int H, int W, int C, int box_w, int box_h, bool mn_major) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 template <int BN, int MODE>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, float* C, TcGeom g, const EpiTC& e, cudaStream_t st) {
   // one persistent CTA per SM; the operand ring takes what the 227 KB leave after the 32 KB epilogue transpose tiles
@@ -933,10 +970,19 @@ int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, float* C, 
 }  // namespace
 
 int fa_gemm_tc_launch(const float* A, const float* B, float* C, int M, int N, int K, int64_t lda, int64_t ldb,
-                      int64_t ldc, int transA, int transB, const FaGemmEpilogue* ep, cudaStream_t st, int passes) {
+                      int64_t ldc, int transA, int transB, const FaGemmEpilogue* ep, cudaStream_t st, int passes,
+                      const FaConvOperand* conv) {
+  // conv != NULL: the operand it names (1 = A, 2 = B) is the implicit 3x3 patch matrix of the token tensor passed in
+  // its place; the caller has set M / N / K and the layout flags as for the materialised matrix
+  if (conv) {
+    const bool ok = conv->C % 32 == 0 && (conv->H * conv->W) % 128 == 0 && (conv->W % 128 == 0 || 128 % conv->W == 0) &&
+                    passes >= 1 && ((conv->which == 1 && !transA) || (conv->which == 2 && !transB && conv->W % 32 == 0));
+    if (!ok) return FA_ERR_UNSUPPORTED;
+  }
   // eligibility: 16-byte aligned bases and row pitches (TMA), a tile-sized problem, driver entry point present
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if (!al16(A) || !al16(B) || (lda % 4) || (ldb % 4)) return FA_ERR_UNSUPPORTED;
+  if (!al16(A) || !al16(B) || (!(conv && conv->which == 1) && (lda % 4)) || (!(conv && conv->which == 2) && (ldb % 4)))
+    return FA_ERR_UNSUPPORTED;
   if (M < 8 || N < 8 || K < 8) return FA_ERR_UNSUPPORTED;
   const bool a_mn = transA != 0;          // op(A)[m,k] = A[k*lda+m]: reduction index is the row -> MN-major
   const bool b_mn = transB == 0;          // op(B)[k,n] = B[k*ldb+n]
@@ -979,6 +1025,7 @@ int fa_gemm_tc_launch(const float* A, const float* B, float* C, int M, int N, in
   static const bool atmem_env = [] { const char* e = getenv("FREQAIR_GEMM_ATMEM"); return !(e && e[0] == '0'); }();
   g.a_tmem = (passes >= 1 && (atmem_env || passes != 3)) ? 1 : 0;
   g.b_exact = (ep && ep->b_is_tf32 && passes >= 1 && passes <= 2) ? 1 : 0;
+  if (conv) { g.conv = conv->which; g.cH = conv->H; g.cW = conv->W; g.cC = conv->C; }
   if ((e.a_rowsum || e.a_kscale) && !g.a_tmem) return FA_ERR_UNSUPPORTED;      // both ride the TMEM staging of A
   g.tiles_m = (M + BM - 1) / BM;
   int bn = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 96 ? 96 : 128));
@@ -1020,10 +1067,14 @@ int fa_gemm_tc_launch(const float* A, const float* B, float* C, int M, int N, in
 
   CUtensorMap ta, tb;
   bool ok;
-  if (!a_mn) ok = make_map(&ta, A, M, K, lda, BK, BM, false);          // A [M,K]: box {32 k, 128 m}
+  if (g.conv == 1) {                  // 128 tokens = 128 / W whole image rows, or a 128-pixel segment of one row
+    const int bw = conv->W >= 128 ? 128 : conv->W;
+    ok = make_map_nhwc(&ta, A, conv->B, conv->H, conv->W, conv->C, bw, 128 / bw, false);
+  } else if (!a_mn) ok = make_map(&ta, A, M, K, lda, BK, BM, false);          // A [M,K]: box {32 k, 128 m}
   else ok = make_map(&ta, A, K, M, lda, 32, BK, true);                // A stored [K,M]: box {32 m, 32 k}
   if (!ok) { fa_set_error("fa_gemm(tcgen05): cuTensorMapEncodeTiled failed for A"); return FA_ERR_CUDA; }
-  if (!b_mn) ok = make_map(&tb, B, N, K, ldb, BK, bn, false);          // W [N,K]: box {32 k, bn n}
+  if (g.conv == 2) ok = make_map_nhwc(&tb, B, conv->B, conv->H, conv->W, conv->C, 32, 1, true);   // 32 tokens of one row
+  else if (!b_mn) ok = make_map(&tb, B, N, K, ldb, BK, bn, false);          // W [N,K]: box {32 k, bn n}
   else ok = make_map(&tb, B, K, N, ldb, 32, BK, true);                // B stored [K,N]: box {32 n, 32 k}
   if (!ok) { fa_set_error("fa_gemm(tcgen05): cuTensorMapEncodeTiled failed for B"); return FA_ERR_CUDA; }
   switch (mode) {

@@ -38,38 +38,73 @@ class InputProjFn(torch.autograd.Function):
         return None, dW, db, None          # the input image never needs a gradient on this path
 
 
+def flip_weight_matrix(wk, Cin):
+    """[Co, (ky,kx,ci)] -> [Ci, ((2-ky),(2-kx),co)]: the weight with which the data gradient of a 3x3 s1 p1 convolution is
+    itself a 3x3 s1 p1 convolution of dY (fa_conv3x3_gemm on the gradient)."""
+    Co = wk.shape[0]
+    return wk.view(Co, 9, Cin).flip(1).permute(2, 1, 0).reshape(Cin, 9 * Co).contiguous()
+
+
 class ConvTokFn(torch.autograd.Function):
     """y = act(Conv2d k x k, stride s, pad p on tokens) (+ residual).  Downsample 4x4 s2 p1
     (decoder_Uformer.py:414-430) and the 3x3 / 1x1 convs of DGRN and the ResNet encoder
-    (decoder_DGRN.py:5-6, encoder_ResNet.py:8-15).  ``col`` (optional) is a precomputed patch matrix of x."""
+    (decoder_DGRN.py:5-6, encoder_ResNet.py:8-15).
+
+    3x3 s1 p1 layers whose geometry allows it (ops.conv3x3_eligible: every 64-channel layer of DGRN at 128 x 128) run as
+    IMPLICIT GEMMs - forward, data gradient (the same kernel on dY with the flipped weight) and weight gradient address
+    the token tensor through a 4-D TMA map, so no 9x patch matrix is ever written or read.  The other layers (C = 3
+    stems, 4x4 s2 downsampling) gather an explicit patch matrix (fa_im2col) first."""
 
     @staticmethod
     def forward(ctx, x, wk, b, H, W, k, s, p, act, act_param, residual):
         B, _, C = x.shape
         xc = x.contiguous()
-        col = xc.view(-1, C) if (k == 1 and s == 1 and p == 0) else ops.im2col(xc, B, H, W, C, k, k, s, p)
-        y = torch.empty(col.shape[0], wk.shape[0], device=x.device, dtype=torch.float32)
-        r2 = residual.reshape(y.shape).contiguous() if residual is not None else None
-        ops.gemm(col, wk, y, bias=b, act=act, act_param=act_param, residual=r2)
+        Co = wk.shape[0]
         assert act in (ops.ACT_NONE, ops.ACT_LRELU) and not (act != ops.ACT_NONE and residual is not None)
-        ctx.geom = (B, H, W, C, k, s, p, act, act_param)
+        implicit = k == 3 and s == 1 and p == 1 and ops.conv3x3_eligible(H, W, C, Co)
+        one = k == 1 and s == 1 and p == 0
+        To = B * ((H + 2 * p - k) // s + 1) * ((W + 2 * p - k) // s + 1)
+        y = torch.empty(To, Co, device=x.device, dtype=torch.float32)
+        r2 = residual.reshape(y.shape).contiguous() if residual is not None else None
+        wkc = wk.contiguous()
+        if implicit:
+            ops.conv3x3_gemm(xc, wkc, y, B, H, W, bias=b, act=act, act_param=act_param, residual=r2)
+        else:
+            col = xc.view(-1, C) if one else ops.im2col(xc, B, H, W, C, k, k, s, p)
+            ops.gemm(col, wkc, y, bias=b, act=act, act_param=act_param, residual=r2)
+        ctx.geom = (B, H, W, C, k, s, p, act, act_param, implicit)
         ctx.has_bias, ctx.has_res = b is not None, residual is not None
-        # the patch matrix is rebuilt in backward (one streaming pass) instead of being kept alive
-        ctx.save_for_backward(xc, wk, y if act != ops.ACT_NONE else None)
-        return y.view(B, -1, wk.shape[0])
+        # the patch matrix (explicit path) is rebuilt in backward (one streaming pass) instead of being kept alive
+        ctx.save_for_backward(xc, wkc, y if act != ops.ACT_NONE else None)
+        return y.view(B, -1, Co)
 
     @staticmethod
     def backward(ctx, dy):
         xc, wk, y = ctx.saved_tensors
-        B, H, W, C, k, s, p, act, act_param = ctx.geom
-        g = dy.reshape(-1, wk.shape[0]).contiguous()
+        B, H, W, C, k, s, p, act, act_param, implicit = ctx.geom
+        Co = wk.shape[0]
+        g = dy.reshape(-1, Co).contiguous()
         dres = dy if ctx.has_res else None
         if act != ops.ACT_NONE:
             g = ops.act_bwd(g, y, act, act_param)      # LeakyReLU only: sign(out) == sign(pre)
+        dW = _z(wk)
+        if implicit:
+            db = torch.zeros(Co, device=g.device) if ctx.has_bias else None
+            ops.conv3x3_wgrad(g, xc, dW, B, H, W, accumulate=True, dbias=db)
+            dx = None
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty(B * H * W, C, device=g.device, dtype=torch.float32)
+                if ops.conv3x3_eligible(H, W, Co, C):
+                    ops.conv3x3_gemm(g.view(B, H * W, Co), flip_weight_matrix(wk, C), dx, B, H, W)
+                else:                                  # e.g. the 3-channel tail: explicit patch gradient
+                    dcol = torch.empty(B * H * W, 9 * C, device=g.device, dtype=torch.float32)
+                    ops.gemm(g, wk, dcol, transB=False)
+                    dx = ops.col2im(dcol, B, H, W, C, 3, 3, 1, 1)
+                dx = dx.view(B, H * W, C)
+            return dx, dW, db, None, None, None, None, None, None, None, dres
         one = (k == 1 and s == 1 and p == 0)
         col = xc.view(-1, C) if one else ops.im2col(xc, B, H, W, C, k, k, s, p)
-        dW = _z(wk)
-        db = torch.empty(wk.shape[0], device=g.device) if ctx.has_bias else None
+        db = torch.empty(Co, device=g.device) if ctx.has_bias else None
         if db is not None:
             ops.colsum(g, db)
         ops.gemm(g, col, dW, transA=True, transB=False, accumulate=True)

@@ -20,19 +20,39 @@ def default_conv(in_channels, out_channels, kernel_size, bias=True):
     return nn.Conv2d(in_channels, out_channels, kernel_size, padding=(kernel_size // 2), bias=bias)
 
 
+def _pad_rows(w, rows=32):
+    return torch.cat([w, w.new_zeros(rows - w.shape[0], *w.shape[1:])], 0).contiguous()
+
+
 class DGMFn(torch.autograd.Function):
-    """out = lrelu_slope(x + DCN(x, inter) + SFT(x, inter)); slope 1.0 = the bare DGM."""
+    """out = lrelu_slope(x + DCN(x, inter) + SFT(x, inter)); slope 1.0 = the bare DGM.
+
+    Offset / mask convolution (Conv2d(2C -> 27, 3x3) on cat([x, inter]), deform_conv.py:57-59): where the geometry
+    allows (every DGM of the 128 x 128, 64-channel DGRN) it runs as two IMPLICIT-GEMM convolutions - one over x, one over
+    the degradation map - accumulating into a 32-wide om buffer (27 channels + 5 zero pad so that rows are 128 bytes and
+    Cout % 4 == 0); its backward takes dom [T, 32] as a 32-channel token tensor: weight gradients by fa_conv3x3_wgrad,
+    data gradients by the same implicit kernel with the flipped weights.  No 9x patch matrix of x or of the degradation
+    map, and none of their gradients, ever exists.  Small / odd geometries (tests at n_feats 8) keep the explicit
+    fa_im2col path with a patch matrix of the degradation map shared by all DGMs (``col_i``)."""
 
     @staticmethod
     def forward(ctx, x, it, col_i, wom_x, wom_i, bom, wdcn, wg0, wg2, wb0, wb2, H, W, slope):
         B, HW, C = x.shape
         T = B * HW
         x2 = x.reshape(T, C).contiguous()
-        it2 = it.reshape(T, -1)
-        colx = ops.im2col(x2, B, H, W, C, 3, 3, 1, 1)
-        om = torch.empty(T, 27, device=x.device, dtype=torch.float32)
-        ops.gemm(colx, wom_x, om, bias=bom)
-        ops.gemm(col_i, wom_i, om, accumulate=True)
+        it2 = it.reshape(T, -1).contiguous()
+        Ci = it2.shape[1]
+        implicit = col_i is None
+        if implicit:
+            wx32, wi32, b32 = _pad_rows(wom_x), _pad_rows(wom_i), _pad_rows(bom)
+            om = torch.empty(T, 32, device=x.device, dtype=torch.float32)
+            ops.conv3x3_gemm(it2, wi32, om, B, H, W, bias=b32)
+            ops.conv3x3_gemm(x2, wx32, om, B, H, W, accumulate=True)
+        else:
+            colx = ops.im2col(x2, B, H, W, C, 3, 3, 1, 1)
+            om = torch.empty(T, 27, device=x.device, dtype=torch.float32)
+            ops.gemm(colx, wom_x, om, bias=bom)
+            ops.gemm(col_i, wom_i, om, accumulate=True)
         dcol = ops.dcn_im2col(x2, om, B, H, W, C)
         Co = wdcn.shape[0]
         dcn = torch.empty(T, Co, device=x.device, dtype=torch.float32)
@@ -46,14 +66,14 @@ class DGMFn(torch.autograd.Function):
         ops.gemm(it2, wb0, b1, act=ops.ACT_LRELU, act_param=0.1)
         ops.gemm(b1, wb2, beta)
         out = ops.sft_fuse_fwd(x2, dcn, gamma, beta, slope)
-        ctx.geom = (B, H, W, C, slope)
+        ctx.geom = (B, H, W, C, Ci, slope, implicit)
         ctx.save_for_backward(x2, it2, col_i, om, dcn, g1, gamma, b1, beta, wom_x, wom_i, wdcn, wg0, wg2, wb0, wb2)
         return out.view(B, HW, Co)
 
     @staticmethod
     def backward(ctx, dout):
         (x2, it2, col_i, om, dcn, g1, gamma, b1, beta, wom_x, wom_i, wdcn, wg0, wg2, wb0, wb2) = ctx.saved_tensors
-        B, H, W, C, slope = ctx.geom
+        B, H, W, C, Ci, slope, implicit = ctx.geom
         T = x2.shape[0]
         dev = x2.device
         dxa, ddcn, dgamma, dbeta = ops.sft_fuse_bwd(x2, dcn, gamma, beta, dout.reshape(T, -1).contiguous(), slope)
@@ -78,22 +98,36 @@ class DGMFn(torch.autograd.Function):
         ddcol = dcol                                        # reuse the buffer for the gradient
         ops.gemm(ddcn, wdcn, ddcol, transB=False)
         dxb, dom = ops.dcn_col2im(x2, om, ddcol, B, H, W, C)
-        # offset / mask conv
-        dbom = torch.empty(27, device=dev)
-        ops.colsum(dom, dbom)
-        colx = ops.im2col(x2, B, H, W, C, 3, 3, 1, 1)
-        dwom_x, dwom_i = _z(wom_x), _z(wom_i)
-        ops.gemm(dom, colx, dwom_x, transA=True, transB=False, accumulate=True)
-        ops.gemm(dom, col_i, dwom_i, transA=True, transB=False, accumulate=True)
-        ops.gemm(dom, wom_x, colx, transB=False)            # colx buffer becomes d(colx)
-        dxc = ops.col2im(colx, B, H, W, C, 3, 3, 1, 1).view(T, C)
-        dcol_i = None
-        if ctx.needs_input_grad[2]:
-            dcol_i = torch.empty_like(col_i)
-            ops.gemm(dom, wom_i, dcol_i, transB=False)
+        del ddcol, dcol
         dx = torch.empty_like(x2)
         ops.add2d(dxa, dxb, dx)
-        ops.add2d(dx, dxc, dx)
+        dcol_i = None
+        if implicit:
+            from .convs import flip_weight_matrix
+            wx32, wi32 = _pad_rows(wom_x), _pad_rows(wom_i)
+            dwx32 = torch.zeros(32, 9 * C, device=dev)
+            dwi32 = torch.zeros(32, 9 * Ci, device=dev)
+            db32 = torch.zeros(32, device=dev)
+            ops.conv3x3_wgrad(dom, x2, dwx32, B, H, W, accumulate=True, dbias=db32)
+            ops.conv3x3_wgrad(dom, it2, dwi32, B, H, W, accumulate=True)
+            dwom_x, dwom_i, dbom = dwx32[:27], dwi32[:27], db32[:27]
+            dom3 = dom.view(B, H * W, 32)
+            ops.conv3x3_gemm(dom3, flip_weight_matrix(wx32, C), dx, B, H, W, accumulate=True)
+            if ctx.needs_input_grad[1]:
+                ops.conv3x3_gemm(dom3, flip_weight_matrix(wi32, Ci), dit, B, H, W, accumulate=True)
+        else:
+            dbom = torch.empty(27, device=dev)
+            ops.colsum(dom, dbom)
+            colx = ops.im2col(x2, B, H, W, C, 3, 3, 1, 1)
+            dwom_x, dwom_i = _z(wom_x), _z(wom_i)
+            ops.gemm(dom, colx, dwom_x, transA=True, transB=False, accumulate=True)
+            ops.gemm(dom, col_i, dwom_i, transA=True, transB=False, accumulate=True)
+            ops.gemm(dom, wom_x, colx, transB=False)            # colx buffer becomes d(colx)
+            dxc = ops.col2im(colx, B, H, W, C, 3, 3, 1, 1).view(T, C)
+            if ctx.needs_input_grad[2]:
+                dcol_i = torch.empty_like(col_i)
+                ops.gemm(dom, wom_i, dcol_i, transB=False)
+            ops.add2d(dx, dxc, dx)
         return (dx.view(B, H * W, C), dit.view(B, H * W, -1), dcol_i, dwom_x, dwom_i, dbom, dwdcn, dwg0, dwg2, dwb0,
                 dwb2, None, None, None)
 
@@ -187,7 +221,9 @@ class DGRN(nn.Module):
         it = getattr(inter, '_fa_tokens', None)
         if it is None:
             it = NchwToTokensFn.apply(inter)
-        col_i = Im2colFn.apply(it, H, W)
+        # explicit path only: the patch matrix of the degradation map, shared by all 50 offset convolutions
+        implicit = ops.conv3x3_eligible(H, W, self.n_feats, 32) and ops.conv3x3_eligible(H, W, it.shape[-1], 32)
+        col_i = None if implicit else Im2colFn.apply(it, H, W)
         t = NchwToTokensFn.apply(x)
         h = conv_tokens(t, self.head[0], H, W)
         res = h

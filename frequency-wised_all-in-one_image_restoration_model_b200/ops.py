@@ -143,6 +143,47 @@ def gemm(A, B, C, transA=False, transB=True, bias=None, act=ACT_NONE, act_param=
     return C
 
 
+def conv3x3_eligible(H, W, Cin, Cout=8):
+    """Geometry the implicit-GEMM 3x3 convolution accepts (fa_conv3x3_gemm / fa_conv3x3_wgrad)."""
+    return (Cin % 32 == 0 and Cout >= 8 and Cout % 4 == 0 and (H * W) % 128 == 0 and W % 32 == 0
+            and (W % 128 == 0 or 128 % W == 0))
+
+
+def conv3x3_gemm(x, wk, y, B, H, W, bias=None, act=ACT_NONE, act_param=0.0, residual=None, aux=None, aux_act=ACT_NONE,
+                 aux_param=0.0, accumulate=False, backend=0):
+    """y[T, Cout] = epi(conv3x3_s1_p1(x [B,H*W,Cin]) with wk [Cout, 9*Cin]) without a patch matrix (implicit GEMM)."""
+    _f32(x, wk)
+    Cin, Cout = x.shape[-1], wk.shape[0]
+    _, _, ldy = _rows2d(y)
+    if FLOP_COUNTER[0] is not None:
+        FLOP_COUNTER[0] += 2 * B * H * W * Cout * 9 * Cin
+    e = FaGemmEpilogue()
+    e.bias = bias.data_ptr() if bias is not None else None
+    e.act, e.act_param, e.alpha = act, act_param, 1.0
+    e.rows_per_scale = 1
+    if residual is not None:
+        _, _, e.ldr = _rows2d(residual)
+        e.residual = residual.data_ptr()
+    if aux is not None:
+        _, _, e.ldaux = _rows2d(aux)
+        e.aux = aux.data_ptr()
+    e.aux_act, e.aux_param = aux_act, aux_param
+    e.accumulate = 1 if accumulate else 0
+    _call('fa_conv3x3_gemm', _p(x), _p(wk), _p(y), B, H, W, Cin, Cout, ldy, ctypes.byref(e), backend, _stream())
+    return y
+
+
+def conv3x3_wgrad(g, x, dwk, B, H, W, accumulate=True, dbias=None, backend=0):
+    """dwk[Cout, 9*Cin] (+)= g[T, Cout]^T . patches(x); dbias += column sums of g (implicit GEMM, no patch matrix)."""
+    _f32(x, dwk)
+    Cin = x.shape[-1]
+    _, Cout, ldg = _rows2d(g)
+    if FLOP_COUNTER[0] is not None:
+        FLOP_COUNTER[0] += 2 * B * H * W * Cout * 9 * Cin
+    _call('fa_conv3x3_wgrad', _p(g), ldg, _p(x), _p(dwk), B, H, W, Cin, Cout, int(accumulate), _p(dbias), backend, _stream())
+    return dwk
+
+
 def colsum(X, out, rowscale=None, rows_per_scale=1, accumulate=False):
     M, N, ld = _rows2d(X)
     _call('fa_colsum', _p(X), _p(out), M, N, ld, _p(rowscale), rows_per_scale, int(accumulate), _stream())
@@ -398,18 +439,19 @@ def nchw_to_tokens(x, B, HW, C):
 
 
 # ----------------------------------------------------------------------------- DGRN pieces
-def dcn_im2col(x, om, B, H, W, C):
+def dcn_im2col(x, om, B, H, W, C, col=None):
+    """om [T, 27 or 32] (row pitch = its width)."""
     _f32(x, om)
-    col = torch.empty(B * H * W, 9 * C, device=x.device, dtype=torch.float32)
-    _call('fa_dcn_im2col', _p(x), _p(om), _p(col), B, H, W, C, _stream())
+    col = torch.empty(B * H * W, 9 * C, device=x.device, dtype=torch.float32) if col is None else col
+    _call('fa_dcn_im2col', _p(x), _p(om), om.shape[-1], _p(col), B, H, W, C, _stream())
     return col
 
 
 def dcn_col2im(x, om, dcol, B, H, W, C):
     _f32(x, om, dcol)
     dx = torch.zeros_like(x)
-    dom = torch.empty_like(om)
-    _call('fa_dcn_col2im', _p(x), _p(om), _p(dcol), _p(dx), _p(dom), B, H, W, C, _stream())
+    dom = torch.empty_like(om) if om.shape[-1] == 27 else torch.zeros_like(om)     # pad columns of a 32-wide dom stay 0
+    _call('fa_dcn_col2im', _p(x), _p(om), om.shape[-1], _p(dcol), _p(dx), _p(dom), B, H, W, C, _stream())
     return dx, dom
 
 

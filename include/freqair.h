@@ -25,7 +25,7 @@ extern "C" {
 typedef void* fa_stream_t; /* cudaStream_t */
 
 /* ------------------------------------------------------------------ library */
-#define FREQAIR_ABI_VERSION 4      /* bumped whenever a prototype or struct in this header changes */
+#define FREQAIR_ABI_VERSION 6      /* bumped whenever a prototype or struct in this header changes */
 const char* fa_version(void);
 int fa_abi_version(void);          /* the FREQAIR_ABI_VERSION the library was compiled against (checked at load time) */
 const char* fa_last_error_string(void);
@@ -194,6 +194,20 @@ int fa_im2col(const float* x, float* col, int B, int H, int W, int C, int kh, in
               fa_stream_t stream);
 int fa_col2im(const float* col, float* dx, int B, int H, int W, int C, int kh, int kw, int stride, int pad,
               fa_stream_t stream);
+/* 3x3 s1 p1 convolution on NHWC tokens as an IMPLICIT GEMM: the patch matrix col[(b,y,x)][(ky,kx,ci)] is never written -
+ * the TMA producer of the tcgen05 contraction addresses x [B,H,W,Cin] through a 4-D tensor map and lets the
+ * out-of-bounds zero fill do the padding, so the layer reads x once instead of writing and re-reading 9x its size.
+ *   fa_conv3x3_gemm : y[T, Cout] (row pitch ldy) = epi(col . wk^T), wk = [Cout][(ky,kx,ci)], epilogue as fa_gemm.
+ *                     The data gradient is the same call on dY with the flipped, transposed weight
+ *                     wk'[ci][((2-ky),(2-kx),co)] = wk[co][(ky,kx,ci)].
+ *   fa_conv3x3_wgrad: dwk[Cout][(ky,kx,ci)] (+)= g[T, Cout]^T . col ; dbias (may be NULL) += column sums of g.
+ * Eligible: Cin % 32 == 0, (H*W) % 128 == 0, W a multiple or a divisor of 128 (wgrad: W % 32 == 0); anything else is an
+ * error (the caller keeps the explicit fa_im2col + fa_gemm path for those layers).  backend: 0 / 2 = 3xTF32, 4, 5.
+ * ref: Conv2d at decoder_DGRN.py:5-6 (58 layers of DGRN), encoder_ResNet.py:8-15. */
+int fa_conv3x3_gemm(const float* x, const float* wk, float* y, int B, int H, int W, int Cin, int Cout, int64_t ldy,
+                    const FaGemmEpilogue* epi, int backend, fa_stream_t stream);
+int fa_conv3x3_wgrad(const float* g, int64_t ldg, const float* x, float* dwk, int B, int H, int W, int Cin, int Cout,
+                     int accumulate, float* dbias, int backend, fa_stream_t stream);
 /* 3x3 s1 p1 conv from tokens [B,H*W,C] to a FEW output channels, written as an NCHW image [B,Co,H*W] with the bias and
  * an optional residual image added: OutputProj + the network's global skip (decoder_Uformer.py:476-499, :1171).
  * C % 4 == 0, C <= 128, Co <= 4.  wk = [Co][(ky,kx,ci)].  No patch matrix is built (it would be 9*C/Co times the output).
@@ -218,15 +232,17 @@ int fa_tokens_to_nchw(const float* t, const float* res, float* y, int B, int HW,
 int fa_nchw_to_tokens(const float* x, float* t, int B, int HW, int C, fa_stream_t stream);
 
 /* ------------------------------------------------------------------ DGRN (K7, K8)
- * DCNv2 3x3 s1 p1, groups 1, deformable_groups 1 on NHWC tokens.  om [B*H*W][27]: raw output of conv_offset_mask
+ * DCNv2 3x3 s1 p1, groups 1, deformable_groups 1 on NHWC tokens.  om [B*H*W][ldom >= 27]: raw output of conv_offset_mask
  * in the reference's channel order (deform_conv.py:59-62): o1 = ch 0..8, o2 = ch 9..17, mask = sigmoid(ch 18..26);
  * offset = cat(o1,o2) so tap k reads (dy,dx) = (om[2k], om[2k+1]) of the 18 offset channels.
  * fwd writes col [B*H*W][9*C] = mask_k * bilinear(x, p + p_k + offset_k) for the contraction with weight (fa_gemm).
- * bwd: from dcol -> dx (atomic scatter, caller zero-fills), dom [B*H*W][27].
+ * bwd: from dcol -> dx (atomic scatter, caller zero-fills), dom [B*H*W][ldom] (entries 0..26 of every row written).
+ * ldom = 32 lets the offset / mask convolution run as the implicit GEMM (fa_conv3x3_gemm wants Cout % 4 == 0) and its
+ * backward take dom as a 32-channel token tensor.
  * ref: DCN_layer.forward deform_conv.py:56-67 + mmcv modulated_deform_conv2d (absent; parity unpinned). */
-int fa_dcn_im2col(const float* x, const float* om, float* col, int B, int H, int W, int C, fa_stream_t stream);
-int fa_dcn_col2im(const float* x, const float* om, const float* dcol, float* dx, float* dom, int B, int H, int W, int C,
-                  fa_stream_t stream);
+int fa_dcn_im2col(const float* x, const float* om, int ldom, float* col, int B, int H, int W, int C, fa_stream_t stream);
+int fa_dcn_col2im(const float* x, const float* om, int ldom, const float* dcol, float* dx, float* dom, int B, int H, int W,
+                  int C, fa_stream_t stream);
 /* SFT + DGM tail (decoder_DGRN.py:22-32,49-57,79-81): out = act(x + dcn + x*gamma + beta) */
 int fa_sft_fuse_fwd(const float* x, const float* dcn, const float* gamma, const float* beta, float* out, int64_t n,
                     float slope, fa_stream_t stream);

@@ -643,3 +643,41 @@ def test_device_train_set_mirrors_reference_draws(ops):
             else:
                 assert not torch.equal(dv[i], cv[i]) and (dv[i] - cv[i]).abs().mean().item() < 0.15
         it[t] = (it[t] + 1) % len(order[t])
+
+
+@pytest.mark.parametrize('B,H,W,Ci,Co', [(2, 128, 128, 64, 64), (3, 32, 32, 32, 48), (1, 8, 256, 64, 24), (2, 16, 64, 96, 64)])
+def test_conv3x3_implicit_gemm(ops, B, H, W, Ci, Co):
+    """3x3 s1 p1 convolution on tokens as an implicit GEMM (4-D TMA patch operand, zero padding by out-of-bounds fill):
+    forward with bias + LeakyReLU, data gradient through the flipped / transposed weight, weight and bias gradients -
+    against fp64 torch conv2d autograd.  Geometries: one image row per M tile (W = 128), several rows per tile (W < 128),
+    a row segment per tile (W > 128)."""
+    assert ops.conv3x3_eligible(H, W, Ci, Co)
+    x = gen(B, H * W, Ci, scale=0.7)
+    w = gen(Co, Ci, 3, 3, seed=1, scale=0.1)
+    b = gen(Co, seed=2, scale=0.3)
+    g = gen(B * H * W, Co, seed=3)
+    xr = x.double().view(B, H, W, Ci).permute(0, 3, 1, 2).requires_grad_(True)
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    pre = F.conv2d(xr, wr, br, padding=1)
+    yr = F.leaky_relu(pre, 0.1)
+    yr.backward(g.double().view(B, H, W, Co).permute(0, 3, 1, 2))
+    wk = w.permute(0, 2, 3, 1).reshape(Co, 9 * Ci).contiguous()
+    xd, wkd = dev(x), dev(wk)
+    y = torch.empty(B * H * W, Co, device='cuda')
+    ops.conv3x3_gemm(xd, wkd, y, B, H, W, bias=dev(b), act=ops.ACT_LRELU, act_param=0.1)
+    ref = yr.permute(0, 2, 3, 1).reshape(B * H * W, Co)
+    close(y, ref, 2e-5, 'conv3x3 implicit fwd')
+    # gradient w.r.t. the pre-activation, then the two contractions of the backward
+    # (LeakyReLU mask from the fp64 pre-activation: a value within round-off of 0 may change sign between implementations)
+    mask = torch.where(pre.detach() > 0, 1.0, 0.1).permute(0, 2, 3, 1).reshape(B * H * W, Co).float()
+    gp = dev(g * mask)
+    dwk = torch.zeros(Co, 9 * Ci, device='cuda')
+    db = torch.zeros(Co, device='cuda')
+    ops.conv3x3_wgrad(gp, xd, dwk, B, H, W, accumulate=True, dbias=db)
+    close(dwk, wr.grad.permute(0, 2, 3, 1).reshape(Co, 9 * Ci), 5e-5, 'conv3x3 implicit dW')
+    close(db, br.grad, 5e-5, 'conv3x3 implicit db')
+    if Co % 32 == 0:
+        wflip = wk.view(Co, 9, Ci).flip(1).permute(2, 1, 0).reshape(Ci, 9 * Co).contiguous()
+        dx = torch.empty(B * H * W, Ci, device='cuda')
+        ops.conv3x3_gemm(gp.view(B, H * W, Co), dev(wflip), dx, B, H, W)
+        close(dx, xr.grad.permute(0, 2, 3, 1).reshape(B * H * W, Ci), 5e-5, 'conv3x3 implicit dX')

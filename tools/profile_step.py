@@ -22,15 +22,16 @@ def main():
     ap.add_argument('--batch', type=int, default=16)
     ap.add_argument('--top', type=int, default=60)
     ap.add_argument('--gemm', action='store_true')
+    ap.add_argument('--workload', default='train', choices=['train', 'vit_dgrn_train'])
     a = ap.parse_args()
     ops = importlib.import_module(PKG + '.ops')
     synth = importlib.import_module(PKG + '.synth')
     model = importlib.import_module(PKG + '.net.model')
     trainer = importlib.import_module(PKG + '.trainer')
     torch.manual_seed(0)
-    net = model.AirNet(bench.make_opt(a.batch)).cuda().train()
+    net = model.AirNet(bench.make_opt(a.batch, a.workload)).cuda().train()
     ts = trainer.TrainStep(net, lr=2e-4, contrast_loss_weight=0.6)
-    x = [t.cuda() for t in synth.noisy_batch(a.batch, 25)]
+    x = [t.cuda() for t in (synth.mixed_batch(a.batch) if a.workload == 'vit_dgrn_train' else synth.noisy_batch(a.batch, 25))]
     for _ in range(3):
         ts.step(*x)
     torch.cuda.synchronize()
