@@ -484,8 +484,10 @@ def test_joint_attn(ops, H, heads, shift, kind, L):
 
 
 # ----------------------------------------------------------------------------- DGRN pieces
-def test_dcn(ops):
-    B, H, W, C, Co = 2, 12, 10, 8, 6
+@pytest.mark.parametrize('B,H,W,C,Co,ldom', [(2, 12, 10, 8, 6, 27), (2, 9, 11, 64, 16, 27), (1, 16, 16, 64, 8, 32)])
+def test_dcn(ops, B, H, W, C, Co, ldom):
+    """DCNv2 gather / scatter kernels (generic and the pixel-per-warp C = 64 ones; om rows 27 or 32 wide) against the
+    oracle's dense restatement through autograd."""
     x = gen(B, C, H, W).requires_grad_(True)
     om = (gen(B, 27, H, W, seed=1) * 1.5).requires_grad_(True)
     w = gen(Co, C, 3, 3, seed=2).requires_grad_(True)
@@ -494,7 +496,10 @@ def test_dcn(ops):
     ref = airnet.modulated_deform_conv2d(x, torch.cat((o1, o2), 1), torch.sigmoid(m), w)
     ref.backward(dout)
     xt = dev(x.detach().flatten(2).transpose(1, 2))
-    omt = dev(om.detach().flatten(2).transpose(1, 2))
+    omt = om.detach().flatten(2).transpose(1, 2)
+    if ldom > 27:
+        omt = torch.cat([omt, torch.full((B, H * W, ldom - 27), 7.0)], -1)          # pad columns must be ignored
+    omt = dev(omt.reshape(B * H * W, ldom))
     col = ops.dcn_im2col(xt, omt, B, H, W, C)
     wk = dev(w.detach().permute(0, 2, 3, 1).reshape(Co, 9 * C))
     out = torch.empty(B * H * W, Co, device='cuda')
@@ -505,7 +510,7 @@ def test_dcn(ops):
     ops.gemm(dot, wk, dcol, transB=False, backend=1)
     dx, dom = ops.dcn_col2im(xt, omt, dcol, B, H, W, C)
     close(dx.transpose(1, 2).reshape(B, C, H, W), x.grad, 2e-4, 'dcn dx')
-    close(dom.transpose(1, 2).reshape(B, 27, H, W), om.grad, 2e-3, 'dcn dom')
+    close(dom[:, :27].reshape(B, H * W, 27).transpose(1, 2).reshape(B, 27, H, W), om.grad, 2e-3, 'dcn dom')
 
 
 def test_sft_fuse(ops):
