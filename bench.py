@@ -44,6 +44,8 @@ def make_opt(batch, workload='train'):
         o.encoder_type, o.decoder_type, o.encoder_dim, o.frequency_decompose_type = 'ViT', 'ResNet', 64, '4_bands'
     elif workload == 'resnet_dgrn_fwd':
         o.encoder_type, o.decoder_type, o.encoder_dim = 'ResNet', 'ResNet', 256
+    elif workload == 'uformer_dgrn':          # configs[3]: the pairing the package defines (net/decoder_DGRN.py adapter)
+        o.decoder_type = 'ResNet'
     return o
 
 
@@ -270,13 +272,15 @@ def run_inference(args):
     """Per-image latency of tiled inference (test.py:48-71 geometry): a HxW image -> ceil(H/128)*ceil(W/128) tiles ->
     ONE batched eval forward (query encoder trunk + decoder; the contrastive heads the reference computes and discards
     are skipped) -> overlap-averaged reassembly.  e2e includes the H2D copy of the image and the D2H of the result."""
-    size = 512 if args.workload == 'infer512' else 1024
+    size = 512 if '512' in args.workload else 1024
+    dgrn = args.workload.endswith('_dgrn')
+    pair = 'Uformer encoder + DGRN (documented adapter)' if dgrn else 'Uformer+Uformer all_3_bands'
     synth = importlib.import_module(PKG + '.synth')
     model = importlib.import_module(PKG + '.net.model')
     infer = importlib.import_module(PKG + '.infer')
     ops = importlib.import_module(PKG + '.ops')
     torch.manual_seed(0)
-    net = model.AirNet(make_opt(16)).cuda().eval()
+    net = model.AirNet(make_opt(16, 'uformer_dgrn' if dgrn else 'train')).cuda().eval()
     img = synth.gaussian_noise(synth.clean_images(1, size, size, seed=4321), 25, 4322).pin_memory()
     dimg = img.cuda()
     W, K = max(args.warmup, 3), max(args.steps, 1)
@@ -306,7 +310,7 @@ def run_inference(args):
     torch.cuda.synchronize()
     ms_e2e = f0.elapsed_time(f1) / K
     ntiles = (size // 128) ** 2
-    emit({'metric': f'{size}x{size} inference ms/img (Uformer+Uformer all_3_bands, {ntiles} tiles of 128x128)',
+    emit({'metric': f'{size}x{size} inference ms/img ({pair}, {ntiles} tiles of 128x128)',
                       'value': ms, 'unit': 'ms/img', 'n_gpus': 1, 'steps': K, 'warmup': W, 'ms_per_step': ms,
                       'higher_is_better': False, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                       'config': {'workload': f'tiled eval forward of one {size}x{size} sigma=25 image, random init', 'tiles': ntiles,
@@ -400,6 +404,52 @@ def run_dgrn_forward(args):
           'cpu_baseline': cpu_baseline})
 
 
+def check_grads(net, ts, synth, B, rank, world, dist):
+    """with the batch sharded over `world` ranks, the bucketed all-reduce must leave on every rank
+    the gradients one GPU computes for the concatenated batch.  Batch-coupled pieces are taken out so that the
+    comparison is exact up to summation order: the encoder runs in eval mode (BatchNorm running statistics, no MoCo
+    queue), DropPath is off, the loss is the L1 term (mean over the local samples; the mean over ranks is the 1/world
+    the optimiser applies).  Both passes go through the same hooks and NCCL buckets: pass 1 with each rank's own shard,
+    pass 2 with the full batch on every rank (its all-reduce sums `world` identical copies)."""
+    losses = importlib.import_module(PKG + '.losses')
+    net.E.eval()
+    net.R.train()
+    for m in net.modules():
+        if hasattr(m, 'drop_path_prob'):
+            m.drop_path_prob = 0.0
+    b = max(B // world, 1)
+    xq, _, clean = synth.noisy_batch(b * world, 25, seed=4242)           # the same global batch on every rank
+    xq, clean = xq.cuda(), clean.cuda()
+
+    def grads(x, c):
+        ts.zero_grad()
+        _, inter = net.E(x, x)
+        restored = net.R(x, inter)
+        losses.l1_loss(restored, c).backward()
+        if ts.ddp is not None:
+            ts.ddp.finish()
+        torch.cuda.synchronize()
+        return [s.grad.clone() / world for s in ts.segments]
+    sl = slice(rank * b, (rank + 1) * b)
+    g_ddp = grads(xq[sl].contiguous(), clean[sl].contiguous())
+    g_one = grads(xq, clean)
+    rep = {}
+    for name, a, r in zip(('encoder', 'decoder'), g_ddp, g_one):
+        scale = r.abs().max().item()
+        rep[name] = {'max_abs_err': (a - r).abs().max().item(), 'grad_max_abs': scale, 'n': a.numel(),
+                     'rel_l2': ((a - r).norm() / r.norm().clamp_min(1e-30)).item()}
+    ok = all(v['max_abs_err'] <= 1e-3 * max(v['grad_max_abs'], 1.0) for v in rep.values())
+    if dist is not None:
+        flag = torch.tensor([1.0 if ok else 0.0], device='cuda')
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = bool(flag.item() > 0.5)
+    if rank == 0:
+        emit({'check_grads': rep, 'n_gpus': world, 'global_batch': b * world, 'ok': ok, 'tolerance': '1e-3 max-abs',
+              'buckets': len(ts.ddp.buckets) if ts.ddp is not None else 0})
+    if not ok:
+        raise SystemExit(f'bench.py --check-grads: all-reduced gradients differ from the single-GPU gradients: {rep}')
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -412,13 +462,18 @@ def main():
                          'cuda:0 through stock torch kernels (informational: the stock-library bar on this GPU)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-roofline', action='store_true')
+    ap.add_argument('--check-grads', action='store_true',
+                    help='multi-GPU parity instead of timing (SURVEY section 8e): the all-reduced gradients of a batch '
+                         'sharded over the ranks against the gradients of the same batch on one GPU; prints one JSON line')
     ap.add_argument('--no-graph', action='store_true', help='launch the step kernel by kernel instead of replaying its CUDA graph')
     ap.add_argument('--workload', default='train',
-                    choices=['train', 'infer512', 'infer1024', 'vit_dgrn_train', 'resnet_dgrn_fwd'],
+                    choices=['train', 'infer512', 'infer1024', 'infer512_dgrn', 'infer1024_dgrn', 'vit_dgrn_train',
+                             'resnet_dgrn_fwd'],
                     help='train = the headline configs[1] step (default); vit_dgrn_train = configs[2] (ViT 4_bands + DGRN '
                          'train step on the mixed-degradation batch, batch-sharded over --gpus); resnet_dgrn_fwd = configs[0] '
-                         '(ResNet encoder + DGRN eval forward, batch 4); infer512 / infer1024 = configs[3]-style tiled '
-                         'full-resolution inference latency (Uformer encoder + Uformer decoder), ms per image, 1 GPU')
+                         '(ResNet encoder + DGRN eval forward, batch 4); infer512 / infer1024 = tiled full-resolution inference '
+                         'latency, ms per image, 1 GPU, Uformer encoder + Uformer decoder; infer512_dgrn / infer1024_dgrn = '
+                         'configs[3]: the same with the DGRN restorer (Uformer encoder + DGRN through the documented adapter)')
     args = ap.parse_args()
     claim_stdout()
     if os.environ.get('FREQAIR_WATCHDOG'):                 # debugging aid: dump every thread's stack and exit if stuck
@@ -436,7 +491,7 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device - the freqair path has no CPU fallback (use --impl reference for the CPU baseline)')
-    if args.workload in ('infer512', 'infer1024'):
+    if args.workload.startswith('infer'):
         run_inference(args)
         return
     if args.workload == 'resnet_dgrn_fwd':
@@ -472,6 +527,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.check_grads:
+        check_grads(net, ts, synth, B, rank, world, dist)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     for _ in range(W):
         ts.step(*dev_in)
     barrier()

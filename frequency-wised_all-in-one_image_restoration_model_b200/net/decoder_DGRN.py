@@ -193,6 +193,20 @@ class DGG(nn.Module):
         return conv_tokens(res, self.body[-1], H, W, residual=x)
 
 
+def uformer_inter_to_map(inter, n_feats, H, W):
+    """The adapter this package DEFINES for the Uformer-encoder + DGRN pairing (no counterpart in the reference, which
+    crashes on it): the L per-band bottleneck features [B, 64, 448] (an 8 x 8 token grid, 448 channels) become the
+    [B, n_feats, H, W] degradation map DGRN modulates with by (1) averaging the bands, (2) keeping the first n_feats
+    channels, (3) nearest-neighbour upsampling of the 8 x 8 grid to H x W.  No parameters, so DGRN's state_dict stays the
+    reference's; plain torch ops on 64 x 448 values per image (nothing here is on the hot path)."""
+    m = torch.stack(list(inter), 0).mean(0)                                   # [B, 64, 448]
+    B, N, C = m.shape
+    g = int(round(N ** 0.5))
+    assert g * g == N and C >= n_feats and H % g == 0 and W % g == 0
+    m = m[:, :, :n_feats].transpose(1, 2).reshape(B, n_feats, g, g)
+    return m.repeat_interleave(H // g, 2).repeat_interleave(W // g, 3).contiguous()
+
+
 class DGRN(nn.Module):
     def __init__(self, opt, conv=default_conv):
         super().__init__()
@@ -202,9 +216,13 @@ class DGRN(nn.Module):
             n_feats = opt.encoder_dim // 4
         elif opt.encoder_type == 'ViT':
             n_feats = opt.encoder_dim
-        else:
-            raise NotImplementedError('freqair: DGRN is defined for the ResNet and ViT encoders only (the reference '
-                                      'leaves n_feats undefined otherwise, decoder_DGRN.py:120-129)')
+        elif opt.encoder_type == 'Uformer':
+            # The reference leaves n_feats undefined for this pairing (decoder_DGRN.py:120-129 -> UnboundLocalError)
+            # and hands DGRN a tuple of L token tensors [B, 64, 448] instead of a [B, C, H, W] map: there is nothing to be
+            # faithful to.  BASELINE configs[3] names the pairing, so it is DEFINED here, parameter-free and documented
+            # (DESIGN.md section 0): n_feats = encoder_dim // 4 as for the ResNet encoder, and the degradation map is
+            # uformer_inter_to_map(inter) below.  The state_dict is that of the ResNet-encoder DGRN.
+            n_feats = opt.encoder_dim // 4
         if n_feats % 4:
             raise NotImplementedError(f'freqair: DGRN n_feats={n_feats} must be a multiple of 4 (128-bit NHWC gathers); '
                                       'use --encoder_dim 64 with the ViT encoder as the ViT runs of the reference authors do')
@@ -218,6 +236,8 @@ class DGRN(nn.Module):
 
     def forward(self, x, inter):
         B, _, H, W = x.shape
+        if isinstance(inter, (tuple, list)):               # Uformer encoder: L per-band token tensors [B, 64, 448]
+            inter = uformer_inter_to_map(inter, self.n_feats, H, W)
         it = getattr(inter, '_fa_tokens', None)
         if it is None:
             it = NchwToTokensFn.apply(inter)

@@ -77,10 +77,20 @@ def test_configurations_that_crash_at_reference_head_raise(kw):
         dec.UformerDecoder(make_opt(**kw))
 
 
-def test_dgrn_with_uformer_encoder_raises():
+def test_dgrn_with_uformer_encoder_uses_the_documented_adapter():
+    """BASELINE configs[3] pairs the Uformer encoder with DGRN; the reference crashes on it (decoder_DGRN.py:120-129).
+    The package defines the pairing: n_feats = encoder_dim // 4, state_dict of the ResNet-encoder DGRN, degradation map
+    = band mean -> first n_feats channels -> nearest upsampling of the 8 x 8 token grid (uformer_inter_to_map)."""
     dgrn = importlib.import_module(PKG_NAME + '.net.decoder_DGRN')
-    with pytest.raises(NotImplementedError):
-        dgrn.DGRN(make_opt(encoder_type='Uformer', decoder_type='ResNet'))
+    d = dgrn.DGRN(make_opt(encoder_type='Uformer', decoder_type='ResNet'))
+    ref = load_spec('spec_dgrn64.json')
+    assert {k: list(v.shape) for k, v in d.state_dict().items()} == {k: v[0] for k, v in ref.items()}
+    inter = tuple(torch.arange(2 * 64 * 448, dtype=torch.float32).view(2, 64, 448) * (i + 1) for i in range(3))
+    m = dgrn.uformer_inter_to_map(inter, 64, 128, 128)
+    assert m.shape == (2, 64, 128, 128)
+    mean = (inter[0] + inter[1] + inter[2]) / 3
+    assert torch.equal(m[1, 5, 17, 100], mean[1, (17 // 16) * 8 + 100 // 16, 5])
+    assert torch.equal(m[:, :, 0:16, 16:32], m[:, :, 0:1, 16:17].expand(-1, -1, 16, 16))
 
 
 def test_tile_origins_follow_test_py():

@@ -161,6 +161,48 @@ def test_tiled_inference_matches_per_tile_forward(airnet):
     assert maxerr(out2[0, :, 100, 100], (r[0, :, 100, 100] + r[1, :, 100, 28] + r[2, :, 28, 100] + r[3, :, 28, 28]) / 4) < 1e-5
 
 
+def test_tiled_inference_matches_oracle_tiled_path(airnet):
+    """The device-side tiler (infer.restore_tiled: all tiles in one batched eval forward, overlap-averaged) against the
+    oracle's restatement of test.py:43-71 with the CPU oracle network on a 200 x 264 image (2 x 3 overlapping tiles)."""
+    from oracle import airnet as oa, infer as oinfer
+    infer = importlib.import_module(PKG_NAME + '.infer')
+    detfill.fill_state(airnet.state_dict())
+    airnet.eval()
+    img = synth.gaussian_noise(synth.clean_images(1, 200, 264, seed=4325), 25, 4326)
+    out = infer.restore_tiled(airnet, img.cuda())
+    sd = detfill.make_state(load_spec('spec_airnet_uformer_uformer_L3.json'))
+    with torch.no_grad():
+        ref = oinfer.restore_tiled(lambda tiles: oa.airnet_uformer_forward(sd, tiles, tiles, training=False), img)
+    assert oinfer.tile_origins(200, 264) == ([0, 72], [0, 128, 136])
+    err = maxerr(out, ref)
+    print(f'tiled 200x264 restored err {err:.3e}')
+    assert err < 1e-3
+
+
+def test_evalset_psnr_ssim_parity(airnet):
+    """north_star: PSNR / SSIM within 0.01 dB / 1e-4 on the synthetic eval set - 32 images of 256 x 256, sigma = 25, tiled
+    as test.py does, against the per-image PSNR / SSIM of the UNMODIFIED reference network on the same images and weights
+    (tests/golden/evalset_uu.npz, tools/make_golden_eval.py); plus max-abs <= 1e-3 on the restored pixels."""
+    from oracle import metrics
+    infer = importlib.import_module(PKG_NAME + '.infer')
+    g = load_golden('evalset_uu.npz')
+    detfill.fill_state(airnet.state_dict())
+    airnet.eval()
+    n = g['psnr'].shape[0]
+    clean = synth.clean_images(n, 256, 256, seed=4321)
+    worst_p = worst_s = worst_e = 0.0
+    for i in range(n):
+        noisy = synth.gaussian_noise(clean[i:i + 1], 25, 4322 + i)
+        out = infer.restore_tiled(airnet, noisy.cuda()).cpu()[0]
+        worst_p = max(worst_p, abs(metrics.psnr(out, clean[i]) - float(g['psnr'][i])))
+        worst_s = max(worst_s, abs(metrics.ssim(out, clean[i]) - float(g['ssim'][i])))
+        worst_e = max(worst_e, maxerr(resample(out.flatten(), g['samp'].shape[1]), t(g['samp'][i])))
+        if i == 0:
+            worst_e = max(worst_e, maxerr(out, t(g['first'])))
+    print(f'eval set ({n} images): worst |dPSNR| {worst_p:.2e} dB, worst |dSSIM| {worst_s:.2e}, worst pixel err {worst_e:.3e}')
+    assert worst_p < 0.01 and worst_s < 1e-4 and worst_e < 1e-3
+
+
 def test_airnet_train_step(airnet):
     losses = importlib.import_module(PKG_NAME + '.losses')
     g = load_golden('airnet_uu_train.npz')
