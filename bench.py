@@ -299,7 +299,7 @@ def run_inference(args):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / K
-    launches = ops.launch_count()
+    launches = ops.launch_count() if args.no_graph else run.graph_launches * K     # a replay re-launches the recorded kernels
     out_host = torch.empty(1, 3, size, size).pin_memory()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()

@@ -52,9 +52,12 @@ class GraphedRestorer:
                 restore_tiled(net, self.static_in, patch)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        from . import ops
         self.graph = torch.cuda.CUDAGraph()
+        n0 = ops.launch_count()
         with torch.cuda.graph(self.graph):
             self.static_out = restore_tiled(net, self.static_in, patch)
+        self.graph_launches = ops.launch_count() - n0        # libfreqair kernels recorded in the graph (per replay)
 
     def __call__(self, img):
         self.static_in.copy_(img, non_blocking=True)
