@@ -438,7 +438,16 @@ def check_grads(net, ts, synth, B, rank, world, dist):
         scale = r.abs().max().item()
         rep[name] = {'max_abs_err': (a - r).abs().max().item(), 'grad_max_abs': scale, 'n': a.numel(),
                      'rel_l2': ((a - r).norm() / r.norm().clamp_min(1e-30)).item()}
-    ok = all(v['max_abs_err'] <= 1e-3 * max(v['grad_max_abs'], 1.0) for v in rep.values())
+    # worst parameters by name (diagnosis when the check fails)
+    worst = []
+    for seg, a, r in zip(ts.segments, g_ddp, g_one):
+        names = {id(p): n for n, p in net.named_parameters()}
+        for p_, o in zip(seg.params, seg.offs):
+            e = (a[o:o + p_.numel()] - r[o:o + p_.numel()]).abs().max().item()
+            worst.append((e, names.get(id(p_), '?'), o))
+    worst.sort(reverse=True)
+    rep['worst_parameters'] = [(f'{e:.3e}', n, o) for e, n, o in worst[:12]]
+    ok = all(v['max_abs_err'] <= 1e-3 * max(v['grad_max_abs'], 1.0) for k, v in rep.items() if k != 'worst_parameters')
     if dist is not None:
         flag = torch.tensor([1.0 if ok else 0.0], device='cuda')
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -74,6 +74,8 @@ class BucketedAllReduce:
         self.seen = set()
         self.pending = []
         self.handles = []
+        self.launched = []
+        self.late = []
         per = int(bucket_mb * (1 << 20) // 4)
         for seg in segments:
             n = seg.grad.numel()
@@ -92,7 +94,7 @@ class BucketedAllReduce:
             for i in range(nb):
                 self.buckets.append((seg.grad[bounds[i]:bounds[i + 1]], counts[i]))
             for p, bs in zip(seg.params, owners):
-                p.register_post_accumulate_grad_hook(self._make_hook(bs))
+                p.register_post_accumulate_grad_hook(self._make_hook(bs, id(p)))
                 self.bucket_of[id(p)] = bs
         self.reset()
 
@@ -108,10 +110,13 @@ class BucketedAllReduce:
             raise RuntimeError('BucketedAllReduce: a parameter was reported complete twice in one step (a weight shared '
                                'by several direct-gradient nodes is not supported under data parallelism)')
         self.seen.add(k)
-        self._dec(bs)
+        self._dec(bs)          # (the AccumulateGrad hook that follows for the same parameter is dropped, see _make_hook)
 
     def _dec(self, bs):
         for b in bs:
+            if self.launched[b]:
+                # a gradient reported complete AFTER its bucket was reduced: the bookkeeping counted something twice
+                self.late.append(b)
             self.pending[b] -= 1
             if self.pending[b] == 0:
                 self._launch(b)
@@ -121,9 +126,18 @@ class BucketedAllReduce:
         self.pending = [c for _, c in self.buckets]
         self.handles = []
         self.launched = [False] * len(self.buckets)
+        self.late = []
 
-    def _make_hook(self, bs):
+    def _make_hook(self, bs, key):
         def hook(_param):
+            # The engine runs AccumulateGrad - and with it this hook - for a parameter even when the block-level backward
+            # returned None for it (its gradient went straight into the flat buffer and was announced by param_ready).
+            # Hook and direct report therefore share one "seen" set: whichever comes first counts, the other is dropped.
+            # (Round 1 counted both; buckets reached zero early and were reduced before their last gradients landed -
+            # found by `bench.py --check-grads` on 2 GPUs.)
+            if key in self.seen:
+                return
+            self.seen.add(key)
             self._dec(bs)
         return hook
 
@@ -143,6 +157,10 @@ class BucketedAllReduce:
                                                      async_op=True))
 
     def finish(self):
+        if self.late:
+            late, self.late = self.late, []
+            raise RuntimeError(f'BucketedAllReduce: gradients were reported complete after their bucket had been reduced '
+                               f'(buckets {sorted(set(late))}): a parameter was counted twice')
         for b, (_, c) in enumerate(self.buckets):
             if not self.launched[b]:           # parameters that received no gradient this step
                 self._launch(b)

@@ -151,3 +151,53 @@ def test_folded_droppath_equals_materialised_scale():
         scale = b.abs().max().item()
         assert (a - b).abs().max().item() <= 2e-5 * scale + 1e-8
         assert a.abs().sum().item() > 0
+
+
+def test_distributed_bookkeeping_single_rank():
+    """The data-parallel step on a 1-rank NCCL group: every parameter must be reported complete exactly once per backward
+    (block-level nodes report their parameters directly, and the engine STILL runs AccumulateGrad - and its hook - for
+    them with an undefined gradient; round 1 counted both, so buckets were reduced before their last gradients landed).
+    BucketedAllReduce.finish() raises when a gradient is reported after its bucket was launched; with one rank the
+    reduced gradients must also equal the plain ones.  The 2-GPU equality is `bench.py --gpus 2 --check-grads`."""
+    import os
+    import socket
+    import torch.distributed as dist
+    trainer = importlib.import_module(PKG_NAME + '.trainer')
+    model = importlib.import_module(PKG_NAME + '.net.model')
+    synth = importlib.import_module(PKG_NAME + '.synth')
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('nccl', rank=0, world_size=1, device_id=torch.device('cuda', 0))
+    try:
+        torch.manual_seed(0)
+        net = model.AirNet(make_opt(2)).cuda().train()
+        for m in net.modules():
+            if hasattr(m, 'drop_path_prob'):
+                m.drop_path_prob = 0.0
+        sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+        x = [t.cuda() for t in synth.noisy_batch(2, 25)]
+        ts = trainer.TrainStep(net, lr=2e-4, contrast_loss_weight=0.6, distributed=True, bucket_mb=8)
+        assert len(ts.ddp.buckets) > 20
+        ts.zero_grad()
+        restored, logits, labels = net(*x[:2])
+        loss, _, _ = ts.loss(restored, logits, labels, x[2])
+        loss.backward()
+        n_early = sum(ts.ddp.launched)
+        ts.ddp.finish()                                   # raises on late / double reports
+        assert n_early > len(ts.ddp.buckets) // 2         # most buckets were reduced while backward was still running
+        g_ddp = [s.grad.clone() for s in ts.segments]
+        ts.ddp, ddp = None, ts.ddp                        # the same step without the all-reduce
+        for seg in ts.segments:
+            for p in seg.params:
+                p._fa_ready = None
+        net.load_state_dict(sd0)
+        ts.zero_grad()
+        restored, logits, labels = net(*x[:2])
+        loss, _, _ = ts.loss(restored, logits, labels, x[2])
+        loss.backward()
+        for a, s in zip(g_ddp, ts.segments):
+            assert (a - s.grad).abs().max().item() <= 2e-5 * s.grad.abs().max().item() + 1e-8
+    finally:
+        dist.destroy_process_group()
