@@ -584,7 +584,7 @@ def main():
     value = world * B * K / (ms * 1e-3)
     e2e = world * B * K / (ms_e2e * 1e-3)
 
-    roofline = None
+    roofline = roofline_hbm = None
     cpu_baseline = None
     if not args.no_roofline:
         # dominant kernel class = the dense contractions (fa_gemm): time every launch with in-stream events
@@ -600,18 +600,52 @@ def main():
         ops.FLOP_COUNTER[0] = None
         peak = measure_tf32_peak() if rank == 0 else 1.0
         ach = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        # DRAM bytes per launch of the same kernel class from the committed ncu pass over one step (tools/one_step.py
+        # under `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`; profiles/r2_step_traffic.json)
+        traffic, traffic_note = None, None
+        tpath = os.path.join(ROOT, 'profiles', 'r2_step_traffic.json')
+        if os.path.exists(tpath) and not vit:
+            tj = json.load(open(tpath))
+            traffic = tj.get('gemm', {}).get('dram_bytes_per_launch')
+            traffic_note = tj.get('note')
         roofline = {'bound': 'tensor', 'kernel': 'fa_gemm (all dense contractions of the step)', 'achieved': ach,
-                    'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak if peak else None, 'traffic': None,
+                    'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak if peak else None, 'traffic': traffic,
+                    'traffic_note': traffic_note,
                     'launches_per_step': gemm_n, 'avg_launch_ms': gemm_ms / max(gemm_n, 1),
                     'algorithmic_gflop_per_step': flops / 1e9, 'share_of_step': gemm_ms / (ms / K),
                     'share_basis': 'sum of the per-launch event times (kernel-by-kernel launch, every kernel alone on the '
-                                   'GPU) over the graph-replay step time; the ncu launch list in profiles/ gives 58 %',
+                                   'GPU) over the graph-replay step time; the ncu launch list in profiles/ gives the share '
+                                   'under serialised launches',
                     'peak_source': 'dense TF32 cuBLAS 8192^3 measured in this run (MEASURED_PEAKS.json holds bf16 only: '
                                    'the contractions run fp32/tf32, SURVEY.md section 8d)',
-                    'note': 'achieved counts ALGORITHMIC flops (2MNK); the product path issues 3 tf32 MMAs per product '
-                            '(error-compensated 3xTF32, needed for the 1e-3 parity bar), so the tensor pipe does 3x this '
-                            'work (compute-class shapes run 175-198 TFLOP/s algorithmic = 520-590 TFLOP/s of raw tf32 MMA, DESIGN.md section 3); '
-                            'K <= 224 layers at the 128^2 / 64^2 levels are HBM-bound (2.3-3.2 TB/s, tools/bench_kernels.py)'}
+                    'note': 'achieved counts ALGORITHMIC flops (2MNK) of ~1 000 launches of ~100 shapes; the restorer\'s LeFF '
+                            'contractions run 1xTF32, every other layer class 3xTF32 (3 MMAs per product, needed for the '
+                            '1e-3 parity bar: DESIGN.md section 3), and about half of the launches are HBM-class shapes '
+                            '(K <= 224 at the 128^2 / 64^2 levels; per-shape GB/s in profiles/r2_bench_kernels_gemm.txt)'}
+        # second roofline: the HBM-bound class (depthwise conv + LayerNorm), algorithmic bytes / event time
+        hbm_peak = None
+        ppath = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+        if os.path.exists(ppath):
+            hbm_peak = json.load(open(ppath)).get('hbm_gbs')
+        bw_ms = bw_n = 0
+        ops.BYTE_COUNTER[0] = 0
+        for cls in (ops.K_DWCONV, ops.K_LN):
+            ops.prof_begin(cls)
+            ts.step(*dev_in)
+            torch.cuda.synchronize()
+            m_, n_ = ops.prof_end()
+            bw_ms += m_
+            bw_n += n_
+        nbytes = ops.BYTE_COUNTER[0] / 2            # both classes were counted in both profiled steps
+        ops.BYTE_COUNTER[0] = None
+        roofline_hbm = {'bound': 'hbm', 'kernel': 'fa_dwconv3x3_fwd/bwd + fa_layernorm_fwd/bwd', 'achieved': nbytes / (bw_ms * 1e-3) / 1e9 if bw_ms else 0.0,
+                        'peak': hbm_peak if hbm_peak else 6650.0, 'unit': 'GB/s',
+                        'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if hbm_peak else '6.65 TB/s (of fallback)',
+                        'launches_per_step': bw_n, 'avg_launch_ms': bw_ms / max(bw_n, 1),
+                        'algorithmic_gb_per_step': nbytes / 1e9, 'share_of_step': bw_ms / (ms / K), 'traffic': None}
+        roofline_hbm['frac'] = roofline_hbm['achieved'] / roofline_hbm['peak']
+        if os.path.exists(tpath) and not vit:
+            roofline_hbm['traffic'] = json.load(open(tpath)).get('dwconv_ln', {}).get('dram_bytes_per_launch')
     if dist is not None:
         dist.barrier()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -635,7 +669,7 @@ def main():
                         'ms_per_step': ms_e2e / K, 'last_loss': last},
                 'gpu_launches': launches, 'gpu_launches_per_step': launches / K,
                 'step_tflop': (STEP_GFLOP_PER_CROP * B / 1e3) if not vit else None,
-                'roofline': roofline, 'cpu_baseline': cpu_baseline}
+                'roofline': roofline, 'roofline_hbm': roofline_hbm, 'cpu_baseline': cpu_baseline}
         emit(line)
     if dist is not None:
         dist.destroy_process_group()

@@ -464,7 +464,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
   const uint32_t ready_count = A_TMEM ? (ASPLIT_WARPS + (need_b ? BSPLIT_WARPS : 0)) * 32 : SPLIT_WARPS * 32;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], ready_count); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
+    // (32-wide N tiles: one 32-column chunk per tile, so the two epilogue warp groups take alternate TILES and each
+    // accumulator stage is drained by 4 warps)
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], (NCHUNK == 1 && g.k_chunk <= KC_BLOCKS * BK) ? EPI_WARPS / 2 : EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -778,12 +780,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     // epilogues that read nothing from global memory and write every element exactly once take the lean store path
     const bool store_only = (MODE == EPI_PLAIN && !epi.atomic && !epi.accumulate) ||
                             (MODE == EPI_FWD && !epi.residual && !epi.rowscale);
+    // ALT (BN = 32): a tile is one chunk; warp group `half` owns every second tile of this CTA (all accumulation units of
+    // it) instead of idling - the skinny contractions of the C = 28 level are paced by this epilogue
+    // (only when every tile is ONE accumulation unit, k <= 256: unit u then lives in TMEM stage u % 2 = the owning group,
+    // so each group sees every phase of its own tmem_full barrier; a group that skipped phases could not tell parity p
+    // of the next phase from parity p of the one before)
+    const bool ALT = NCHUNK == 1 && g.k_chunk <= KC_BLOCKS * BK;
     uint32_t lu = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    int tix = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tix) {
       const int sp = t % g.splits, rest = t / g.splits;
       const int m0 = (rest / g.tiles_n) * BM, n0 = (rest % g.tiles_n) * BN;
       const int kbeg = sp * g.k_chunk;
       const int nkb = (min(g.K, kbeg + g.k_chunk) - kbeg + BK - 1) / BK;
+      if (ALT && (tix & 1) != half) {             // the other group's tile: only keep the unit counter in step
+        lu += (uint32_t)((nkb + KC_BLOCKS - 1) / KC_BLOCKS);
+        continue;
+      }
+      const int cbase = ALT ? 0 : half;           // chunks cbase, cbase + 2
       float v[2][32];
       for (int kb0 = 0; kb0 < nkb; kb0 += KC_BLOCKS, ++lu) {
         const uint32_t as = lu & 1;
@@ -792,14 +806,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
         const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
-          if (half + 2 * ci < NCHUNK) {
+          if (cbase + 2 * ci < NCHUNK) {
             if (kb0 == 0) {
-              tc_ld32(taddr + (uint32_t)((half + 2 * ci) * 32), v[ci]);
+              tc_ld32(taddr + (uint32_t)((cbase + 2 * ci) * 32), v[ci]);
             } else {
 #pragma unroll
               for (int hh = 0; hh < 2; ++hh) {
                 float tmp[16];
-                tc_ld16(taddr + (uint32_t)((half + 2 * ci) * 32 + hh * 16), tmp);
+                tc_ld16(taddr + (uint32_t)((cbase + 2 * ci) * 32 + hh * 16), tmp);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[ci][hh * 16 + j] += tmp[j];
               }
@@ -813,7 +827,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
       const int row0 = m0 + q * 32;
 #pragma unroll
       for (int ci = 0; ci < 2; ++ci) {
-        const int c = half + 2 * ci;
+        const int c = cbase + 2 * ci;
         if (c < NCHUNK && n0 + c * 32 < g.N) {
           // transpose through smem: thread = row writes its 32 columns (8 x float4, conflict-free by the XOR swizzle)
 #pragma unroll

@@ -15,6 +15,8 @@ from ._lib import FaGemmEpilogue
 ACT_NONE, ACT_GELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
 ACT_MUL = 4                     # aux_act only: aux already holds the derivative, multiply by it
 FLOP_COUNTER = [None]          # bench.py roofline leg: set to 0 to accumulate 2*M*N*K of every fa_gemm call
+BYTE_COUNTER = [None]          # bench.py HBM roofline leg: set to 0 to accumulate the ALGORITHMIC bytes
+                               # of every depthwise-conv / LayerNorm launch
 # fa_gemm backend used when a call does not name one: 0 = auto (tcgen05 3xTF32 where eligible, else fp32 SIMT).
 # FREQAIR_GEMM_BACKEND=1 forces the fp32 SIMT kernel everywhere (A/B accuracy and speed comparisons).
 DEFAULT_GEMM_BACKEND = int(os.environ.get('FREQAIR_GEMM_BACKEND', '0'))
@@ -263,6 +265,8 @@ def layernorm_fwd(x, gamma, beta, y=None, want_stats=True):
     y = torch.empty_like(x) if y is None else y
     mean = torch.empty(rows, device=x.device, dtype=torch.float32) if want_stats else None
     rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if want_stats else None
+    if BYTE_COUNTER[0] is not None:
+        BYTE_COUNTER[0] += 8 * rows * C
     _call('fa_layernorm_fwd', _p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), rows, C, _stream())
     return y, mean, rstd
 
@@ -272,6 +276,8 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dgamma, dbeta, dx=None):
     C = x.shape[-1]
     rows = x.numel() // C
     dx = torch.empty_like(x) if dx is None else dx
+    if BYTE_COUNTER[0] is not None:            # read dy, x (+ dres), write dx
+        BYTE_COUNTER[0] += 4 * rows * C * (3 + (dres is not None))
     _call('fa_layernorm_bwd', _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dgamma), _p(dbeta),
           rows, C, _stream())
     return dx
@@ -347,6 +353,8 @@ def dwconv_fwd(h1, w, b, B, H, W, C, want_act=True, u2_mode=0):
     _f32(h1, w, b)
     u2 = torch.empty_like(h1) if u2_mode is not None else None
     h2 = torch.empty_like(h1) if want_act else None
+    if BYTE_COUNTER[0] is not None:            # read h1, write the one or two outputs
+        BYTE_COUNTER[0] += 4 * h1.numel() * (1 + (u2 is not None) + (h2 is not None))
     _call('fa_dwconv3x3_fwd', _p(h1), _p(w), _p(b), _p(u2), _p(h2), u2_mode or 0, B, H, W, C, _stream())
     return u2, h2
 
@@ -355,6 +363,8 @@ def dwconv_bwd(du2, h1, u1, w, dw, db, B, H, W, C):
     """h1=None: the kernel recomputes h1 = gelu(u1) for the weight gradient instead of reading it."""
     _f32(du2, h1, u1, w)
     du1 = torch.empty_like(du2)
+    if BYTE_COUNTER[0] is not None:            # read du2 (+ h1) (+ u1), write du1
+        BYTE_COUNTER[0] += 4 * du2.numel() * (2 + (h1 is not None) + (u1 is not None))
     _call('fa_dwconv3x3_bwd', _p(du2), _p(h1), _p(u1), _p(w), _p(du1), _p(dw), _p(db), B, H, W, C, _stream())
     return du1
 

@@ -174,9 +174,55 @@ def bench_attn():
             print(f'{f"joint_bwd kind{kind} B{B} {H}x{H} h{heads}":46s} {ms:8.3f} {3 * fl / ms / 1e9:8.1f} {28 * T * C / ms / 1e6:8.0f}', flush=True)
 
 
+def bench_dgrn():
+    """The DGRN-side kernels at configs[0] / configs[2] shapes (128 x 128, 64 channels) and the standalone band filter (K1),
+    BatchNorm (K9) and SFT (K8) kernels: algorithmic GB/s against the HBM roof; the implicit-GEMM convs also in TFLOP/s."""
+    from importlib import import_module
+    fd = import_module(PKG + '.net.utils.frequency_decompose')
+    print(f'{"kernel":52s} {"ms":>8s} {"GB/s":>8s} {"TFLOP/s":>8s}')
+
+    def rep(name, fn, byts, flops=0):
+        ms = timeit(fn)
+        print(f'{name:52s} {ms:8.3f} {byts / ms / 1e6:8.0f} {flops / ms / 1e9:8.1f}', flush=True)
+    for B in (4, 16):
+        H = W = 128; C = 64; T = B * H * W
+        x = torch.randn(T, C, device='cuda'); om = torch.randn(T, 32, device='cuda') * 0.5
+        col = torch.empty(T, 9 * C, device='cuda'); dcol = torch.randn(T, 9 * C, device='cuda')
+        rep(f'dcn_im2col B{B} 128x128 C64', lambda: ops.dcn_im2col(x, om, B, H, W, C, col), 4 * T * (C + 32 + 9 * C))
+        rep(f'dcn_col2im B{B} 128x128 C64', lambda: ops.dcn_col2im(x, om, dcol, B, H, W, C), 4 * T * (C + 32 + 9 * C + C + 32))
+        wk = torch.randn(C, 9 * C, device='cuda') * 0.05; y = torch.empty(T, C, device='cuda'); b = torch.randn(C, device='cuda')
+        fl = 2 * T * C * 9 * C
+        rep(f'conv3x3 implicit fwd B{B} 64->64 +bias+lrelu', lambda: ops.conv3x3_gemm(x.view(B, H * W, C), wk, y, B, H, W, bias=b, act=ops.ACT_LRELU, act_param=0.1), 8 * T * C, fl)
+        dwk = torch.zeros(C, 9 * C, device='cuda')
+        rep(f'conv3x3 implicit wgrad B{B} 64->64', lambda: ops.conv3x3_wgrad(y, x.view(B, H * W, C), dwk, B, H, W), 8 * T * C, fl)
+        colx = torch.empty(T, 9 * C, device='cuda')
+        rep(f'  (explicit: im2col + gemm B{B})', lambda: (ops.im2col(x.view(B, H * W, C), B, H, W, C, 3, 3, 1, 1), ops.gemm(colx, wk, y, bias=b)), 8 * T * C, fl)
+        g = torch.randn(T, C, device='cuda'); be = torch.randn(T, C, device='cuda'); d = torch.randn(T, C, device='cuda')
+        rep(f'sft_fuse_fwd B{B}', lambda: ops.sft_fuse_fwd(x, d, g, be, 0.1), 20 * T * C)
+        rep(f'sft_fuse_bwd B{B}', lambda: ops.sft_fuse_bwd(x, d, g, be, y, 0.1), 36 * T * C)
+        del x, om, col, dcol, colx
+    # K1 standalone: band split / filter of 64 x 64 attention maps and 128 x 128 images
+    for nmaps, n in ((74752 // 4, 64), (48, 128), (4096, 128)):
+        xm = torch.rand(nmaps, n, n, device='cuda')
+        bob = fd.half_band_map('frequency_decompose_1', 0.5, n).cuda()
+        coef = torch.randn(1, 3, device='cuda') * 0.3
+        rep(f'band_filter {nmaps} maps {n}x{n}', lambda: ops.band_filter(xm, bob, coef, nmaps, 1), 8 * nmaps * n * n)
+        rep(f'band_split (3 bands) {nmaps} maps {n}x{n}', lambda: ops.band_split(xm, bob, 3), 16 * nmaps * n * n)
+    # K9: BatchNorm statistics / apply on the encoder-head layout [B, 256, 128*128]
+    Bq, Cq, S = 16, 256, 16384
+    h = torch.randn(Bq, Cq, S, device='cuda'); sc = torch.rand(Cq, device='cuda'); sh = torch.randn(Cq, device='cuda')
+    rep('bn_stats [16,256,16384]', lambda: ops.bn_stats(h, Bq, Cq, S), 4 * h.numel())
+    rep('bn_apply (+lrelu+pool) [16,256,16384]', lambda: ops.bn_apply(h, sc, sh, 0.1, Bq, Cq, S), 4 * h.numel())
+    pm = torch.randn(99_715_312, device='cuda'); pk = torch.randn_like(pm)
+    rep('momentum_update 99.7M params', lambda: ops.momentum_update(pk, pm, 0.999), 12 * pm.numel())
+    gr = torch.randn_like(pm); m1 = torch.zeros_like(pm); v1 = torch.zeros_like(pm)
+    rep('adam_step 99.7M params', lambda: ops.adam_step(pm, gr, m1, v1, 2e-4, 0.9, 0.999, 1e-8, 3), 28 * pm.numel())
+    rep('round_tf32 99.7M params', lambda: ops.round_tf32(pm, pk), 8 * pm.numel())
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
-    ap.add_argument('what', choices=['gemm', 'epi', 'misc', 'attn'])
+    ap.add_argument('what', choices=['gemm', 'epi', 'misc', 'attn', 'dgrn'])
     ap.add_argument('--backend', type=int, default=0)
     ap.add_argument('--only', default=None)
     ap.add_argument('--layouts', default='NT,NN,TN')
@@ -190,3 +236,5 @@ if __name__ == '__main__':
         bench_misc()
     if a.what == 'attn':
         bench_attn()
+    if a.what == 'dgrn':
+        bench_dgrn()
