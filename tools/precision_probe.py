@@ -41,7 +41,7 @@ def tr(x):
 
 
 MODES = {'rn1': (rn, rn), 'aexact': (lambda x: x, rn), 'trunc1': (tr, tr), 'fp32': (lambda x: x, lambda x: x)}
-STATE = {'opA': None, 'opB': None, 'only': None, 'cls': None}
+STATE = {'opA': None, 'opB': None, 'only': None, 'cls': None, 'bwd_only': False, 'dw_only': False}
 
 
 def _ops():
@@ -57,6 +57,8 @@ class LinFn(torch.autograd.Function):
         ctx.ops = (opA, opB)
         ctx.save_for_backward(x, W)
         ctx.has_b = b is not None
+        if STATE['bwd_only'] or STATE['dw_only']:
+            return _linear(x, W, b)
         return _linear(opA(x), opB(W), b)
 
     @staticmethod
@@ -64,7 +66,7 @@ class LinFn(torch.autograd.Function):
         opA, opB = ctx.ops
         x, W = ctx.saved_tensors
         g2, x2 = g.reshape(-1, g.shape[-1]), x.reshape(-1, x.shape[-1])
-        dx = (opA(g2) @ opB(W)).view(x.shape)
+        dx = ((g2 @ W) if STATE['dw_only'] else (opA(g2) @ opB(W))).view(x.shape)
         dW = opA(g2).t() @ opB(x2)
         return dx, dW, (g2.sum(0) if ctx.has_b else None)
 
@@ -76,6 +78,8 @@ class ConvFn(torch.autograd.Function):
         ctx.ops, ctx.cfg = (opA, opB), (stride, padding)
         ctx.save_for_backward(x, W)
         ctx.has_b = b is not None
+        if STATE['bwd_only'] or STATE['dw_only']:
+            return _conv2d(x, W, b, stride=stride, padding=padding)
         return _conv2d(opA(x), opB(W), b, stride=stride, padding=padding)
 
     @staticmethod
@@ -83,7 +87,10 @@ class ConvFn(torch.autograd.Function):
         opA, opB = ctx.ops
         x, W = ctx.saved_tensors
         s, p = ctx.cfg
-        dx = torch.nn.grad.conv2d_input(x.shape, opB(W), opA(g), stride=s, padding=p)
+        if STATE['dw_only']:
+            dx = torch.nn.grad.conv2d_input(x.shape, W, g, stride=s, padding=p)
+        else:
+            dx = torch.nn.grad.conv2d_input(x.shape, opB(W), opA(g), stride=s, padding=p)
         dW = torch.nn.grad.conv2d_weight(opB(x), W.shape, opA(g), stride=s, padding=p)
         return dx, dW, (g.sum((0, 2, 3)) if ctx.has_b else None), None, None
 
@@ -95,13 +102,15 @@ class ConvTFn(torch.autograd.Function):
         opA, opB = _ops()
         ctx.ops = (opA, opB)
         ctx.save_for_backward(x, W)
+        if STATE['bwd_only'] or STATE['dw_only']:
+            return _convT(x, W, b, stride=2)
         return _convT(opA(x), opB(W), b, stride=2)
 
     @staticmethod
     def backward(ctx, g):
         opA, opB = ctx.ops
         x, W = ctx.saved_tensors
-        dx = _conv2d(opA(g), opB(W), stride=2)
+        dx = _conv2d(g, W, stride=2) if STATE['dw_only'] else _conv2d(opA(g), opB(W), stride=2)
         # dW[ci,co,ky,kx] = sum x[b,ci,y,x] g[b,co,2y+ky,2x+kx]
         B, Ci, H, Wd = x.shape
         gg = opA(g).view(B, -1, H, 2, Wd, 2)
@@ -197,9 +206,12 @@ def main():
     ap.add_argument('--modes', default='rn1,aexact,trunc1')
     ap.add_argument('--only', default=None, help='comma list of layer classes to treat (leff, attn, head, conv); default all')
     ap.add_argument('--json', default=None)
+    ap.add_argument('--bwd-only', action='store_true', help='forward contractions stay fp32; only dX and dW get the treatment')
+    ap.add_argument('--dw-only', action='store_true', help='only the weight-gradient contractions get the treatment')
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count() or 1)
     base = run('fp32', None)
+    STATE['bwd_only'], STATE['dw_only'] = a.bwd_only, a.dw_only
     only = set(a.only.split(',')) if a.only else None
     report = {}
     for mode in a.modes.split(','):
@@ -218,7 +230,7 @@ def main():
                'grad_maxabs': worst_abs, 'grad_worst_rel_to_own_scale': worst_rel, 'grad_worst_name': worst_name,
                'grads_over_1e-3_abs': n_over}
         report[mode] = rep
-        print(mode, 'only=' + str(a.only), json.dumps(rep))
+        print(mode, 'only=' + str(a.only), 'bwd_only' if a.bwd_only else ('dw_only' if a.dw_only else ''), json.dumps(rep))
     if a.json:
         with open(a.json, 'w') as f:
             json.dump({'only': a.only, 'report': report}, f, indent=1)
