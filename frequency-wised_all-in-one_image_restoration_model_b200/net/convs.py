@@ -34,7 +34,7 @@ class InputProjFn(torch.autograd.Function):
         dW = torch.zeros(ctx.wshape, device=g.device)
         db = torch.empty(ctx.wshape[0], device=g.device)
         ops.colsum(g, db)
-        ops.gemm(g, col, dW, transA=True, transB=False, accumulate=True)
+        ops.gemm(g, col, dW, transA=True, transB=False, accumulate=True, backend=ops.BWD_BACKEND)
         return None, dW, db, None          # the input image never needs a gradient on this path
 
 
@@ -56,7 +56,8 @@ class ConvTokFn(torch.autograd.Function):
     stems, 4x4 s2 downsampling) gather an explicit patch matrix (fa_im2col) first."""
 
     @staticmethod
-    def forward(ctx, x, wk, b, H, W, k, s, p, act, act_param, residual):
+    def forward(ctx, x, wk, b, H, W, k, s, p, act, act_param, residual, bwd_backend=0):
+        ctx.bwd_backend = bwd_backend          # fa_gemm backend of the backward contractions (Uformer path: ops.BWD_BACKEND)
         B, _, C = x.shape
         xc = x.contiguous()
         Co = wk.shape[0]
@@ -101,19 +102,19 @@ class ConvTokFn(torch.autograd.Function):
                     ops.gemm(g, wk, dcol, transB=False)
                     dx = ops.col2im(dcol, B, H, W, C, 3, 3, 1, 1)
                 dx = dx.view(B, H * W, C)
-            return dx, dW, db, None, None, None, None, None, None, None, dres
+            return dx, dW, db, None, None, None, None, None, None, None, dres, None
         one = (k == 1 and s == 1 and p == 0)
         col = xc.view(-1, C) if one else ops.im2col(xc, B, H, W, C, k, k, s, p)
         db = torch.empty(Co, device=g.device) if ctx.has_bias else None
         if db is not None:
             ops.colsum(g, db)
-        ops.gemm(g, col, dW, transA=True, transB=False, accumulate=True)
+        ops.gemm(g, col, dW, transA=True, transB=False, accumulate=True, backend=ctx.bwd_backend)
         dx = None
         if ctx.needs_input_grad[0]:
             dcol = torch.empty_like(col) if not one else torch.empty(col.shape, device=g.device)
-            ops.gemm(g, wk, dcol, transB=False)
+            ops.gemm(g, wk, dcol, transB=False, backend=ctx.bwd_backend)
             dx = dcol.view(B, H * W, C) if one else ops.col2im(dcol, B, H, W, C, k, k, s, p)
-        return dx, dW, db, None, None, None, None, None, None, None, dres
+        return dx, dW, db, None, None, None, None, None, None, None, dres, None
 
 
 def conv_tokens(x, conv, H, W, act=ops.ACT_NONE, act_param=0.0, residual=None):
@@ -246,9 +247,9 @@ class UpsampleCatFn(torch.autograd.Function):
         ops.copy2d(d2[:, Co:], dskip)
         dW, db4 = _z(wk), torch.empty(4 * Co, device=d2.device)
         ops.colsum(dg, db4)
-        ops.gemm(dg, x2, dW, transA=True, transB=False, accumulate=True)
+        ops.gemm(dg, x2, dW, transA=True, transB=False, accumulate=True, backend=ops.BWD_BACKEND)
         dx = torch.empty_like(x2)
-        ops.gemm(dg, wk, dx, transB=False)
+        ops.gemm(dg, wk, dx, transB=False, backend=ops.BWD_BACKEND)
         return dx.view(B, H * W, Ci), dW, db4, dskip.view(B, 4 * H * W, Cs), None, None
 
 

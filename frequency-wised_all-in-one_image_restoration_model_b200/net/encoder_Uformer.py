@@ -205,14 +205,16 @@ class UformerEncoder(nn.Module):
         """Contrastive head of band i (encoder_Uformer.py:975-984)."""
         ed, S = self.opt.encoder_dim, self.img_size * self.img_size
         ln, fc = self.mlp_head[i][0], self.mlp_head[i][1]
-        f = linear(layer_norm(xi, ln.weight, ln.bias), fc.weight, fc.bias)            # [B, 64, ed*256]
+        BB = ops.BWD_BACKEND
+        f = linear(layer_norm(xi, ln.weight, ln.bias), fc.weight, fc.bias, bwd_backend=BB)            # [B, 64, ed*256]
         bn = self.norm[i][0]
         if self.training:
             bn.num_batches_tracked += 1
         pooled, _ = BNHeadFn.apply(f.reshape(f.shape[0], ed, S), bn.weight, bn.bias, bn.running_mean, bn.running_var,
                                    self.training, 0.1, False)
         m = self.mlp[i]
-        return linear(linear(pooled, m[0].weight, m[0].bias, ops.ACT_LRELU, 0.1), m[2].weight, m[2].bias)
+        return linear(linear(pooled, m[0].weight, m[0].bias, ops.ACT_LRELU, 0.1, bwd_backend=BB), m[2].weight, m[2].bias,
+                      bwd_backend=BB)
 
     def forward(self, x, mask=None):
         assert mask is None

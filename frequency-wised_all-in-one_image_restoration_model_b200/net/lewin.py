@@ -161,6 +161,7 @@ def leff_bwd(gs, sv, xn2, w1, b1, wdw, bdw, w2, b2, B, H, W, dp=None, be=0):
     """gs: gradient wrt the LeFF output; dp: its per-sample DropPath scale when it is folded into the two contractions
     that consume gs (None: already applied). Returns dxn2 and the parameter gradients (None where they were
     accumulated straight into the parameters' .grad buffers)."""
+    be = ops.BWD_BACKEND if be == 0 else be        # backward contractions: ops.BWD_BACKEND unless the forward class is reduced already
     dW2, dW2r = _wbuf(w2)
     db2b, db2 = _wbuf(b2)
     ops.gemm(gs, sv['h2'], dW2, transA=True, transB=False, accumulate=True, a_rowsum=db2b, a_kscale=dp,
@@ -230,7 +231,7 @@ class DecoderBlockFn(torch.autograd.Function):
         g1 = ops.layernorm_bwd(dxn2, x1, mean2, rstd2, n2w, g, dn2w, dn2b)
         _ready(P_n2w, P_n2b)
         gs1, dpf = _fold(g1, dp_a, H * W)
-        do, dWp, dbp = linear_param_grads(gs1, o, P_wp, P_bp, dp=dpf, rps=H * W)
+        do, dWp, dbp = linear_param_grads(gs1, o, P_wp, P_bp, dp=dpf, rps=H * W, backend=ops.BWD_BACKEND)
         dq = torch.empty(T, C, device=g.device)
         dkv = torch.empty(T, 2 * C, device=g.device)
         dtable, dtabler = _wbuf(P_table)
@@ -239,8 +240,8 @@ class DecoderBlockFn(torch.autograd.Function):
         ops.win_attn_bwd(q_, kv_, do, dq, dkv, B, H, W, heads, hd, shift, hd ** -0.5, table, dtable, coef,
                          heads, dcoef, bob, nbands)
         _ready(P_table)
-        dxn, dWq, dbq = linear_param_grads(dq, xn, P_wq, P_bq)
-        _, dWkv, dbkv = linear_param_grads(dkv, xn, P_wkv, P_bkv, dx=dxn, accumulate_dx=True)
+        dxn, dWq, dbq = linear_param_grads(dq, xn, P_wq, P_bq, backend=ops.BWD_BACKEND)
+        _, dWkv, dbkv = linear_param_grads(dkv, xn, P_wkv, P_bkv, dx=dxn, accumulate_dx=True, backend=ops.BWD_BACKEND)
         dn1w, dn1wr = _wbuf(P_n1w)
         dn1b, dn1br = _wbuf(P_n1b)
         dx = ops.layernorm_bwd(dxn, x2d, mean1, rstd1, n1w, g1, dn1w, dn1b)
@@ -326,27 +327,27 @@ class EncoderBlockFn(torch.autograd.Function):
         dkv = torch.empty(T, 2 * C, device=dev)
         gB = [None] * 7
         if msa == 'origin':
-            doA, dWpA, dbpA = linear_param_grads(gs1, oA, P_wpA, P_bpA, dp=dpf, rps=H * W)
+            doA, dWpA, dbpA = linear_param_grads(gs1, oA, P_wpA, P_bpA, dp=dpf, rps=H * W, backend=ops.BWD_BACKEND)
             dtabA = _z(tabA)
             qA_, kvA_ = _QKV(buf=qkvA).views(T, C)
             ops.win_attn_bwd(qA_, kvA_, doA, dq, dkv, LB, H, W, heads, hd, shift, scale, tabA, dtabA, None,
                              heads, None, None, 0)
         else:
-            doB, dWpB, dbpB = linear_param_grads(gs1, oB, P_wpB, P_bpB, dp=dpf, rps=H * W)
+            doB, dWpB, dbpB = linear_param_grads(gs1, oB, P_wpB, P_bpB, dp=dpf, rps=H * W, backend=ops.BWD_BACKEND)
             dtabB = _z(tabB)
             qB_, kvB_ = _QKV(buf=qkvB).views(T, C)
             ops.joint_attn_bwd(qB_, kvB_, doB, dq, dkv, L, B, H, W, heads, hd, shift, scale, tabB, dtabB, 1)
-            dyA, dWqB, dbqB = linear_param_grads(dq, yA, P_wqB, P_bqB)
-            _, dWkvB, dbkvB = linear_param_grads(dkv, yA, P_wkvB, P_bkvB, dx=dyA, accumulate_dx=True)
+            dyA, dWqB, dbqB = linear_param_grads(dq, yA, P_wqB, P_bqB, backend=ops.BWD_BACKEND)
+            _, dWkvB, dbkvB = linear_param_grads(dkv, yA, P_wkvB, P_bkvB, dx=dyA, accumulate_dx=True, backend=ops.BWD_BACKEND)
             gB = [dtabB, dWqB, dbqB, dWkvB, dbkvB, dWpB, dbpB]
-            doA, dWpA, dbpA = linear_param_grads(dyA, oA, P_wpA, P_bpA)
+            doA, dWpA, dbpA = linear_param_grads(dyA, oA, P_wpA, P_bpA, backend=ops.BWD_BACKEND)
             dtabA = _z(tabA)
             dq = torch.empty(T, C, device=dev)
             dkv = torch.empty(T, 2 * C, device=dev)
             qA_, kvA_ = _QKV(buf=qkvA).views(T, C)
             ops.joint_attn_bwd(qA_, kvA_, doA, dq, dkv, L, B, H, W, heads, hd, shift, scale, tabA, dtabA, 0)
-        dxn, dWqA, dbqA = linear_param_grads(dq, xn, P_wqA, P_bqA)
-        _, dWkvA, dbkvA = linear_param_grads(dkv, xn, P_wkvA, P_bkvA, dx=dxn, accumulate_dx=True)
+        dxn, dWqA, dbqA = linear_param_grads(dq, xn, P_wqA, P_bqA, backend=ops.BWD_BACKEND)
+        _, dWkvA, dbkvA = linear_param_grads(dkv, xn, P_wkvA, P_bkvA, dx=dxn, accumulate_dx=True, backend=ops.BWD_BACKEND)
         dn1w, dn1wr = _wbuf(P_n1w)
         dn1b, dn1br = _wbuf(P_n1b)
         dx = ops.layernorm_bwd(dxn, x2d, mean1, rstd1, n1w, g1, dn1w, dn1b)
@@ -360,7 +361,8 @@ class LinearFn(torch.autograd.Function):
     """y = act(x W^T + b) (+ residual) on the last dim (nn.Linear + optional LeakyReLU/GELU epilogue)."""
 
     @staticmethod
-    def forward(ctx, x, W, b, act, act_param, residual):
+    def forward(ctx, x, W, b, act, act_param, residual, bwd_backend=0):
+        ctx.bwd_backend = bwd_backend
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
         y = torch.empty(x2.shape[0], W.shape[0], device=x.device, dtype=torch.float32)
         pre = torch.empty_like(y) if (act == ops.ACT_GELU or (act != ops.ACT_NONE and residual is not None)) else None
@@ -384,12 +386,13 @@ class LinearFn(torch.autograd.Function):
             # LeakyReLU: sign(out) == sign(pre-activation), so the saved output serves as aux
             g = ops.act_bwd(g, pre, act, ap)
         P_W, P_b = ctx.params
-        dx, dW, db = linear_param_grads(g, x2, P_W, P_b, want_dx=ctx.needs_input_grad[0])
-        return (dx.view(ctx.xshape) if dx is not None else None), dW, db, None, None, dres
+        dx, dW, db = linear_param_grads(g, x2, P_W, P_b, want_dx=ctx.needs_input_grad[0], backend=ctx.bwd_backend)
+        return (dx.view(ctx.xshape) if dx is not None else None), dW, db, None, None, dres, None
 
 
-def linear(x, W, b=None, act=ops.ACT_NONE, act_param=0.0, residual=None):
-    return LinearFn.apply(x, W, b, act, act_param, residual)
+def linear(x, W, b=None, act=ops.ACT_NONE, act_param=0.0, residual=None, bwd_backend=0):
+    """bwd_backend: fa_gemm backend of the two backward contractions (0 = 3xTF32; the Uformer heads pass ops.BWD_BACKEND)."""
+    return LinearFn.apply(x, W, b, act, act_param, residual, bwd_backend)
 
 
 class LayerNormFn(torch.autograd.Function):

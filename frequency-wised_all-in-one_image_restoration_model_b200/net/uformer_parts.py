@@ -54,7 +54,7 @@ class Downsample(nn.Module):
         H = W = int(math.sqrt(L))
         c = self.conv[0]
         return ConvTokFn.apply(x, conv_weight_matrix(c.weight), c.bias, H, W, self.k, self.s, self.p,
-                                  ops.ACT_NONE, 0.0, None)
+                                  ops.ACT_NONE, 0.0, None, ops.BWD_BACKEND)
 
 
 class Upsample(nn.Module):

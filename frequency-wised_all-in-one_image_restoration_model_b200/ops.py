@@ -28,7 +28,13 @@ GEMM_3X, GEMM_SIMT, GEMM_2X, GEMM_1X = 0, 1, 4, 5     # fa_gemm backend ids (inc
 # convolutions, encoder heads) exceeds or touches the bar under TF32 rounding and stays on the error-compensated 3xTF32
 # path, and so does the ENCODER's LeFF: its bottleneck tokens (`inter`) moved by 1.14e-3 under 1xTF32.
 # FREQAIR_LEFF_BACKEND / FREQAIR_LEFF_ENC_BACKEND select the fa_gemm backend of the two (0 = 3xTF32, 4 = 2x, 5 = 1x).
+# BACKWARD contractions (dX = dY.W and dW = dY^T.X) of the Uformer path - every layer class - also run 1xTF32: they do
+# not touch the forward activations at all, and on the golden train step rounding both operands of every backward
+# contraction moves no gradient by more than 1.1e-4 (tools/precision_probe.py --bwd-only; bar 1e-3).  The ViT / ResNet /
+# DGRN paths keep 3xTF32 in both directions (ill-conditioned 12-layer ViT, discontinuous DCN offset gradients).
+# FREQAIR_BWD_BACKEND=0 puts them back on 3xTF32.
 LEFF_BACKEND = int(os.environ.get('FREQAIR_LEFF_BACKEND', str(GEMM_1X)))
+BWD_BACKEND = int(os.environ.get('FREQAIR_BWD_BACKEND', str(GEMM_1X)))
 LEFF_ENC_BACKEND = int(os.environ.get('FREQAIR_LEFF_ENC_BACKEND', str(GEMM_3X)))
 K_GEMM, K_WIN_ATTN, K_JOINT_ATTN, K_BAND, K_LN, K_DWCONV, K_IM2COL, K_BN, K_OPTIM, K_DCN, K_ELEM = range(1, 12)
 
