@@ -539,7 +539,7 @@ def main():
     if args.check_grads:
         check_grads(net, ts, synth, B, rank, world, dist)
         if dist is not None:
-            dist.destroy_process_group()
+            shutdown(dist, ts)
         return
     for _ in range(W):
         ts.step(*dev_in)
@@ -672,7 +672,33 @@ def main():
                 'roofline': roofline, 'roofline_hbm': roofline_hbm, 'cpu_baseline': cpu_baseline}
         emit(line)
     if dist is not None:
+        shutdown(dist, ts)
+
+
+def shutdown(dist, ts=None):
+    """Leave a multi-rank run for certain.  A captured CUDA graph that contains NCCL kernels must be released before the
+    communicator is destroyed (with `--no-roofline` the graph used to stay alive and destroy_process_group never returned:
+    an 8-GPU run printed its line and then sat until the harness killed it).  The JSON line is out by now, so after a last
+    barrier every rank drops the graph, destroys the group under a watchdog and exits the interpreter without running
+    further destructors."""
+    if ts is not None:
+        ts.graph = None
+        ts.static_out = ts.static_in = None
+    torch.cuda.synchronize()
+    try:
+        dist.barrier()
+    except Exception:
+        pass
+    wd = threading.Timer(60.0, lambda: os._exit(0))            # if teardown hangs anyway: leave after 60 s (the line is out)
+    wd.daemon = True
+    wd.start()
+    try:
         dist.destroy_process_group()
+    except Exception:
+        pass
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == '__main__':
