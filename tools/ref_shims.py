@@ -1,6 +1,6 @@
 """Shims that let ``/root/reference/net`` import and run on a CPU-only box (build container only).
 
-Used by ``tools/make_golden.py`` and ``tests/test_oracle_vs_reference.py``; never on the GPU box
+Used by ``tools/make_golden*.py`` and ``tests/test_shim_host.py``; never on the GPU box
 (``/root/reference`` does not exist there) and never by the product.
 
 * ``timm.models.layers`` (absent): DropPath / to_2tuple / trunc_normal_ restated.  DropPath draws
