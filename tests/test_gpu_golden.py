@@ -203,6 +203,24 @@ def test_evalset_psnr_ssim_parity(airnet):
     assert worst_p < 0.01 and worst_s < 1e-4 and worst_e < 1e-3
 
 
+def test_airnet_eval_batch16_vs_oracle(airnet):
+    """The benched batch size: eval forward of 16 different crops (the golden vectors are batch 2) against the CPU oracle
+    on the same name-keyed weights - per-sample indexing of the band coefficients, window gathers and DropPath-free
+    residuals at B = 16."""
+    from oracle import airnet as oa
+    detfill.fill_state(airnet.state_dict())
+    airnet.eval()
+    xq, _, _ = synth.noisy_batch(16, 25, seed=777)
+    with torch.no_grad():
+        y = airnet(xq.cuda(), xq.cuda())
+    sd = detfill.make_state(load_spec('spec_airnet_uformer_uformer_L3.json'))
+    with torch.no_grad():
+        ref = oa.airnet_uformer_forward(sd, xq, xq, training=False)
+    err = maxerr(y, ref)
+    print(f'B=16 eval restored err vs oracle {err:.3e}')
+    assert err < 1e-3
+
+
 def test_airnet_train_step(airnet):
     losses = importlib.import_module(PKG_NAME + '.losses')
     g = load_golden('airnet_uu_train.npz')
