@@ -514,6 +514,10 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # The gradient all-reduce needs ~10 GB/s (1.09 GB per 110 ms step) and overlaps persistent one-CTA-per-SM
+        # contraction kernels: every SM NCCL holds costs those kernels a wave.  Measured at 2 GPUs (ms/step): NCCL default
+        # 113.2, 16 CTAs 111.6, 8 CTAs 113.4, 4 CTAs 114.8 (too few: the last bucket's tail shows) - 16 unless the user says otherwise.
+        os.environ.setdefault('NCCL_MAX_CTAS', '16')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     ops = importlib.import_module(PKG + '.ops')
     synth = importlib.import_module(PKG + '.synth')
