@@ -45,8 +45,11 @@ constexpr int EPI_WARPS = 8;
 constexpr int EPI_WARP0 = 2 + SPLIT_WARPS;     // first epilogue warp (TMEM lane quarter = warp % 4)
 constexpr int NTHREADS = 32 * (2 + SPLIT_WARPS + EPI_WARPS);
 constexpr int A_BYTES = BM * BK * 4;
-constexpr int TMEM_A_COL0 = 256;    // a_tmem: ring of {A, A_lo} k-blocks (2 x 32 columns per stage) behind the two accumulators
-constexpr int MAX_TMEM_A_STAGES = 4;
+// a_tmem: the ring of {A, A_lo} k-blocks (32 or 2 x 32 TMEM columns per stage) starts right behind the two accumulators,
+// at column 2 * BN, and takes the rest of the 512 columns: 4 stages for 3x / 2x on 128-wide tiles, 7 on 32-wide ones - the
+// huge-M, one-k-block-per-tile contractions of the 128 x 128 level are bound by the LATENCY of the load -> stage -> MMA ->
+// free loop (ncu: every role, the TMA warp included, waits ~half of the time with 4 stages in flight), so depth is speed
+constexpr int tmem_a_stages(int bn, int passes) { return (512 - 2 * bn) / (passes == 1 ? 32 : 64); }
 
 // epilogue flavours
 enum { EPI_PLAIN = 0,   // alpha, accumulate, split-K atomics                         (dX, dW)
@@ -277,6 +280,9 @@ struct TcGeom {
                  // nearest TF32), 1 = rn(A).rn(B), 0 = raw operands, truncated by the tensor core (measurement only)
   int a_tmem;    // passes >= 1: A (and A_lo) are staged in TMEM by the split warps (MMA reads only B from shared memory)
   int b_exact;   // passes 1 / 2: B is already TF32-representable (pre-rounded by its producer): the split warps skip it
+  int a_lin;     // a_tmem, A = [M, K] with lda == K <= 32 (one k-block per tile): the 128 x K tile is a CONTIGUOUS 512 K bytes,
+                 // fetched through a flat {32, M K / 32} view of A as 4 K full 128-byte rows instead of 128 rows of 4 K bytes that
+                 // straddle 128-byte lines (K = 28: 112 line requests per tile instead of ~240); lands unswizzled, row r at r * 4 K
   // Implicit 3x3 (stride 1, pad 1) patch operand over NHWC tokens x [cB, cH, cW, cC]: the patch matrix
   // col[(b,y,x)][(ky,kx,ci)] = x[b, y+ky-1, x+kx-1, ci] (0 outside the image) is never materialised - the producer
   // addresses x through a 4-D tensor map {C, W, H, B} and lets TMA's out-of-bounds zero fill do the padding.
@@ -438,6 +444,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
   constexpr int B_BYTES = BN * BK * 4;
   constexpr int TMEM_COLS = 2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : 256);
   constexpr int NCHUNK = BN / 32;
+  constexpr uint32_t TMEM_A_COL0 = 2 * BN;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int STAGES = g.stages;
@@ -497,12 +504,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[s], ph);
           if (elect_one()) {
-          mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+          mbar_expect_tx(&full[s], (g.a_lin ? BM * g.K * 4 : A_BYTES) + B_BYTES);
           const int k0 = kbeg + kb * BK;
           if (g.conv == 1) {
             const int hw = g.cH * g.cW, bi = m0 / hw, rem = m0 - bi * hw, y0 = rem / g.cW, x0 = rem - y0 * g.cW;
             const int tap = k0 / g.cC, c0 = k0 - tap * g.cC;
             tma_load_4d(sA + s * A_BYTES, &tmA, &full[s], c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, bi);
+          } else if (g.a_lin) {
+            tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], 0, (m0 >> 5) * g.K);
           } else if (!A_MN) {
             tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], k0, m0);
           } else {
@@ -663,7 +672,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
       uint32_t ph = 0;
       int s = 0;
       const uint32_t tbase = tmem_base + ((uint32_t)(q4 * 32) << 16) + TMEM_A_COL0;
-      const uint32_t abase = smem_u32(sA) + (A_MN ? (r >> 5) * 4096 + (r & 7) * 4 : r * 128);
+      const bool A_LIN = g.a_lin != 0;
+      const int kq = g.K >> 2;                  // a_lin: float4s per row (odd: the row stride is conflict-free)
+      const uint32_t abase = smem_u32(sA) + (A_LIN ? r * g.K * 4 : (A_MN ? (r >> 5) * 4096 + (r & 7) * 4 : r * 128));
       const int cm = (r & 31) >> 3;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int sp = t % g.splits;
@@ -673,7 +684,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
           mbar_wait(&full[s], ph);
           const uint32_t a0 = abase + s * A_BYTES;
           float av[32];
-          if (!A_MN) {
+          if (A_LIN) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 v = c < kq ? lds128(a0 + (c << 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              av[4 * c] = v.x; av[4 * c + 1] = v.y; av[4 * c + 2] = v.z; av[4 * c + 3] = v.w;
+            }
+          } else if (!A_MN) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               const float4 v = lds128(a0 + (((c ^ r) & 7) << 4));
@@ -922,7 +939,7 @@ EncodeTiledFn get_encode() {
 
 // row-major matrix [rows, cols] with row stride ld (floats); box = {box_cols (inner), box_rows}
 bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
-              bool mn_major) {
+              bool mn_major, bool flat = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -930,7 +947,8 @@ bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   flat ? CU_TENSOR_MAP_SWIZZLE_NONE : (mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -957,8 +975,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, float* C, TcGeom g, con
   const int budget = 227 * 1024 - 1024 - tail_bytes;
   int stages = budget / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  const int tmem_a_stages = g.passes == 1 ? 2 * MAX_TMEM_A_STAGES : MAX_TMEM_A_STAGES;    // 256 TMEM columns / {32, 64} per stage
-  if (g.a_tmem && stages > tmem_a_stages) stages = tmem_a_stages;
+  if (g.a_tmem && stages > tmem_a_stages(BN, g.passes)) stages = tmem_a_stages(BN, g.passes);
   g.stages = stages;
   const size_t smem = 1024 + (size_t)stages * stage_bytes + tail_bytes;
   auto kern = gemm_tc_kernel<BN, MODE>;
@@ -1078,13 +1095,17 @@ int fa_gemm_tc_launch(const float* A, const float* B, float* C, int M, int N, in
     while (bn > 32 && (bn == 96 || (int64_t)g.tiles_m * ((N + bn - 1) / bn) < kNumSMs)) bn = (bn == 96) ? 64 : bn >> 1;
   }
   g.tiles_n = (N + bn - 1) / bn;
+  static const bool alin_env = [] { const char* e = getenv("FREQAIR_GEMM_ALIN"); return !(e && e[0] == '0'); }();
+  g.a_lin = (alin_env && g.a_tmem && !a_mn && !conv && g.splits == 1 && K <= BK && K % 4 == 0 && ((K >> 2) & 1) && lda == K &&
+             ((int64_t)M * K) % 32 == 0) ? 1 : 0;
 
   CUtensorMap ta, tb;
   bool ok;
   if (g.conv == 1) {                  // 128 tokens = 128 / W whole image rows, or a 128-pixel segment of one row
     const int bw = conv->W >= 128 ? 128 : conv->W;
     ok = make_map_nhwc(&ta, A, conv->B, conv->H, conv->W, conv->C, bw, 128 / bw, false);
-  } else if (!a_mn) ok = make_map(&ta, A, M, K, lda, BK, BM, false);          // A [M,K]: box {32 k, 128 m}
+  } else if (g.a_lin) ok = make_map(&ta, A, (int64_t)M * K / 32, 32, 32, 32, 4 * K, false, true);   // flat view: box {32, 4 K}
+  else if (!a_mn) ok = make_map(&ta, A, M, K, lda, BK, BM, false);          // A [M,K]: box {32 k, 128 m}
   else ok = make_map(&ta, A, K, M, lda, 32, BK, true);                // A stored [K,M]: box {32 m, 32 k}
   if (!ok) { fa_set_error("fa_gemm(tcgen05): cuTensorMapEncodeTiled failed for A"); return FA_ERR_CUDA; }
   if (g.conv == 2) ok = make_map_nhwc(&tb, B, conv->B, conv->H, conv->W, conv->C, 32, 1, true);   // 32 tokens of one row

@@ -194,12 +194,14 @@ def test_gemm_a_kscale_and_bwd_rowscale(ops, backend):
                  a_k_rows_per_scale=rps, backend=1)
 
 
-@pytest.mark.parametrize('backend', [2, 3])
+@pytest.mark.parametrize('backend', [2, 3, 5])
 @pytest.mark.parametrize('tA,tB', [(False, True), (False, False), (True, False), (True, True)])
-@pytest.mark.parametrize('M,N,K', [(128 * 151 + 40, 256, 96), (128 * 150, 64, 1056), (128 * 3 + 4, 128 * 60, 72)])
+@pytest.mark.parametrize('M,N,K', [(128 * 151 + 40, 256, 96), (128 * 150, 64, 1056), (128 * 3 + 4, 128 * 60, 72),
+                                   (128 * 1200 + 8, 28, 28), (128 * 700, 56, 56), (128 * 500 + 4, 96, 28)])
 def test_gemm_tc_many_tiles(ops, M, N, K, tA, tB, backend):
     """Shapes with several waves of tiles per SM (persistent loop, ring and accumulator phases wrapping many times), odd
-    tile counts, ragged M, both B layouts, split-K; exact on TF32-representable data."""
+    tile counts, ragged M, both B layouts, split-K; exact on TF32-representable data.  The last three are the one-k-block
+    tiles of the 128 x 128 level, where the A ring in TMEM is 7 / 6 / 5 stages deep (32- / 64- / 96-wide tiles)."""
     A = quant(gen(K, M) if tA else gen(M, K))
     B = quant(gen(N, K, seed=1) if tB else gen(K, N, seed=1))
     C = torch.full((M, N), float('nan'), device='cuda')
