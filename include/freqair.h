@@ -53,7 +53,8 @@ enum { FA_ACT_NONE = 0, FA_ACT_GELU = 1, FA_ACT_LRELU = 2, FA_ACT_SIGMOID = 3 };
  *          4 = tcgen05 2xTF32: op(A) exact (hi + lo split), op(B) rounded to the nearest TF32 inside the kernel
  *          (relative operand error <= 2^-12, unbiased), 5 = tcgen05 1xTF32 with BOTH operands rounded to nearest.
  *          4 and 5 fall back to the SIMT kernel for ineligible shapes like 0 does.  Which layer classes may use them is
- *          a parity decision made by the caller (the LeFF contractions; everything else stays 3x). */
+ *          a parity decision made by the caller (the restorer's LeFF forward and the backward
+ *          contractions of the Uformer path run 5; every other forward contraction stays 3x). */
 typedef struct FaGemmEpilogue {
   const float* bias;
   int act; float act_param;
