@@ -280,6 +280,10 @@ struct TcGeom {
                  // nearest TF32), 1 = rn(A).rn(B), 0 = raw operands, truncated by the tensor core (measurement only)
   int a_tmem;    // passes >= 1: A (and A_lo) are staged in TMEM by the split warps (MMA reads only B from shared memory)
   int b_exact;   // passes 1 / 2: B is already TF32-representable (pre-rounded by its producer): the split warps skip it
+  int it_stride, it_dsp, it_dtn, it_dtm;     // grid size and its (split, n tile, m tile) decomposition: TileIt::next
+  int b_res;     // a_tmem, one n tile, one k-block, no split: every work unit uses the SAME B tile - it is fetched (and split /
+                 // rounded) once per ring slot instead of once per unit (148 CTAs re-reading one 3 KB tile made an L2 hot spot:
+                 // 20 of the 61 us of 786432 x 28 x 28)
   int a_lin;     // a_tmem, A = [M, K] with lda == K <= 32 (one k-block per tile): the 128 x K tile is a CONTIGUOUS 512 K bytes,
                  // fetched through a flat {32, M K / 32} view of A as 4 K full 128-byte rows instead of 128 rows of 4 K bytes that
                  // straddle 128-byte lines (K = 28: 112 line requests per tile instead of ~240); lands unswizzled, row r at r * 4 K
@@ -437,6 +441,25 @@ __device__ __forceinline__ void epi_chunk_store(uint32_t stg_s, float alpha, flo
   }
 }
 
+// Work units of a persistent CTA: t = blockIdx.x, + gridDim.x, ...; unit t = ((m tile * tiles_n) + n tile) * splits + split.
+// Every warp role walks the same sequence; the decomposition is carried incrementally (three adds with carry, the stride's
+// own decomposition comes from the host in TcGeom) because two integer divisions per unit and role were a visible part
+// of the per-tile hand-off time on the one-k-block shapes.
+struct TileIt {
+  int t, sp, tn, tm;
+  __device__ __forceinline__ TileIt(int t0, const TcGeom& g) {
+    t = t0; sp = t0 % g.splits;
+    const int r = t0 / g.splits;
+    tn = r % g.tiles_n; tm = r / g.tiles_n;
+  }
+  __device__ __forceinline__ void next(const TcGeom& g) {
+    t += g.it_stride;
+    sp += g.it_dsp; int c = sp >= g.splits ? 1 : 0; sp -= c ? g.splits : 0;
+    tn += g.it_dtn + c; c = tn >= g.tiles_n ? 1 : 0; tn -= c ? g.tiles_n : 0;
+    tm += g.it_dtm + c;
+  }
+};
+
 template <int BN, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
@@ -496,15 +519,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
       // (whole warp walks the loop, an elected lane issues: coordinates and addresses stay in uniform registers)
       uint32_t ph = 1;               // parity to wait for on empty[s]: flips every time the ring wraps (no division per k-block)
       int s = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int sp = t % g.splits, rest = t / g.splits;
-        const int m0 = (rest / g.tiles_n) * BM, n0 = (rest % g.tiles_n) * BN;
-        const int kbeg = sp * g.k_chunk;
+      int filled = 0;                // b_res: ring slots whose (single, shared) B tile has been fetched
+      for (TileIt it(blockIdx.x, g); it.t < total_tiles; it.next(g)) {
+        const int m0 = it.tm * BM, n0 = it.tn * BN;
+        const int kbeg = it.sp * g.k_chunk;
         const int nkb = (min(g.K, kbeg + g.k_chunk) - kbeg + BK - 1) / BK;
         for (int kb = 0; kb < nkb; ++kb) {
+          const bool load_b = !g.b_res || filled < STAGES;
+          filled += (filled < STAGES) ? 1 : 0;
           mbar_wait(&empty[s], ph);
           if (elect_one()) {
-          mbar_expect_tx(&full[s], (g.a_lin ? BM * g.K * 4 : A_BYTES) + B_BYTES);
+          mbar_expect_tx(&full[s], (g.a_lin ? BM * g.K * 4 : A_BYTES) + (load_b ? B_BYTES : 0));
           const int k0 = kbeg + kb * BK;
           if (g.conv == 1) {
             const int hw = g.cH * g.cW, bi = m0 / hw, rem = m0 - bi * hw, y0 = rem / g.cW, x0 = rem - y0 * g.cW;
@@ -518,7 +543,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
             for (int j = 0; j < BM / 32; ++j) tma_load_2d(sA + s * A_BYTES + j * 4096, &tmA, &full[s], m0 + 32 * j, k0);
           }
-          if (g.conv == 2) {
+          if (!load_b) {
+          } else if (g.conv == 2) {
             const int hw = g.cH * g.cW, bi = k0 / hw, rem = k0 - bi * hw, y0 = rem / g.cW, x0 = rem - y0 * g.cW;
 #pragma unroll
             for (int j = 0; j < BN / 32; ++j) {
@@ -549,9 +575,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
       const uint32_t astep = A_MN ? 1024u : 32u, bstep = B_MN ? 1024u : 32u;
       uint32_t ph = 0, lu = 0;           // lu = accumulation units issued (a unit = up to KC_BLOCKS k-blocks of one tile)
       int s = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int sp = t % g.splits;
-        const int kbeg = sp * g.k_chunk;
+      for (TileIt it(blockIdx.x, g); it.t < total_tiles; it.next(g)) {
+        const int kbeg = it.sp * g.k_chunk;
         const int nkb = (min(g.K, kbeg + g.k_chunk) - kbeg + BK - 1) / BK;
         for (int kb0 = 0; kb0 < nkb; kb0 += KC_BLOCKS, ++lu) {
           const uint32_t as = lu & 1;
@@ -676,9 +701,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
       const int kq = g.K >> 2;                  // a_lin: float4s per row (odd: the row stride is conflict-free)
       const uint32_t abase = smem_u32(sA) + (A_LIN ? r * g.K * 4 : (A_MN ? (r >> 5) * 4096 + (r & 7) * 4 : r * 128));
       const int cm = (r & 31) >> 3;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int sp = t % g.splits;
-        const int kbeg = sp * g.k_chunk;
+      for (TileIt it(blockIdx.x, g); it.t < total_tiles; it.next(g)) {
+        const int kbeg = it.sp * g.k_chunk;
         const int nkb = (min(g.K, kbeg + g.k_chunk) - kbeg + BK - 1) / BK;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full[s], ph);
@@ -726,9 +750,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         if (has_rs) {
-          const int rest = t / g.splits;
-          const int row = (rest / g.tiles_n) * BM + r;
-          if (rest % g.tiles_n == 0 && row < g.M) atomicAdd(epi.a_rowsum + row, rsum);     // each A tile counted once
+          const int row = it.tm * BM + r;
+          if (it.tn == 0 && row < g.M) atomicAdd(epi.a_rowsum + row, rsum);     // each A tile counted once
           rsum = 0.f;
         }
       }
@@ -740,12 +763,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
         constexpr int NB = B_BYTES / 16 / (BSPLIT_WARPS * 32);
         uint32_t ph = 0;
         int s = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-          const int sp = t % g.splits;
-          const int kbeg = sp * g.k_chunk;
+        int filled = 0;              // b_res: ring slots whose B tile is already split / rounded (done once per slot)
+        for (TileIt it(blockIdx.x, g); it.t < total_tiles; it.next(g)) {
+          const int kbeg = it.sp * g.k_chunk;
           const int nkb = (min(g.K, kbeg + g.k_chunk) - kbeg + BK - 1) / BK;
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&full[s], ph);
+            if (g.b_res && filled >= STAGES) {               // resident B: nothing to do but publish the stage
+              mbar_arrive(&ready[s]);
+              if (++s == STAGES) { s = 0; ph ^= 1; }
+              continue;
+            }
+            ++filled;
             const uint32_t b = smem_u32(sB + s * B_BYTES) + st * 16, bl = smem_u32(sBlo + s * B_BYTES) + st * 16;
             float4 rb[NB];
 #pragma unroll
@@ -770,9 +799,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
       const int st = threadIdx.x - 64;        // 0..SPLIT_WARPS*32-1
       uint32_t ph = 0;
       int s = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int sp = t % g.splits;
-        const int kbeg = sp * g.k_chunk;
+      for (TileIt it(blockIdx.x, g); it.t < total_tiles; it.next(g)) {
+        const int kbeg = it.sp * g.k_chunk;
         const int nkb = (min(g.K, kbeg + g.k_chunk) - kbeg + BK - 1) / BK;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full[s], ph);
@@ -805,10 +833,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     const bool ALT = NCHUNK == 1 && g.k_chunk <= KC_BLOCKS * BK;
     uint32_t lu = 0;
     int tix = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tix) {
-      const int sp = t % g.splits, rest = t / g.splits;
-      const int m0 = (rest / g.tiles_n) * BM, n0 = (rest % g.tiles_n) * BN;
-      const int kbeg = sp * g.k_chunk;
+    for (TileIt it(blockIdx.x, g); it.t < total_tiles; it.next(g), ++tix) {
+      const int m0 = it.tm * BM, n0 = it.tn * BN;
+      const int kbeg = it.sp * g.k_chunk;
       const int nkb = (min(g.K, kbeg + g.k_chunk) - kbeg + BK - 1) / BK;
       if (ALT && (tix & 1) != half) {             // the other group's tile: only keep the unit counter in step
         lu += (uint32_t)((nkb + KC_BLOCKS - 1) / KC_BLOCKS);
@@ -982,6 +1009,8 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, float* C, TcGeom g, con
   FA_SMEM_ATTR_ONCE(227 * 1024, kern);
   const int64_t total = (int64_t)g.tiles_m * g.tiles_n * g.splits;
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
+  g.it_stride = grid; g.it_dsp = grid % g.splits;
+  g.it_dtn = (grid / g.splits) % g.tiles_n; g.it_dtm = (grid / g.splits) / g.tiles_n;
   kern<<<grid, NTHREADS, smem, st>>>(ta, tb, C, g, e);
   FA_LAUNCH_CHECK("fa_gemm(tcgen05)");
   return FA_OK;
@@ -1098,6 +1127,8 @@ int fa_gemm_tc_launch(const float* A, const float* B, float* C, int M, int N, in
   static const bool alin_env = [] { const char* e = getenv("FREQAIR_GEMM_ALIN"); return !(e && e[0] == '0'); }();
   g.a_lin = (alin_env && g.a_tmem && !a_mn && !conv && g.splits == 1 && K <= BK && K % 4 == 0 && ((K >> 2) & 1) && lda == K &&
              ((int64_t)M * K) % 32 == 0) ? 1 : 0;
+
+  g.b_res = (alin_env && g.a_tmem && !conv && g.splits == 1 && g.tiles_n == 1 && K <= BK) ? 1 : 0;
 
   CUtensorMap ta, tb;
   bool ok;
